@@ -1,0 +1,136 @@
+/* jurassic_b200.h -- C ABI of the B200-native EGA forward model (core library libjurassic_b200.so).
+ *
+ * Plain C: pointers, sizes and strides only; no CUDA or torch types.  The core library is independent of the
+ * reference's compile-time dimensions (ND, NG, ...): callers describe their ctl_t / atm_t / obs_t / tbl_t through
+ * the "views" below (base pointers + strides into the caller's structs, nothing is copied on the host side).
+ * The reference-facing entry points (formod_GPU and the batched extension, taking the reference's own structs)
+ * live in the thin per-(ND,NG) layer declared in jurassic_b200_dropin.h.
+ *
+ * Reference interface each piece replaces (paths below /root/reference):
+ *   jrb_ctl_view        <- the ctl_t fields the path reads            src/jurassic.h:229-347
+ *   jrb_atm_view        <- atm_t                                      src/jurassic.h:215-226
+ *   jrb_obs_view        <- obs_t                                      src/jurassic.h:371-385
+ *   jrb_tbl_view        <- tbl_t                                      src/jurassic.h:390-425
+ *   jrb_set_tables      <- get_tbl_on_GPU                             src/GPUdrivers.cu:78-93
+ *   jrb_formod_batch    <- formod_GPU / formod_one_package            src/GPUdrivers.cu:187-250, 262-360
+ *                          (same work as formod_CPU, src/CPUdrivers.c:108-151, for npk packages at once)
+ *   jrb_stage / jrb_run_staged / jrb_fetch_staged : the three phases of jrb_formod_batch, separately callable so
+ *                          that the device path can be timed with inputs resident in HBM.
+ *
+ * All functions return 0 on success, a negative code on failure; jrb_last_error() gives the message.
+ * There is NO CPU fallback: without a usable CUDA device every compute entry point fails.
+ */
+#ifndef JURASSIC_B200_H
+#define JURASSIC_B200_H
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define JRB_OK 0
+#define JRB_ERR_ARG (-1)
+#define JRB_ERR_CUDA (-2)
+#define JRB_ERR_STATE (-3)
+#define JRB_ERR_LIMIT (-4)
+
+#define JRB_NLOS 400   /* max. LOS points per ray  (NLOS,  src/jurassic.h:169) */
+#define JRB_TBLNS 1201 /* source-function temperatures (TBLNS, src/jurassic.h:187) */
+#define JRB_MAX_NG 64  /* limits of the packed formats */
+#define JRB_MAX_NW 8
+
+/* Control parameters read by the path (values AFTER read_ctl's automatic CTM_* switch-off, src/jurassic.c:954-968). */
+typedef struct {
+  int ng, nd, nw;
+  const double *nu;  /* [nd] channel centroid wavenumbers [cm^-1] */
+  const int *window; /* [nd] extinction window per channel */
+  int ctm_co2, ctm_h2o, ctm_n2, ctm_o2;
+  int ig_co2, ig_h2o; /* find_emitter(ctl,"CO2"/"H2O"), -1 if absent (src/jurassic.c:198-207) */
+  int refrac;
+  double rayds, raydz;
+  double hydz; /* < 0: no hydrostatic adjustment */
+  int write_bbt;
+  int formod; /* must be 2 (EGA) */
+  int ip;     /* must be 1 (1-D profile interpolation) */
+} jrb_ctl_view;
+
+typedef struct {
+  int np;
+  double *time, *z, *lon, *lat, *p, *t; /* [np]; p is written when hydz >= 0 */
+  double *q; long q_stride;             /* q[ig*q_stride + ip], ig < ng */
+  double *k; long k_stride;             /* k[iw*k_stride + ip], iw < nw */
+} jrb_atm_view;
+
+typedef struct {
+  int nr;
+  const double *time, *obsz, *obslon, *obslat, *vpz, *vplon, *vplat; /* [nr] inputs */
+  double *tpz, *tplon, *tplat;                                       /* [nr] outputs */
+  double *rad, *tau; /* outputs, element (ir,id) at [ir*row_stride + id]; rad is also read for the NaN mask */
+  long row_stride;   /* = ND of the caller's obs_t */
+  int nd_reset;      /* columns [nd, nd_reset) are reset to rad=0, tau=1 like the reference (= ND) */
+} jrb_obs_view;
+
+/* Row-major [g][p][t][u][d] arrays exactly as in tbl_t; dim_* are the ALLOCATED extents (NG, TBLNP, ...). */
+typedef struct {
+  int dim_g, dim_p, dim_t, dim_u, dim_d, dim_s;
+  const int32_t *np; /* [g][d] */
+  const int32_t *nt; /* [g][p][d] */
+  const int32_t *nu; /* [g][p][t][d] */
+  const double *p;   /* [g][p][d] */
+  const double *t;   /* [g][p][t][d] */
+  const float *u;    /* [g][p][t][u][d] */
+  const float *eps;  /* [g][p][t][u][d] */
+  const double *sr;  /* [s][d] */
+  const double *st;  /* [s] */
+} jrb_tbl_view;
+
+typedef struct {
+  long long n_packages, n_rays, n_ray_channels, n_los_points; /* of the last run */
+  long long n_kernel_launches;                                /* kernels of this library launched by the last run */
+  float ms_raytrace, ms_ega, ms_total_device;                 /* CUDA-event times of the last run (device path) */
+  long long h2d_bytes, d2h_bytes;                             /* of the last stage / fetch */
+  int ega_kernel_variant;                                     /* 0 generic, 1 fast (templated) */
+  int ega_ngb, ega_ctm_mask;
+  long long table_blob_bytes;
+} jrb_stats;
+
+typedef struct jrb_context jrb_context;
+
+int jrb_device_count(void);
+int jrb_create(jrb_context **out, int device);
+void jrb_destroy(jrb_context *ctx);
+const char *jrb_last_error(const jrb_context *ctx); /* ctx may be NULL: last error of jrb_create */
+
+int jrb_set_control(jrb_context *ctx, const jrb_ctl_view *ctl);
+/* pack tbl_t into per-(gas,channel) slabs and upload (requires jrb_set_control first) */
+int jrb_set_tables(jrb_context *ctx, const jrb_tbl_view *tbl);
+/* multi-GPU: the packed slabs are one position-independent device blob that can be broadcast (e.g. NCCL) */
+int jrb_tables_blob(jrb_context *ctx, void **dev_ptr, size_t *nbytes);
+int jrb_tables_alloc_blob(jrb_context *ctx, size_t nbytes, void **dev_ptr); /* receiver side */
+int jrb_tables_adopt_blob(jrb_context *ctx);                                 /* after the blob has been filled */
+
+/* select kernel: -1 auto, 0 force generic, 1 force fast (fails if tables do not allow it) */
+int jrb_set_kernel_variant(jrb_context *ctx, int variant);
+
+/* complete forward model for npk packages, host buffers in and out (H2D + kernels + D2H, synchronous) */
+int jrb_formod_batch(jrb_context *ctx, int npk, const jrb_atm_view *atm, const jrb_obs_view *obs);
+
+/* the same in three phases */
+int jrb_stage(jrb_context *ctx, int npk, const jrb_atm_view *atm, const jrb_obs_view *obs);
+int jrb_run_staged(jrb_context *ctx);
+int jrb_fetch_staged(jrb_context *ctx, int npk, const jrb_obs_view *obs);
+
+/* device pointers of the staged results (rad/tau compact [n_rays][nd]); for device-side gathers */
+int jrb_staged_results(jrb_context *ctx, double **rad_dev, double **tau_dev, long long *n_rays, int *nd);
+/* debug/test: copy the LOS of staged ray r (after jrb_run_staged) into out[np][rec]; returns np via *np_out */
+int jrb_debug_los(jrb_context *ctx, long long ray, double *out, int max_doubles, int *np_out, int *rec_doubles,
+                  double *tsurf_out);
+
+int jrb_get_stats(const jrb_context *ctx, jrb_stats *out);
+const char *jrb_version(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

@@ -1,0 +1,47 @@
+/* jurassic_b200_dropin.h -- reference-facing entry points of libjurassic_b200_dropin_nd<ND>_ng<NG>.so.
+ *
+ * This thin C layer is compiled once per compile-time dimension set (-DND=.. -DNG=.., like the reference itself,
+ * src/jurassic.h:137-145) because the layouts of ctl_t / atm_t / obs_t / tbl_t depend on ND and NG.  It only turns
+ * the reference's structs into the pointer/stride views of jurassic_b200.h and forwards to the core library.
+ *
+ *   formod_GPU             replaces  formod_GPU()            src/GPUdrivers.cu:253-262 (declared src/CPUdrivers.c:153-155)
+ *                          called by formod()                src/CPUdrivers.c:189-190 when ctl->useGPU != 0
+ *   jr_b200_init           replaces  the first-call block    src/GPUdrivers.cu:275-329 (+ get_tbl_on_GPU :78-93)
+ *   jr_b200_formod_batch   new: many (atm_t, obs_t) packages per call -- a single obs_t holds at most NR = 1088 rays
+ *                          (src/jurassic.h:151), far too few to occupy a B200
+ *   jr_b200_finalize       new: releases what the reference never frees (src/GPUdrivers.cu:309)
+ *
+ * Error behaviour mirrors the reference: fatal conditions print a message and exit(EXIT_FAILURE) (ERRMSG,
+ * src/jurassic.h:68-72); ctl->checkmode != 0 prints a note and returns without computing (src/GPUdrivers.cu:337).
+ * The struct types are the reference's own (include its jurassic.h before this header) or the layout-identical
+ * mirrors of jurassic-gpu_b200/csrc/jr_structs.h.
+ */
+#ifndef JURASSIC_B200_DROPIN_H
+#define JURASSIC_B200_DROPIN_H
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+/* Drop-in for the reference symbol.  Tables: if jr_b200_init() was not called, they are taken from the
+ * reference's get_tbl(ctl) (src/jr_common.h:60-78) when that symbol is linked in, else the call is fatal. */
+void formod_GPU(ctl_t const *ctl, atm_t *atm, obs_t *obs);
+
+/* Explicit initialisation with a caller-owned table (kept only until this call returns).
+ * device < 0 selects ctl->MPIlocalrank like the reference (src/GPUdrivers.cu:288). Returns 0 or exits. */
+int jr_b200_init(ctl_t const *ctl, tbl_t const *tbl, int device);
+
+/* formod_GPU semantics for each of npackages (atm[i], obs[i]) pairs, one device batch. */
+void jr_b200_formod_batch(ctl_t const *ctl, atm_t *const atm[], obs_t *const obs[], int npackages);
+
+void jr_b200_finalize(void);
+
+/* introspection for tests: dimension macros this layer was compiled with: {ND, NG, NP, NR, NW, NLOS, TBLNP, TBLNT,
+ * TBLNU, TBLNS, LEN} and sizeof(ctl_t, atm_t, obs_t, tbl_t) */
+void jr_b200_dims(int dims[11], long long sizes[4]);
+/* the core context behind the drop-in (struct jrb_context*, see jurassic_b200.h), NULL before initialisation */
+void *jr_b200_core_context(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

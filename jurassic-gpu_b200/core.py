@@ -1,0 +1,283 @@
+"""ctypes binding of the core C ABI (include/jurassic_b200.h) plus dimension-agnostic host containers.
+
+This is harness glue for tests and bench.py: all computing happens in libjurassic_b200.so (hand-written CUDA for
+sm_100a).  There is deliberately no CPU fallback -- a missing library or missing GPU raises.
+"""
+import ctypes as C
+import os
+
+import numpy as np
+
+from . import abi
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIBDIR = os.path.join(_HERE, "lib")
+CORE_LIB = os.path.join(LIBDIR, "libjurassic_b200.so")
+
+_lib = None
+
+
+class JrbError(RuntimeError):
+    pass
+
+
+def load_core():
+    """dlopen the core library and declare every symbol of include/jurassic_b200.h (no compute is triggered)."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(CORE_LIB):
+        raise JrbError(f"{CORE_LIB} is missing: run `python -c 'import __graft_entry__ as g; g.build()'` "
+                       "(the CUDA extension is mandatory, there is no fallback path)")
+    lib = C.CDLL(CORE_LIB, mode=C.RTLD_GLOBAL)
+    vp = C.c_void_p
+    lib.jrb_version.restype = C.c_char_p
+    lib.jrb_device_count.restype = C.c_int
+    lib.jrb_create.argtypes = [C.POINTER(vp), C.c_int]
+    lib.jrb_destroy.argtypes = [vp]
+    lib.jrb_destroy.restype = None
+    lib.jrb_last_error.argtypes = [vp]
+    lib.jrb_last_error.restype = C.c_char_p
+    lib.jrb_set_control.argtypes = [vp, C.POINTER(abi.CtlView)]
+    lib.jrb_set_tables.argtypes = [vp, C.POINTER(abi.TblView)]
+    lib.jrb_tables_blob.argtypes = [vp, C.POINTER(vp), C.POINTER(C.c_size_t)]
+    lib.jrb_tables_alloc_blob.argtypes = [vp, C.c_size_t, C.POINTER(vp)]
+    lib.jrb_tables_adopt_blob.argtypes = [vp]
+    lib.jrb_set_kernel_variant.argtypes = [vp, C.c_int]
+    lib.jrb_formod_batch.argtypes = [vp, C.c_int, C.POINTER(abi.AtmView), C.POINTER(abi.ObsView)]
+    lib.jrb_stage.argtypes = [vp, C.c_int, C.POINTER(abi.AtmView), C.POINTER(abi.ObsView)]
+    lib.jrb_run_staged.argtypes = [vp]
+    lib.jrb_fetch_staged.argtypes = [vp, C.c_int, C.POINTER(abi.ObsView)]
+    lib.jrb_staged_results.argtypes = [vp, C.POINTER(vp), C.POINTER(vp), C.POINTER(C.c_longlong), C.POINTER(C.c_int)]
+    lib.jrb_debug_los.argtypes = [vp, C.c_longlong, abi.c_double_p, C.c_int, abi.c_int_p, abi.c_int_p, abi.c_double_p]
+    lib.jrb_get_stats.argtypes = [vp, C.POINTER(abi.Stats)]
+    for f in ("jrb_create", "jrb_set_control", "jrb_set_tables", "jrb_tables_blob", "jrb_tables_alloc_blob",
+              "jrb_tables_adopt_blob", "jrb_set_kernel_variant", "jrb_formod_batch", "jrb_stage", "jrb_run_staged",
+              "jrb_fetch_staged", "jrb_staged_results", "jrb_debug_los", "jrb_get_stats"):
+        getattr(lib, f).restype = C.c_int
+    _lib = lib
+    return lib
+
+
+EXPORTED_SYMBOLS = ["jrb_version", "jrb_device_count", "jrb_create", "jrb_destroy", "jrb_last_error",
+                    "jrb_set_control", "jrb_set_tables", "jrb_tables_blob", "jrb_tables_alloc_blob",
+                    "jrb_tables_adopt_blob", "jrb_set_kernel_variant", "jrb_formod_batch", "jrb_stage",
+                    "jrb_run_staged", "jrb_fetch_staged", "jrb_staged_results", "jrb_debug_los", "jrb_get_stats"]
+
+
+def _dp(a):
+    return a.ctypes.data_as(abi.c_double_p)
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# dimension-agnostic containers (numpy, C-contiguous)
+# ---------------------------------------------------------------------------------------------------------------
+class Control:
+    """The ctl_t fields the path reads (src/jurassic.h:229-347), defaults as read_ctl (src/jurassic.c:928-1021)."""
+
+    def __init__(self, emitters, nu, window=None, nw=1, ctm_co2=1, ctm_h2o=1, ctm_n2=1, ctm_o2=1, refrac=1,
+                 rayds=10.0, raydz=0.5, hydz=-999.0, write_bbt=0, tblbase="-"):
+        self.emitters = list(emitters)
+        self.ng = len(self.emitters)
+        self.nu = np.ascontiguousarray(nu, dtype=np.float64)
+        self.nd = int(self.nu.size)
+        self.nw = nw
+        self.window = np.zeros(self.nd, dtype=np.int32) if window is None else np.ascontiguousarray(window, np.int32)
+        self.ctm_co2, self.ctm_h2o, self.ctm_n2, self.ctm_o2 = ctm_co2, ctm_h2o, ctm_n2, ctm_o2
+        self.refrac, self.rayds, self.raydz, self.hydz, self.write_bbt = refrac, rayds, raydz, hydz, write_bbt
+        self.formod, self.ip = 2, 1
+        self.tblbase = tblbase
+        self.auto_ctm()
+
+    def auto_ctm(self):
+        """read_ctl's automatic switch-off of continua without a channel in range (src/jurassic.c:954-968)."""
+        nu = self.nu
+        if not np.any(nu < 4000): self.ctm_co2 = 0
+        if not np.any(nu < 20000): self.ctm_h2o = 0
+        if not np.any((nu >= 2120) & (nu <= 2605)): self.ctm_n2 = 0
+        if not np.any((nu >= 1360) & (nu <= 1805)): self.ctm_o2 = 0
+
+    def find_emitter(self, name):
+        for i, e in enumerate(self.emitters):
+            if e.lower() == name.lower():
+                return i
+        return -1
+
+    def view(self):
+        v = abi.CtlView()
+        v.ng, v.nd, v.nw = self.ng, self.nd, self.nw
+        v.nu = _dp(self.nu)
+        v.window = self.window.ctypes.data_as(abi.c_int_p)
+        v.ctm_co2, v.ctm_h2o, v.ctm_n2, v.ctm_o2 = self.ctm_co2, self.ctm_h2o, self.ctm_n2, self.ctm_o2
+        v.ig_h2o = self.find_emitter("H2O") if self.ctm_h2o else -999
+        v.ig_co2 = self.find_emitter("CO2") if self.ctm_co2 else -999
+        v.refrac, v.rayds, v.raydz, v.hydz = self.refrac, self.rayds, self.raydz, self.hydz
+        v.write_bbt, v.formod, v.ip = self.write_bbt, self.formod, self.ip
+        return v
+
+    @property
+    def ctm_mask(self):
+        v = self.view()
+        return ((v.ctm_co2 == 1 and v.ig_co2 >= 0) * 8 + (v.ctm_h2o == 1 and v.ig_h2o >= 0) * 4 +
+                (v.ctm_n2 == 1) * 2 + (v.ctm_o2 == 1))
+
+
+class Tables:
+    """Emissivity + source tables in tbl_t's row-major [g][p][T][u][d] order with freely chosen extents."""
+
+    def __init__(self, ng, nd, dim_p, dim_t, dim_u):
+        self.dims = (ng, dim_p, dim_t, dim_u, nd)
+        self.np = np.zeros((ng, nd), np.int32)
+        self.nt = np.zeros((ng, dim_p, nd), np.int32)
+        self.nu = np.zeros((ng, dim_p, dim_t, nd), np.int32)
+        self.p = np.zeros((ng, dim_p, nd), np.float64)
+        self.t = np.zeros((ng, dim_p, dim_t, nd), np.float64)
+        self.u = np.zeros((ng, dim_p, dim_t, dim_u, nd), np.float32)
+        self.eps = np.zeros((ng, dim_p, dim_t, dim_u, nd), np.float32)
+        self.sr = np.zeros((abi.TBLNS, nd), np.float64)
+        self.st = 100.0 + 0.25 * np.arange(abi.TBLNS, dtype=np.float64)
+
+    def view(self):
+        g, p, t, u, d = self.dims
+        v = abi.TblView()
+        v.dim_g, v.dim_p, v.dim_t, v.dim_u, v.dim_d, v.dim_s = g, p, t, u, d, abi.TBLNS
+        i32 = C.POINTER(C.c_int32)
+        v.np, v.nt, v.nu = (self.np.ctypes.data_as(i32), self.nt.ctypes.data_as(i32), self.nu.ctypes.data_as(i32))
+        v.p, v.t = _dp(self.p), _dp(self.t)
+        v.u = self.u.ctypes.data_as(C.POINTER(C.c_float))
+        v.eps = self.eps.ctypes.data_as(C.POINTER(C.c_float))
+        v.sr, v.st = _dp(self.sr), _dp(self.st)
+        return v
+
+
+class Package:
+    """One (atm_t, obs_t) pair of the reference, as compact arrays."""
+
+    def __init__(self, ng, nw, nd, n_atm, n_rays):
+        self.ng, self.nw, self.nd = ng, nw, nd
+        self.atm_time = np.zeros(n_atm); self.z = np.zeros(n_atm); self.lon = np.zeros(n_atm)
+        self.lat = np.zeros(n_atm); self.p = np.zeros(n_atm); self.t = np.zeros(n_atm)
+        self.q = np.zeros((max(ng, 1), n_atm)); self.k = np.zeros((max(nw, 1), n_atm))
+        self.time = np.zeros(n_rays); self.obsz = np.zeros(n_rays); self.obslon = np.zeros(n_rays)
+        self.obslat = np.zeros(n_rays); self.vpz = np.zeros(n_rays); self.vplon = np.zeros(n_rays)
+        self.vplat = np.zeros(n_rays)
+        self.tpz = np.zeros(n_rays); self.tplon = np.zeros(n_rays); self.tplat = np.zeros(n_rays)
+        self.rad = np.zeros((n_rays, nd)); self.tau = np.zeros((n_rays, nd))
+
+    @property
+    def n_atm(self):
+        return self.z.size
+
+    @property
+    def n_rays(self):
+        return self.obsz.size
+
+    def atm_view(self):
+        v = abi.AtmView()
+        v.np = self.n_atm
+        v.time, v.z, v.lon, v.lat, v.p, v.t = (_dp(self.atm_time), _dp(self.z), _dp(self.lon), _dp(self.lat),
+                                               _dp(self.p), _dp(self.t))
+        v.q, v.q_stride = _dp(self.q), self.q.shape[1]
+        v.k, v.k_stride = _dp(self.k), self.k.shape[1]
+        return v
+
+    def obs_view(self):
+        v = abi.ObsView()
+        v.nr = self.n_rays
+        v.time, v.obsz, v.obslon, v.obslat = _dp(self.time), _dp(self.obsz), _dp(self.obslon), _dp(self.obslat)
+        v.vpz, v.vplon, v.vplat = _dp(self.vpz), _dp(self.vplon), _dp(self.vplat)
+        v.tpz, v.tplon, v.tplat = _dp(self.tpz), _dp(self.tplon), _dp(self.tplat)
+        v.rad, v.tau = _dp(self.rad), _dp(self.tau)
+        v.row_stride, v.nd_reset = self.rad.shape[1], self.rad.shape[1]
+        return v
+
+
+# ---------------------------------------------------------------------------------------------------------------
+class Context:
+    """One GPU context of the core library."""
+
+    def __init__(self, device=0):
+        self.lib = load_core()
+        self.h = C.c_void_p()
+        rc = self.lib.jrb_create(C.byref(self.h), device)
+        if rc != 0:
+            raise JrbError(f"jrb_create failed ({rc}): {self.lib.jrb_last_error(None).decode()}")
+        self._keep = []
+
+    def _check(self, rc, what):
+        if rc != 0:
+            raise JrbError(f"{what} failed ({rc}): {self.lib.jrb_last_error(self.h).decode()}")
+
+    def close(self):
+        if self.h:
+            self.lib.jrb_destroy(self.h)
+            self.h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def set_control(self, ctl):
+        v = ctl.view()
+        self._check(self.lib.jrb_set_control(self.h, C.byref(v)), "jrb_set_control")
+
+    def set_tables(self, tbl):
+        v = tbl.view()
+        self._check(self.lib.jrb_set_tables(self.h, C.byref(v)), "jrb_set_tables")
+
+    def set_kernel_variant(self, variant):
+        self._check(self.lib.jrb_set_kernel_variant(self.h, variant), "jrb_set_kernel_variant")
+
+    def tables_blob(self):
+        p, n = C.c_void_p(), C.c_size_t()
+        self._check(self.lib.jrb_tables_blob(self.h, C.byref(p), C.byref(n)), "jrb_tables_blob")
+        return p.value, n.value
+
+    def tables_alloc_blob(self, nbytes):
+        p = C.c_void_p()
+        self._check(self.lib.jrb_tables_alloc_blob(self.h, nbytes, C.byref(p)), "jrb_tables_alloc_blob")
+        return p.value
+
+    def tables_adopt_blob(self):
+        self._check(self.lib.jrb_tables_adopt_blob(self.h), "jrb_tables_adopt_blob")
+
+    def _views(self, packages):
+        n = len(packages)
+        av = (abi.AtmView * n)(*[p.atm_view() for p in packages])
+        ov = (abi.ObsView * n)(*[p.obs_view() for p in packages])
+        return n, av, ov
+
+    def formod_batch(self, packages):
+        n, av, ov = self._views(packages)
+        self._check(self.lib.jrb_formod_batch(self.h, n, av, ov), "jrb_formod_batch")
+
+    def stage(self, packages):
+        n, av, ov = self._views(packages)
+        self._check(self.lib.jrb_stage(self.h, n, av, ov), "jrb_stage")
+
+    def run_staged(self):
+        self._check(self.lib.jrb_run_staged(self.h), "jrb_run_staged")
+
+    def fetch_staged(self, packages):
+        n, av, ov = self._views(packages)
+        self._check(self.lib.jrb_fetch_staged(self.h, n, ov), "jrb_fetch_staged")
+
+    def staged_results(self):
+        r, t, n, nd = C.c_void_p(), C.c_void_p(), C.c_longlong(), C.c_int()
+        self._check(self.lib.jrb_staged_results(self.h, C.byref(r), C.byref(t), C.byref(n), C.byref(nd)),
+                    "jrb_staged_results")
+        return r.value, t.value, n.value, nd.value
+
+    def debug_los(self, ray):
+        npo, rec, ts = C.c_int(), C.c_int(), C.c_double()
+        buf = np.zeros(abi.NLOS * 512)
+        self._check(self.lib.jrb_debug_los(self.h, ray, _dp(buf), buf.size, C.byref(npo), C.byref(rec), C.byref(ts)),
+                    "jrb_debug_los")
+        return buf[: npo.value * rec.value].reshape(npo.value, rec.value).copy(), ts.value
+
+    def stats(self):
+        s = abi.Stats()
+        self._check(self.lib.jrb_get_stats(self.h, C.byref(s)), "jrb_get_stats")
+        return {f[0]: getattr(s, f[0]) for f in abi.Stats._fields_}

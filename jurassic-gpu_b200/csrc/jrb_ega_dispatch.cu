@@ -1,0 +1,52 @@
+// jrb_ega_dispatch.cu -- picks the specialised EGA kernel for (ng, continuum mask).
+// JRB_MASK_LIST (bit m set = mask m was built) lets development builds compile a subset.
+#include "jrb_ega_fast.cuh"
+
+#ifndef JRB_MASK_LIST
+#define JRB_MASK_LIST 0xffff
+#endif
+
+namespace jrb {
+
+#define JRB_DECL(m) template <> cudaError_t launch_ega_fast_mask<m>(const EgaArgs &, cudaStream_t, int, int *);
+JRB_DECL(0) JRB_DECL(1) JRB_DECL(2) JRB_DECL(3) JRB_DECL(4) JRB_DECL(5) JRB_DECL(6) JRB_DECL(7)
+JRB_DECL(8) JRB_DECL(9) JRB_DECL(10) JRB_DECL(11) JRB_DECL(12) JRB_DECL(13) JRB_DECL(14) JRB_DECL(15)
+#undef JRB_DECL
+
+bool ega_fast_available(int ng, int ctm_mask) {
+  return ng >= 1 && ng <= 8 && ctm_mask >= 0 && ctm_mask < 16 && ((JRB_MASK_LIST >> ctm_mask) & 1);
+}
+
+template <int M>
+static cudaError_t call_mask(const EgaArgs &a, cudaStream_t s, int sm, int *ngb) {
+  if constexpr (((JRB_MASK_LIST) >> M) & 1) return launch_ega_fast_mask<M>(a, s, sm, ngb);
+  else return cudaErrorInvalidValue;
+}
+
+cudaError_t launch_ega_fast(const EgaArgs &a, cudaStream_t stream, int *ngb_out) {
+  if (!ega_fast_available(a.ng, a.ctm_mask)) return cudaErrorInvalidValue;
+  int dev = 0, sm = 148;
+  cudaGetDevice(&dev);
+  cudaDeviceGetAttribute(&sm, cudaDevAttrMultiProcessorCount, dev);
+  switch (a.ctm_mask) {
+    case 0: return call_mask<0>(a, stream, sm, ngb_out);
+    case 1: return call_mask<1>(a, stream, sm, ngb_out);
+    case 2: return call_mask<2>(a, stream, sm, ngb_out);
+    case 3: return call_mask<3>(a, stream, sm, ngb_out);
+    case 4: return call_mask<4>(a, stream, sm, ngb_out);
+    case 5: return call_mask<5>(a, stream, sm, ngb_out);
+    case 6: return call_mask<6>(a, stream, sm, ngb_out);
+    case 7: return call_mask<7>(a, stream, sm, ngb_out);
+    case 8: return call_mask<8>(a, stream, sm, ngb_out);
+    case 9: return call_mask<9>(a, stream, sm, ngb_out);
+    case 10: return call_mask<10>(a, stream, sm, ngb_out);
+    case 11: return call_mask<11>(a, stream, sm, ngb_out);
+    case 12: return call_mask<12>(a, stream, sm, ngb_out);
+    case 13: return call_mask<13>(a, stream, sm, ngb_out);
+    case 14: return call_mask<14>(a, stream, sm, ngb_out);
+    case 15: return call_mask<15>(a, stream, sm, ngb_out);
+  }
+  return cudaErrorInvalidValue;
+}
+
+} // namespace jrb

@@ -1,0 +1,54 @@
+// jrb_internal.h -- kernel argument blocks and launch prototypes shared between the host runtime and the kernels.
+#pragma once
+#include "jrb_device.cuh"
+
+namespace jrb {
+
+struct TraceArgs {
+  long long n_rays;
+  // ray geometry SoA: rows 0..6 = obsz, obslon, obslat, vpz, vplon, vplat, time ; row stride geo_stride
+  const double *geo;
+  long long geo_stride;
+  const int *ray_pkg; // [n_rays] package (= atmosphere set) of each ray
+  // atmosphere sets, concatenated point arrays
+  const long long *pkg_atm_off; // [npk]
+  const int *pkg_atm_np;        // [npk]
+  const double *atm_time, *atm_z, *atm_lon, *atm_lat, *atm_p, *atm_t;
+  const double *atm_q, *atm_k; // [ng][atm_stride], [nw][atm_stride]
+  long long atm_stride;
+  // control
+  int refrac, ig_h2o;
+  double rayds, raydz;
+  // outputs
+  LosLayout los;
+  double *los_data; // [n_rays][NLOS][rec]
+  int *ray_np;      // [n_rays]
+  double *ray_tsurf;
+  double *tp;       // rows tpz, tplon, tplat ; row stride geo_stride
+  TblDev tbl;       // used when los.fast
+};
+
+struct EgaArgs {
+  long long n_rays;
+  int ng, nd, nw;
+  int ctm_mask;       // CO2*8 + H2O*4 + N2*2 + O2 (fourbit, src/CPUdrivers.c:130-134)
+  int ig_co2, ig_h2o;
+  int write_bbt;
+  LosLayout los;
+  const double *los_data;
+  const int *ray_np;
+  const double *ray_tsurf;
+  const double *chan;   // [CH_NFIELDS][nd]
+  const int *window;    // [nd]
+  TblDev tbl;
+  double *rad, *tau;    // [n_rays][nd]
+  unsigned long long *work_counter; // dynamic work distribution (zeroed before launch)
+};
+
+cudaError_t launch_raytrace(const TraceArgs &a, cudaStream_t stream);
+cudaError_t launch_ega_generic(const EgaArgs &a, cudaStream_t stream);
+// fast path: returns cudaErrorInvalidValue if (ng, ctm_mask) has no instantiation
+cudaError_t launch_ega_fast(const EgaArgs &a, cudaStream_t stream, int *ngb_out);
+bool ega_fast_available(int ng, int ctm_mask);
+
+} // namespace jrb

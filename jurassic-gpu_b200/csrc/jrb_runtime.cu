@@ -1,0 +1,574 @@
+// jrb_runtime.cu -- host runtime behind the C ABI of include/jurassic_b200.h: context, table residency,
+// staging of packages into compact device arrays, kernel sequencing, result scatter.
+//
+// Replaces the reference's lane machinery (gpuLane_t / formod_one_package / formod_GPU,
+// src/GPUdrivers.cu:176-360): instead of copying whole atm_t/obs_t structs (2.8 MB + 1.8 MB per 1088 rays, mostly
+// unused NP/NR/ND padding) per call, any number of packages is packed into one pinned staging buffer holding only
+// the populated prefixes, moved with a single H2D copy, processed by two kernels per LOS chunk (ray tracer, EGA) and
+// returned with a single D2H copy.
+#include "jrb_host.h"
+
+#include <algorithm>
+#include <cmath>
+#include <cstdio>
+#include <cstring>
+#include <mutex>
+
+using namespace jrb;
+
+namespace {
+
+struct DevBuf {
+  void *p = nullptr;
+  size_t cap = 0;
+  cudaError_t ensure(size_t n) {
+    if (n <= cap) return cudaSuccess;
+    if (p) cudaFree(p);
+    p = nullptr; cap = 0;
+    cudaError_t e = cudaMalloc(&p, n);
+    if (e == cudaSuccess) cap = n;
+    return e;
+  }
+  void release() { if (p) cudaFree(p); p = nullptr; cap = 0; }
+};
+struct PinBuf {
+  void *p = nullptr;
+  size_t cap = 0;
+  cudaError_t ensure(size_t n) {
+    if (n <= cap) return cudaSuccess;
+    if (p) cudaFreeHost(p);
+    p = nullptr; cap = 0;
+    cudaError_t e = cudaMallocHost(&p, n);
+    if (e == cudaSuccess) cap = n;
+    return e;
+  }
+  void release() { if (p) cudaFreeHost(p); p = nullptr; cap = 0; }
+};
+
+std::string g_create_error;
+
+inline size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
+
+} // namespace
+
+struct jrb_context {
+  int device = 0;
+  int sm_count = 148;
+  cudaStream_t stream = nullptr;
+  std::string err;
+  std::mutex mtx;
+
+  // control
+  bool have_ctl = false;
+  int ng = 0, nd = 0, nw = 0, ctm_mask = 0, ig_co2 = -1, ig_h2o = -1, refrac = 1, write_bbt = 0;
+  double rayds = 10, raydz = 0.5, hydz = -999;
+  std::vector<double> nu;
+  std::vector<int> window;
+  DevBuf d_chan, d_window;
+
+  // tables
+  bool have_tbl = false;
+  DevBuf d_blob;
+  size_t blob_bytes = 0;
+  TblHeader th;
+  TblDev td;
+  int variant_req = -1;
+
+  // staged batch
+  bool staged = false, ran = false;
+  int npk = 0;
+  long long n_rays = 0, n_atm = 0;
+  std::vector<int> pk_nr;
+  std::vector<long long> pk_ray_off;
+  std::vector<std::pair<long long, int>> nan_mask; // (global ray, channel) whose input radiance was non-finite
+  PinBuf h_in, h_out;
+  DevBuf d_in, d_out, d_los, d_np, d_tsurf, d_counter;
+  // pointers into d_in / d_out
+  double *geo = nullptr, *atm = nullptr;
+  int *ray_pkg = nullptr, *pkg_atm_np = nullptr;
+  long long *pkg_atm_off = nullptr;
+  double *o_rad = nullptr, *o_tau = nullptr, *o_tp = nullptr;
+  long long chunk_rays = 0;
+  LosLayout los;
+  int use_fast = 0;
+  std::vector<cudaEvent_t> events;
+  jrb_stats stats;
+  bool np_fetched = false;
+
+  int fail(int code, const std::string &m) { err = m; return code; }
+  int cuda_fail(cudaError_t e, const char *what) {
+    err = std::string(what) + ": " + cudaGetErrorString(e);
+    return JRB_ERR_CUDA;
+  }
+};
+
+#define CU(call)                                                \
+  do {                                                          \
+    cudaError_t e_ = (call);                                    \
+    if (e_ != cudaSuccess) return ctx->cuda_fail(e_, #call);    \
+  } while (0)
+
+extern "C" {
+
+const char *jrb_version(void) { return "jurassic-b200 0.1 (sm_100a)"; }
+
+int jrb_device_count(void) {
+  int n = 0;
+  if (cudaGetDeviceCount(&n) != cudaSuccess) { cudaGetLastError(); return 0; }
+  return n;
+}
+
+const char *jrb_last_error(const jrb_context *ctx) { return ctx ? ctx->err.c_str() : g_create_error.c_str(); }
+
+int jrb_create(jrb_context **out, int device) {
+  if (!out) return JRB_ERR_ARG;
+  *out = nullptr;
+  int n = 0;
+  cudaError_t e = cudaGetDeviceCount(&n);
+  if (e != cudaSuccess || n < 1) {
+    g_create_error = std::string("no usable CUDA device (this library has no CPU fallback): ") +
+                     (e != cudaSuccess ? cudaGetErrorString(e) : "device count is 0");
+    cudaGetLastError();
+    return JRB_ERR_CUDA;
+  }
+  if (device < 0 || device >= n) { g_create_error = "device ordinal out of range"; return JRB_ERR_ARG; }
+  e = cudaSetDevice(device);
+  if (e != cudaSuccess) { g_create_error = std::string("cudaSetDevice: ") + cudaGetErrorString(e); return JRB_ERR_CUDA; }
+  jrb_context *ctx = new jrb_context();
+  ctx->device = device;
+  cudaDeviceGetAttribute(&ctx->sm_count, cudaDevAttrMultiProcessorCount, device);
+  e = cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking);
+  if (e != cudaSuccess) { g_create_error = std::string("cudaStreamCreate: ") + cudaGetErrorString(e); delete ctx; return JRB_ERR_CUDA; }
+  std::memset(&ctx->stats, 0, sizeof(ctx->stats));
+  *out = ctx;
+  return JRB_OK;
+}
+
+void jrb_destroy(jrb_context *ctx) {
+  if (!ctx) return;
+  cudaSetDevice(ctx->device);
+  cudaStreamSynchronize(ctx->stream);
+  for (auto ev : ctx->events) cudaEventDestroy(ev);
+  ctx->d_chan.release(); ctx->d_window.release(); ctx->d_blob.release();
+  ctx->d_in.release(); ctx->d_out.release(); ctx->d_los.release(); ctx->d_np.release(); ctx->d_tsurf.release();
+  ctx->d_counter.release(); ctx->h_in.release(); ctx->h_out.release();
+  cudaStreamDestroy(ctx->stream);
+  delete ctx;
+}
+
+int jrb_set_control(jrb_context *ctx, const jrb_ctl_view *c) {
+  if (!ctx || !c) return JRB_ERR_ARG;
+  std::lock_guard<std::mutex> lk(ctx->mtx);
+  if (c->ng < 0 || c->ng > JRB_MAX_NG) return ctx->fail(JRB_ERR_LIMIT, "ng out of range (max 64)");
+  if (c->nd < 1) return ctx->fail(JRB_ERR_ARG, "nd must be >= 1");
+  if (c->nw < 0 || c->nw > JRB_MAX_NW) return ctx->fail(JRB_ERR_LIMIT, "nw out of range (max 8)");
+  if (c->formod != 2) return ctx->fail(JRB_ERR_ARG, "only FORMOD=2 (EGA) is supported (reference asserts the same, src/jr_common.h:707)");
+  if (c->ip != 1) return ctx->fail(JRB_ERR_ARG, "only IP=1 (1-D profiles) is supported (reference asserts the same, src/jr_common.h:573)");
+  for (int id = 0; id < c->nd; id++)
+    if (c->window[id] < 0 || c->window[id] >= (c->nw > 0 ? c->nw : 1)) return ctx->fail(JRB_ERR_ARG, "window index out of range");
+  CU(cudaSetDevice(ctx->device));
+  if (ctx->have_ctl && (ctx->ng != c->ng || ctx->nd != c->nd)) ctx->have_tbl = false; // tables must be re-packed
+  ctx->ng = c->ng; ctx->nd = c->nd; ctx->nw = c->nw;
+  ctx->ig_co2 = c->ig_co2; ctx->ig_h2o = c->ig_h2o;
+  // fourbit of the reference (src/CPUdrivers.c:130-134)
+  ctx->ctm_mask = ((1 == c->ctm_co2) && (c->ig_co2 >= 0)) * 8 + ((1 == c->ctm_h2o) && (c->ig_h2o >= 0)) * 4 +
+                  (1 == c->ctm_n2) * 2 + (1 == c->ctm_o2) * 1;
+  ctx->refrac = c->refrac; ctx->rayds = c->rayds; ctx->raydz = c->raydz; ctx->hydz = c->hydz;
+  ctx->write_bbt = c->write_bbt;
+  ctx->nu.assign(c->nu, c->nu + c->nd);
+  ctx->window.assign(c->window, c->window + c->nd);
+  std::vector<double> chan;
+  channel_constants(ctx->nd, ctx->nu.data(), ctx->ctm_mask, chan);
+  CU(ctx->d_chan.ensure(chan.size() * sizeof(double)));
+  CU(ctx->d_window.ensure(ctx->nd * sizeof(int)));
+  CU(cudaMemcpyAsync(ctx->d_chan.p, chan.data(), chan.size() * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
+  CU(cudaMemcpyAsync(ctx->d_window.p, ctx->window.data(), ctx->nd * sizeof(int), cudaMemcpyHostToDevice, ctx->stream));
+  CU(cudaStreamSynchronize(ctx->stream));
+  ctx->have_ctl = true;
+  ctx->staged = false;
+  return JRB_OK;
+}
+
+static int adopt_blob_locked(jrb_context *ctx) {
+  unsigned char hdr[sizeof(TblHeader)];
+  CU(cudaMemcpy(hdr, ctx->d_blob.p, sizeof(TblHeader), cudaMemcpyDeviceToHost));
+  int rc = resolve_tables(hdr, (const unsigned char *)ctx->d_blob.p, ctx->th, ctx->td, ctx->err);
+  if (rc != JRB_OK) return rc;
+  if (ctx->th.nbytes > ctx->blob_bytes) return ctx->fail(JRB_ERR_ARG, "table blob truncated");
+  if (ctx->th.ng != ctx->ng || ctx->th.nd != ctx->nd) return ctx->fail(JRB_ERR_ARG, "table blob was packed for another ng/nd");
+  ctx->have_tbl = true;
+  ctx->staged = false;
+  ctx->stats.table_blob_bytes = (long long)ctx->th.nbytes;
+  return JRB_OK;
+}
+
+int jrb_set_tables(jrb_context *ctx, const jrb_tbl_view *tbl) {
+  if (!ctx || !tbl) return JRB_ERR_ARG;
+  std::lock_guard<std::mutex> lk(ctx->mtx);
+  if (!ctx->have_ctl) return ctx->fail(JRB_ERR_STATE, "jrb_set_control must be called before jrb_set_tables");
+  CU(cudaSetDevice(ctx->device));
+  std::vector<unsigned char> blob;
+  int rc = pack_tables(*tbl, ctx->ng, ctx->nd, blob, ctx->err);
+  if (rc != JRB_OK) return rc;
+  CU(ctx->d_blob.ensure(blob.size()));
+  ctx->blob_bytes = blob.size();
+  CU(cudaMemcpy(ctx->d_blob.p, blob.data(), blob.size(), cudaMemcpyHostToDevice));
+  return adopt_blob_locked(ctx);
+}
+
+int jrb_tables_blob(jrb_context *ctx, void **dev_ptr, size_t *nbytes) {
+  if (!ctx || !dev_ptr || !nbytes) return JRB_ERR_ARG;
+  std::lock_guard<std::mutex> lk(ctx->mtx);
+  if (!ctx->have_tbl) return ctx->fail(JRB_ERR_STATE, "no tables set");
+  *dev_ptr = ctx->d_blob.p; *nbytes = ctx->blob_bytes;
+  return JRB_OK;
+}
+
+int jrb_tables_alloc_blob(jrb_context *ctx, size_t nbytes, void **dev_ptr) {
+  if (!ctx || !dev_ptr || nbytes < sizeof(TblHeader)) return JRB_ERR_ARG;
+  std::lock_guard<std::mutex> lk(ctx->mtx);
+  CU(cudaSetDevice(ctx->device));
+  CU(ctx->d_blob.ensure(nbytes));
+  ctx->blob_bytes = nbytes;
+  ctx->have_tbl = false;
+  *dev_ptr = ctx->d_blob.p;
+  return JRB_OK;
+}
+
+int jrb_tables_adopt_blob(jrb_context *ctx) {
+  if (!ctx) return JRB_ERR_ARG;
+  std::lock_guard<std::mutex> lk(ctx->mtx);
+  if (!ctx->have_ctl) return ctx->fail(JRB_ERR_STATE, "jrb_set_control must be called first");
+  if (!ctx->d_blob.p) return ctx->fail(JRB_ERR_STATE, "no blob allocated");
+  CU(cudaSetDevice(ctx->device));
+  return adopt_blob_locked(ctx);
+}
+
+int jrb_set_kernel_variant(jrb_context *ctx, int variant) {
+  if (!ctx || variant < -1 || variant > 1) return JRB_ERR_ARG;
+  std::lock_guard<std::mutex> lk(ctx->mtx);
+  ctx->variant_req = variant;
+  ctx->staged = false;
+  return JRB_OK;
+}
+
+// ---- hydrostatic adjustment on the host (hydrostatic_1d_h2o, src/jr_common.h:714-761; default off) -----------
+static void hydrostatic_host(const jrb_atm_view &a, double hydz, int ig_h2o) {
+  const int npts = 20, ip0 = 0, ip1 = a.np;
+  double dzmin = 1e99;
+  int ipref = 0;
+  for (int ip = ip0; ip < ip1; ip++) {
+    const double dz = std::fabs(a.z[ip] - hydz);
+    if (dz < dzmin) { dzmin = dz; ipref = ip; }
+  }
+  const double lat = a.lat[ipref];
+  const double mmair = 28.96456e-3, mmh2o = 18.0153e-3, rgas = 8.314472; // GSL_CONST_MKSA_MOLAR_GAS (GSL 2.5)
+  auto gravity = [](double z, double la) {
+    const double deg2rad = M_PI / 180., x = std::sin(la * deg2rad), y = std::sin(2 * la * deg2rad);
+    return 9.780318 * (1. + 0.0053024 * x * x - 5.8e-6 * y * y) - 3.086e-3 * z;
+  };
+  auto lin = [](double x0, double y0, double x1, double y1, double x) { return y0 + (x - x0) * (y1 - y0) / (x1 - x0); };
+  const double *qh = (ig_h2o >= 0) ? a.q + (size_t)ig_h2o * a.q_stride : nullptr;
+  double e = 0.;
+  for (int dir = 0; dir < 2; dir++) {
+    const int step = dir == 0 ? 1 : -1;
+    for (int ip = ipref + step; dir == 0 ? ip < ip1 : ip >= ip0; ip += step) {
+      const int prev = ip - step;
+      double mean = 0.;
+      for (int i = 0; i < npts; i++) {
+        const double z = lin(0.0, a.z[prev], npts - 1.0, a.z[ip], (double)i);
+        const double grav = gravity(z, lat);
+        if (qh) e = lin(0.0, qh[prev], npts - 1.0, qh[ip], (double)i);
+        const double temp = lin(0.0, a.t[prev], npts - 1.0, a.t[ip], (double)i);
+        mean += (e * mmh2o + (1 - e) * mmair) * grav / (rgas * temp * npts);
+      }
+      a.p[ip] = a.p[prev] * std::exp(-1000 * mean * (a.z[ip] - a.z[prev]));
+    }
+  }
+}
+
+int jrb_stage(jrb_context *ctx, int npk, const jrb_atm_view *atm, const jrb_obs_view *obs) {
+  if (!ctx || npk < 0 || (npk > 0 && (!atm || !obs))) return JRB_ERR_ARG;
+  std::lock_guard<std::mutex> lk(ctx->mtx);
+  if (!ctx->have_ctl || !ctx->have_tbl) return ctx->fail(JRB_ERR_STATE, "control and tables must be set before staging");
+  CU(cudaSetDevice(ctx->device));
+  const int ng = ctx->ng, nd = ctx->nd, nw = ctx->nw;
+
+  ctx->npk = npk;
+  ctx->pk_nr.resize(npk);
+  ctx->pk_ray_off.resize(npk + 1);
+  std::vector<long long> atm_off(npk + 1);
+  long long R = 0, A = 0;
+  for (int k = 0; k < npk; k++) {
+    if (obs[k].nr < 0 || atm[k].np < 1) return ctx->fail(JRB_ERR_ARG, "package with nr < 0 or empty atmosphere");
+    ctx->pk_nr[k] = obs[k].nr;
+    ctx->pk_ray_off[k] = R; atm_off[k] = A;
+    R += obs[k].nr; A += atm[k].np;
+  }
+  ctx->pk_ray_off[npk] = R; atm_off[npk] = A;
+  ctx->n_rays = R; ctx->n_atm = A;
+
+  if (ctx->hydz >= 0) // modifies the caller's atm->p like the reference's CPU path (src/CPUdrivers.c:97-103)
+    for (int k = 0; k < npk; k++) hydrostatic_host(atm[k], ctx->hydz, ctx->ig_h2o);
+
+  // staging buffer layout (doubles first, then integers)
+  const size_t n_geo = 7 * (size_t)R, n_atm = (size_t)(6 + ng + nw) * A;
+  const size_t off_geo = 0, off_atm = off_geo + n_geo * 8, off_poff = align_up(off_atm + n_atm * 8, 8);
+  const size_t off_rpk = off_poff + (size_t)npk * 8, off_pnp = off_rpk + (size_t)R * 4;
+  const size_t in_bytes = align_up(off_pnp + (size_t)npk * 4, 256) + 256;
+  CU(ctx->h_in.ensure(in_bytes));
+  CU(ctx->d_in.ensure(in_bytes));
+  unsigned char *H = (unsigned char *)ctx->h_in.p;
+  double *hgeo = (double *)(H + off_geo), *hatm = (double *)(H + off_atm);
+  long long *hpoff = (long long *)(H + off_poff);
+  int *hrpk = (int *)(H + off_rpk), *hpnp = (int *)(H + off_pnp);
+
+  ctx->nan_mask.clear();
+  std::vector<std::vector<std::pair<long long, int>>> masks(npk);
+#pragma omp parallel for schedule(dynamic, 4)
+  for (int k = 0; k < npk; k++) {
+    const jrb_obs_view &o = obs[k];
+    const jrb_atm_view &a = atm[k];
+    const long long r0 = ctx->pk_ray_off[k], a0 = atm_off[k];
+    const size_t nrb = (size_t)o.nr * 8, npb = (size_t)a.np * 8;
+    std::memcpy(hgeo + 0 * R + r0, o.obsz, nrb);
+    std::memcpy(hgeo + 1 * R + r0, o.obslon, nrb);
+    std::memcpy(hgeo + 2 * R + r0, o.obslat, nrb);
+    std::memcpy(hgeo + 3 * R + r0, o.vpz, nrb);
+    std::memcpy(hgeo + 4 * R + r0, o.vplon, nrb);
+    std::memcpy(hgeo + 5 * R + r0, o.vplat, nrb);
+    std::memcpy(hgeo + 6 * R + r0, o.time, nrb);
+    std::memcpy(hatm + 0 * A + a0, a.time, npb);
+    std::memcpy(hatm + 1 * A + a0, a.z, npb);
+    std::memcpy(hatm + 2 * A + a0, a.lon, npb);
+    std::memcpy(hatm + 3 * A + a0, a.lat, npb);
+    std::memcpy(hatm + 4 * A + a0, a.p, npb);
+    std::memcpy(hatm + 5 * A + a0, a.t, npb);
+    for (int ig = 0; ig < ng; ig++) std::memcpy(hatm + (size_t)(6 + ig) * A + a0, a.q + (size_t)ig * a.q_stride, npb);
+    for (int iw = 0; iw < nw; iw++) std::memcpy(hatm + (size_t)(6 + ng + iw) * A + a0, a.k + (size_t)iw * a.k_stride, npb);
+    hpoff[k] = a0; hpnp[k] = a.np;
+    for (int ir = 0; ir < o.nr; ir++) {
+      hrpk[r0 + ir] = k;
+      const double *row = o.rad + (size_t)ir * o.row_stride; // save_mask (src/jr_common.h:193-200)
+      for (int id = 0; id < nd; id++)
+        if (!std::isfinite(row[id])) masks[k].push_back({r0 + ir, id});
+    }
+  }
+  for (int k = 0; k < npk; k++) ctx->nan_mask.insert(ctx->nan_mask.end(), masks[k].begin(), masks[k].end());
+
+  CU(cudaMemcpyAsync(ctx->d_in.p, H, in_bytes, cudaMemcpyHostToDevice, ctx->stream));
+  unsigned char *Dv = (unsigned char *)ctx->d_in.p;
+  ctx->geo = (double *)(Dv + off_geo); ctx->atm = (double *)(Dv + off_atm);
+  ctx->pkg_atm_off = (long long *)(Dv + off_poff); ctx->ray_pkg = (int *)(Dv + off_rpk); ctx->pkg_atm_np = (int *)(Dv + off_pnp);
+
+  // outputs
+  const size_t out_bytes = ((size_t)2 * R * nd + 3 * (size_t)R) * 8 + 256;
+  CU(ctx->d_out.ensure(out_bytes));
+  ctx->o_rad = (double *)ctx->d_out.p; ctx->o_tau = ctx->o_rad + (size_t)R * nd; ctx->o_tp = ctx->o_tau + (size_t)R * nd;
+  CU(ctx->d_np.ensure((size_t)(R ? R : 1) * 4));
+  CU(ctx->d_tsurf.ensure((size_t)(R ? R : 1) * 8));
+  CU(ctx->d_counter.ensure(256));
+
+  // kernel choice + LOS buffer
+  const bool fast_ok = ctx->th.all_shared && ctx->th.monotone && ega_fast_available(ng, ctx->ctm_mask);
+  if (ctx->variant_req == 1 && !fast_ok)
+    return ctx->fail(JRB_ERR_STATE, "specialised kernel not applicable (channel-dependent axes, non-monotone columns, ng > 8 or mask not built)");
+  ctx->use_fast = (ctx->variant_req == 0) ? 0 : (fast_ok ? 1 : 0);
+  ctx->los = make_los_layout(ng, nw, ctx->use_fast);
+  const size_t per_ray = (size_t)kNLOS * ctx->los.rec * 8;
+  double los_gb = 24.0;
+  if (const char *s = getenv("JRB_LOS_GB")) { double v = atof(s); if (v > 0.01) los_gb = v; }
+  long long chunk = (long long)(los_gb * 1e9 / (double)per_ray);
+  if (chunk < 1024) chunk = 1024;
+  if (chunk > R) chunk = R;
+  ctx->chunk_rays = chunk;
+  CU(ctx->d_los.ensure((size_t)(chunk ? chunk : 1) * per_ray));
+
+  CU(cudaStreamSynchronize(ctx->stream));
+  ctx->stats.h2d_bytes = (long long)in_bytes;
+  ctx->stats.n_packages = npk; ctx->stats.n_rays = R; ctx->stats.n_ray_channels = R * nd;
+  ctx->staged = true; ctx->ran = false; ctx->np_fetched = false;
+  return JRB_OK;
+}
+
+int jrb_run_staged(jrb_context *ctx) {
+  if (!ctx) return JRB_ERR_ARG;
+  std::lock_guard<std::mutex> lk(ctx->mtx);
+  if (!ctx->staged) return ctx->fail(JRB_ERR_STATE, "nothing staged");
+  CU(cudaSetDevice(ctx->device));
+  const long long R = ctx->n_rays, A = ctx->n_atm;
+  const int ng = ctx->ng, nd = ctx->nd, nw = ctx->nw;
+  const long long nchunks = R > 0 ? (R + ctx->chunk_rays - 1) / ctx->chunk_rays : 0;
+  const size_t need_ev = 2 + 3 * (size_t)nchunks;
+  while (ctx->events.size() < need_ev) { cudaEvent_t ev; CU(cudaEventCreate(&ev)); ctx->events.push_back(ev); }
+  long long launches = 0;
+  int ngb = ng;
+  CU(cudaEventRecord(ctx->events[0], ctx->stream));
+  for (long long c = 0; c < nchunks; c++) {
+    const long long r0 = c * ctx->chunk_rays, r1 = std::min(R, r0 + ctx->chunk_rays);
+    TraceArgs t;
+    t.n_rays = r1 - r0;
+    t.geo = ctx->geo + r0; t.geo_stride = R;
+    t.ray_pkg = ctx->ray_pkg + r0;
+    t.pkg_atm_off = ctx->pkg_atm_off; t.pkg_atm_np = ctx->pkg_atm_np;
+    t.atm_time = ctx->atm + 0 * A; t.atm_z = ctx->atm + 1 * A; t.atm_lon = ctx->atm + 2 * A; t.atm_lat = ctx->atm + 3 * A;
+    t.atm_p = ctx->atm + 4 * A; t.atm_t = ctx->atm + 5 * A; t.atm_q = ctx->atm + 6 * A; t.atm_k = ctx->atm + (size_t)(6 + ng) * A;
+    t.atm_stride = A;
+    t.refrac = ctx->refrac; t.ig_h2o = (ctx->ctm_mask & 4) ? ctx->ig_h2o : -1;
+    t.rayds = ctx->rayds; t.raydz = ctx->raydz;
+    t.los = ctx->los; t.los_data = (double *)ctx->d_los.p;
+    t.ray_np = (int *)ctx->d_np.p + r0; t.ray_tsurf = (double *)ctx->d_tsurf.p + r0;
+    t.tp = ctx->o_tp + r0;
+    t.tbl = ctx->td;
+    CU(cudaEventRecord(ctx->events[2 + 3 * c], ctx->stream));
+    CU(launch_raytrace(t, ctx->stream));
+    launches++;
+    CU(cudaEventRecord(ctx->events[3 + 3 * c], ctx->stream));
+
+    EgaArgs e;
+    e.n_rays = r1 - r0; e.ng = ng; e.nd = nd; e.nw = nw;
+    e.ctm_mask = ctx->ctm_mask; e.ig_co2 = ctx->ig_co2 >= 0 ? ctx->ig_co2 : 0; e.ig_h2o = ctx->ig_h2o >= 0 ? ctx->ig_h2o : 0;
+    e.write_bbt = ctx->write_bbt;
+    e.los = ctx->los; e.los_data = (const double *)ctx->d_los.p;
+    e.ray_np = (const int *)ctx->d_np.p + r0; e.ray_tsurf = (const double *)ctx->d_tsurf.p + r0;
+    e.chan = (const double *)ctx->d_chan.p; e.window = (const int *)ctx->d_window.p;
+    e.tbl = ctx->td;
+    e.rad = ctx->o_rad + (size_t)r0 * nd; e.tau = ctx->o_tau + (size_t)r0 * nd;
+    e.work_counter = (unsigned long long *)ctx->d_counter.p;
+    if (ctx->use_fast) {
+      CU(cudaMemsetAsync(ctx->d_counter.p, 0, 8, ctx->stream));
+      CU(launch_ega_fast(e, ctx->stream, &ngb));
+    } else {
+      CU(launch_ega_generic(e, ctx->stream));
+    }
+    launches++;
+    CU(cudaEventRecord(ctx->events[4 + 3 * c], ctx->stream));
+  }
+  CU(cudaEventRecord(ctx->events[1], ctx->stream));
+  CU(cudaStreamSynchronize(ctx->stream));
+  float ms_rt = 0, ms_ega = 0, ms_tot = 0, ms;
+  for (long long c = 0; c < nchunks; c++) {
+    CU(cudaEventElapsedTime(&ms, ctx->events[2 + 3 * c], ctx->events[3 + 3 * c])); ms_rt += ms;
+    CU(cudaEventElapsedTime(&ms, ctx->events[3 + 3 * c], ctx->events[4 + 3 * c])); ms_ega += ms;
+  }
+  CU(cudaEventElapsedTime(&ms_tot, ctx->events[0], ctx->events[1]));
+  ctx->stats.ms_raytrace = ms_rt; ctx->stats.ms_ega = ms_ega; ctx->stats.ms_total_device = ms_tot;
+  ctx->stats.n_kernel_launches = launches;
+  ctx->stats.ega_kernel_variant = ctx->use_fast; ctx->stats.ega_ngb = ctx->use_fast ? ngb : 0;
+  ctx->stats.ega_ctm_mask = ctx->ctm_mask;
+  ctx->ran = true; ctx->np_fetched = false;
+  return JRB_OK;
+}
+
+int jrb_fetch_staged(jrb_context *ctx, int npk, const jrb_obs_view *obs) {
+  if (!ctx || (npk > 0 && !obs)) return JRB_ERR_ARG;
+  std::lock_guard<std::mutex> lk(ctx->mtx);
+  if (!ctx->ran) return ctx->fail(JRB_ERR_STATE, "jrb_run_staged has not completed");
+  if (npk != ctx->npk) return ctx->fail(JRB_ERR_ARG, "package count differs from the staged batch");
+  CU(cudaSetDevice(ctx->device));
+  const long long R = ctx->n_rays;
+  const int nd = ctx->nd;
+  const size_t out_bytes = ((size_t)2 * R * nd + 3 * (size_t)R) * 8;
+  CU(ctx->h_out.ensure(out_bytes + 256));
+  CU(cudaMemcpyAsync(ctx->h_out.p, ctx->d_out.p, out_bytes, cudaMemcpyDeviceToHost, ctx->stream));
+  CU(cudaStreamSynchronize(ctx->stream));
+  double *hrad = (double *)ctx->h_out.p, *htau = hrad + (size_t)R * nd, *htp = htau + (size_t)R * nd;
+  const double nan = std::nan("");
+  for (auto &m : ctx->nan_mask) hrad[(size_t)m.first * nd + m.second] = nan; // apply_mask (src/jr_common.h:203-210)
+#pragma omp parallel for schedule(dynamic, 4)
+  for (int k = 0; k < npk; k++) {
+    const jrb_obs_view &o = obs[k];
+    const long long r0 = ctx->pk_ray_off[k];
+    const int nr = ctx->pk_nr[k];
+    if (o.nr != nr) continue;
+    std::memcpy(o.tpz, htp + 0 * R + r0, (size_t)nr * 8);
+    std::memcpy(o.tplon, htp + 1 * R + r0, (size_t)nr * 8);
+    std::memcpy(o.tplat, htp + 2 * R + r0, (size_t)nr * 8);
+    for (int ir = 0; ir < nr; ir++) {
+      double *rr = o.rad + (size_t)ir * o.row_stride, *tt = o.tau + (size_t)ir * o.row_stride;
+      std::memcpy(rr, hrad + (size_t)(r0 + ir) * nd, (size_t)nd * 8);
+      std::memcpy(tt, htau + (size_t)(r0 + ir) * nd, (size_t)nd * 8);
+      for (int id = nd; id < o.nd_reset; id++) { rr[id] = 0.0; tt[id] = 1.0; } // all ND columns are reset (src/CPUdrivers.c:58-60)
+    }
+  }
+  for (int k = 0; k < npk; k++)
+    if (obs[k].nr != ctx->pk_nr[k]) return ctx->fail(JRB_ERR_ARG, "obs[k].nr changed between stage and fetch");
+  ctx->stats.d2h_bytes = (long long)out_bytes;
+  return JRB_OK;
+}
+
+int jrb_formod_batch(jrb_context *ctx, int npk, const jrb_atm_view *atm, const jrb_obs_view *obs) {
+  int rc = jrb_stage(ctx, npk, atm, obs);
+  if (rc != JRB_OK) return rc;
+  rc = jrb_run_staged(ctx);
+  if (rc != JRB_OK) return rc;
+  return jrb_fetch_staged(ctx, npk, obs);
+}
+
+int jrb_staged_results(jrb_context *ctx, double **rad_dev, double **tau_dev, long long *n_rays, int *nd) {
+  if (!ctx) return JRB_ERR_ARG;
+  std::lock_guard<std::mutex> lk(ctx->mtx);
+  if (!ctx->staged) return ctx->fail(JRB_ERR_STATE, "nothing staged");
+  if (rad_dev) *rad_dev = ctx->o_rad;
+  if (tau_dev) *tau_dev = ctx->o_tau;
+  if (n_rays) *n_rays = ctx->n_rays;
+  if (nd) *nd = ctx->nd;
+  return JRB_OK;
+}
+
+int jrb_debug_los(jrb_context *ctx, long long ray, double *out, int max_doubles, int *np_out, int *rec_doubles,
+                  double *tsurf_out) {
+  if (!ctx) return JRB_ERR_ARG;
+  std::lock_guard<std::mutex> lk(ctx->mtx);
+  if (!ctx->ran) return ctx->fail(JRB_ERR_STATE, "jrb_run_staged has not completed");
+  if (ray < 0 || ray >= ctx->n_rays) return ctx->fail(JRB_ERR_ARG, "ray out of range");
+  if (ctx->chunk_rays < ctx->n_rays) {
+    // only the last chunk's LOS is still resident
+    const long long last0 = (ctx->n_rays - 1) / ctx->chunk_rays * ctx->chunk_rays;
+    if (ray < last0) return ctx->fail(JRB_ERR_STATE, "LOS of this ray was overwritten by a later chunk");
+    ray -= last0;
+    CU(cudaSetDevice(ctx->device));
+    int np = 0;
+    CU(cudaMemcpy(&np, (int *)ctx->d_np.p + last0 + ray, 4, cudaMemcpyDeviceToHost));
+    if (tsurf_out) CU(cudaMemcpy(tsurf_out, (double *)ctx->d_tsurf.p + last0 + ray, 8, cudaMemcpyDeviceToHost));
+    if (np_out) *np_out = np;
+    if (rec_doubles) *rec_doubles = ctx->los.rec;
+    const size_t n = (size_t)np * ctx->los.rec;
+    if (out) {
+      if ((size_t)max_doubles < n) return ctx->fail(JRB_ERR_ARG, "output buffer too small");
+      CU(cudaMemcpy(out, (double *)ctx->d_los.p + (size_t)ray * kNLOS * ctx->los.rec, n * 8, cudaMemcpyDeviceToHost));
+    }
+    return JRB_OK;
+  }
+  CU(cudaSetDevice(ctx->device));
+  int np = 0;
+  CU(cudaMemcpy(&np, (int *)ctx->d_np.p + ray, 4, cudaMemcpyDeviceToHost));
+  if (tsurf_out) CU(cudaMemcpy(tsurf_out, (double *)ctx->d_tsurf.p + ray, 8, cudaMemcpyDeviceToHost));
+  if (np_out) *np_out = np;
+  if (rec_doubles) *rec_doubles = ctx->los.rec;
+  const size_t n = (size_t)np * ctx->los.rec;
+  if (out) {
+    if ((size_t)max_doubles < n) return ctx->fail(JRB_ERR_ARG, "output buffer too small");
+    CU(cudaMemcpy(out, (double *)ctx->d_los.p + (size_t)ray * kNLOS * ctx->los.rec, n * 8, cudaMemcpyDeviceToHost));
+  }
+  return JRB_OK;
+}
+
+int jrb_get_stats(const jrb_context *cctx, jrb_stats *out) {
+  if (!cctx || !out) return JRB_ERR_ARG;
+  jrb_context *ctx = const_cast<jrb_context *>(cctx);
+  std::lock_guard<std::mutex> lk(ctx->mtx);
+  if (ctx->ran && !ctx->np_fetched) {
+    CU(cudaSetDevice(ctx->device));
+    std::vector<int> np((size_t)ctx->n_rays);
+    if (ctx->n_rays > 0) CU(cudaMemcpy(np.data(), ctx->d_np.p, (size_t)ctx->n_rays * 4, cudaMemcpyDeviceToHost));
+    long long s = 0;
+    for (int v : np) s += v;
+    ctx->stats.n_los_points = s;
+    ctx->np_fetched = true;
+  }
+  *out = ctx->stats;
+  return JRB_OK;
+}
+
+} // extern "C"

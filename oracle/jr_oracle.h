@@ -1,0 +1,16 @@
+/* jr_oracle.h -- TEST INFRASTRUCTURE ONLY: interface of the CPU restatement (see jr_oracle.c). */
+#ifndef JR_ORACLE_H
+#define JR_ORACLE_H
+#include <jurassic_b200.h> /* only for the view structs */
+#ifdef __cplusplus
+extern "C" {
+#endif
+/* complete forward model for one package; same semantics as formod_CPU (src/CPUdrivers.c:108-151). 0 on success */
+int jro_formod(const jrb_ctl_view *ctl, const jrb_tbl_view *tbl, const jrb_atm_view *atm, const jrb_obs_view *obs);
+/* ray tracer only; flattened LOS, see jr_oracle.c */
+int jro_traceray(const jrb_ctl_view *ctl, const jrb_atm_view *atm, const jrb_obs_view *obs, int ir, double *out, double *tsurf);
+int jro_max_threads(void);
+#ifdef __cplusplus
+}
+#endif
+#endif
