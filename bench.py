@@ -1,0 +1,423 @@
+#!/usr/bin/env python3
+"""bench.py -- ray*channel radiances per second of the EGA forward model on N B200 GPUs (BASELINE.json metric).
+
+  python bench.py --gpus 1 --steps K --warmup W             our CUDA path (default)
+  python -m torch.distributed.run --nproc-per-node N ... bench.py --gpus N ...   one rank per GPU, weak scaling
+  python bench.py --impl reference ...                      the reference's own CPU path (oracle/_ref) on the host cores
+
+Workload ("config D" of BASELINE.json / SURVEY.md 8d): synthetic limb sounder, packages of 17 profiles x 64 rays
+(1088 rays, the capacity of one obs_t), 32 channels (785..816 cm^-1), 5 gases, CO2+H2O continua; 115 packages per GPU
+(8 GPUs x 115 = 920 packages = 1 000 960 rays, the "1M rays on 8xB200" case).  A step = one pass of the hot path
+(ray tracing -> column densities -> EGA/continua/Planck/accumulation) over the rank's packages.
+
+value : device path, inputs resident in HBM (jrb_run_staged), wall clock over K steps between synchronisations,
+        max over ranks.
+e2e   : the same through the reference-facing call jr_b200_formod_batch(ctl_t*, atm_t*[], obs_t*[]) with HOST structs:
+        packing + H2D + kernels + D2H + scatter inside the timed region (+ the NCCL gather of radiances for N > 1).
+"""
+import argparse
+import copy
+import ctypes as C
+import importlib
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+METRIC = "ray-channel radiances/sec"
+ND_D, NG_D = 32, 5
+
+
+def algorithmic_bytes_per_ray_channel(sbar, ng):
+    """SURVEY.md 8d / BASELINE.md 3:  B = S(ng*176 + 16) + 16"""
+    return sbar * (ng * 176 + 16) + 16
+
+
+def hbm_peak():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        try:
+            return float(json.load(open(p))["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+        except Exception:
+            pass
+    return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons during the timed region"""
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index):
+        self.idx, self.rows, self.proc = gpu_index, [], None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "200",
+                                          "-i", str(self.idx)], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.th = threading.Thread(target=self._read, daemon=True)
+            self.th.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([x.strip() for x in line.split(",")])
+
+    def stop(self):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            self.proc.kill()
+        sm = [float(r[1]) for r in self.rows if len(r) >= 8 and r[1].replace(".", "").isdigit()]
+        mx = [float(r[2]) for r in self.rows if len(r) >= 8 and r[2].replace(".", "").isdigit()]
+        reasons = set()
+        for r in self.rows:
+            if len(r) >= 8:
+                for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), r[4:8]):
+                    if v.lower().startswith("active"):
+                        reasons.add(name)
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+class CudaAlias:
+    """zero-copy torch view of device memory owned by the library (__cuda_array_interface__)"""
+
+    def __init__(self, ptr, nbytes):
+        self.__cuda_array_interface__ = {"shape": (nbytes,), "typestr": "|u1", "data": (ptr, False), "version": 2}
+
+
+def make_packages(jr, ctl, first, count):
+    return [jr.synth.limb_package(ctl, seed=20240517 + first + i) for i in range(count)]
+
+
+def fill_tbl_struct(tbl_t, tbl):
+    buf = (C.c_char * C.sizeof(tbl_t))()
+    t = tbl_t.from_buffer(buf)
+    g, P, T, U, d = tbl.dims
+    for name, idx in (("np", (slice(0, g), slice(0, d))), ("nt", (slice(0, g), slice(0, P), slice(0, d))),
+                      ("nu", (slice(0, g), slice(0, P), slice(0, T), slice(0, d))), ("p", (slice(0, g), slice(0, P), slice(0, d))),
+                      ("t", (slice(0, g), slice(0, P), slice(0, T), slice(0, d))),
+                      ("u", (slice(0, g), slice(0, P), slice(0, T), slice(0, U), slice(0, d))),
+                      ("eps", (slice(0, g), slice(0, P), slice(0, T), slice(0, U), slice(0, d)))):
+        np.ctypeslib.as_array(getattr(t, name))[idx] = getattr(tbl, name)
+    np.ctypeslib.as_array(t.sr)[:, :d] = tbl.sr
+    np.ctypeslib.as_array(t.st)[:] = tbl.st
+    return t, buf
+
+
+def reference_arm(args, jr):
+    """--impl reference: the reference's own CPU implementation (oracle/_ref, unmodified CPUdrivers.c path, OpenMP over
+    all host cores) on a bounded sample of the same workload per step.  Falls back to the C restatement if oracle/_ref
+    was not built."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return 0
+    sys.path.insert(0, os.path.join(ROOT, "oracle"))
+    import refdrv
+    ctl = jr.synth.control_config_d()
+    tbl = jr.synth.make_tables(ctl)
+    npk = args.ref_packages
+    pkgs = make_packages(jr, ctl, 0, npk)
+    if refdrv.reference_available(ND_D, NG_D):
+        ref = refdrv.Reference(ND_D, NG_D)
+        kind, cores = "reference", ref.threads()
+        c = ref.make_ctl(ctl)
+        tstruct, keep = fill_tbl_struct(ref.tbl_t, tbl)
+        atms = [ref.make_atm(p) for p in pkgs]
+        obss = [ref.make_obs(p) for p in pkgs]
+
+        def step():
+            for a, o in zip(atms, obss):
+                ref.formod_tbl(c, a, o, C.addressof(tstruct))
+    else:
+        orc = refdrv.Oracle()
+        kind, cores = "port", orc.threads()
+        work = [copy.deepcopy(p) for p in pkgs]
+
+        def step():
+            for w in work:
+                orc.formod(ctl, tbl, w)
+    for _ in range(args.warmup):
+        step()
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        step()
+    dt = (time.perf_counter() - t0) / args.steps
+    rc = sum(p.n_rays for p in pkgs) * ctl.nd
+    value = rc / dt
+    sample = f"{npk} Config-D package(s) = {rc} ray-channels per step"
+    print(json.dumps({
+        "impl": "reference", "metric": METRIC, "value": value, "unit": "ray-channels/s", "n_gpus": args.gpus, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": dt * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "f64", "data": "synthetic",
+        "config": {"workload": "config D: synthetic limb sounder, 1088-ray packages x 32 channels x 5 gases (bounded CPU sample)",
+                   "packages_per_step": npk},
+        "cpu_baseline": {"value": value, "unit": "ray-channels/s", "cores": cores, "kind": kind, "sample": sample},
+        "e2e": {"value": value, "unit": "ray-channels/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+    }), flush=True)
+    return 0
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--packages", type=int, default=115, help="packages (of 1088 rays) per GPU")
+    ap.add_argument("--ref-packages", type=int, default=2, help="packages per step of the CPU reference arm")
+    ap.add_argument("--cpu-baseline-seconds", type=float, default=15.0)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-e2e", action="store_true")
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 0)
+
+    jr = importlib.import_module("jurassic-gpu_b200")
+    if args.impl == "reference":
+        return reference_arm(args, jr)
+
+    import torch
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if world != args.gpus and world > 1:
+        raise SystemExit(f"--gpus {args.gpus} but WORLD_SIZE={world}")
+    torch.cuda.set_device(local)
+    dist = None
+    if world > 1:
+        import torch.distributed as dist
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+
+    def barrier():
+        torch.cuda.synchronize()
+        if dist:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    ctl = jr.synth.control_config_d()
+    ctx = jr.Context(local)  # raises without the CUDA library / a GPU: there is no fallback
+    ctx.set_control(ctl)
+
+    # ---- tables: packed once on rank 0, broadcast as one blob over NCCL/NVLink ----
+    tbl = None
+    t_tab0 = time.perf_counter()
+    if rank == 0:
+        tbl = jr.synth.make_tables(ctl)
+        ctx.set_tables(tbl)
+    if dist:
+        n = torch.zeros(1, dtype=torch.int64, device="cuda")
+        if rank == 0:
+            ptr, nbytes = ctx.tables_blob()
+            n[0] = nbytes
+        dist.broadcast(n, 0)
+        nbytes = int(n.item())
+        if rank != 0:
+            ptr = ctx.tables_alloc_blob(nbytes)
+        blob = torch.as_tensor(CudaAlias(ptr, nbytes), device=torch.device("cuda", local))
+        dist.broadcast(blob, 0)
+        torch.cuda.synchronize()
+        if rank != 0:
+            ctx.tables_adopt_blob()
+    t_tables = time.perf_counter() - t_tab0
+
+    # ---- this rank's contiguous slice of packages (weak scaling: fixed work per GPU) ----
+    pkgs = make_packages(jr, ctl, rank * args.packages, args.packages)
+    ctx.stage(pkgs)
+    for _ in range(max(args.warmup, 1) if args.warmup else 0):
+        ctx.run_staged()
+    sampler = ClockSampler(local)
+    barrier()
+    sampler.start()
+    ega_ms, rt_ms, launches = [], [], 0
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        ctx.run_staged()  # synchronous: returns after the step's kernels have finished
+        st = ctx.stats()
+        ega_ms.append(st["ms_ega"]); rt_ms.append(st["ms_raytrace"]); launches += st["n_kernel_launches"]
+    barrier()
+    dt = time.perf_counter() - t0
+    clocks = sampler.stop()
+    st = ctx.stats()
+    my_rc, my_rays, my_los = st["n_ray_channels"], st["n_rays"], st["n_los_points"]
+
+    def allmax(x):
+        if not dist:
+            return x
+        t = torch.tensor([x], dtype=torch.float64, device="cuda"); dist.all_reduce(t, op=dist.ReduceOp.MAX); return float(t.item())
+
+    def allsum(x):
+        if not dist:
+            return x
+        t = torch.tensor([x], dtype=torch.float64, device="cuda"); dist.all_reduce(t, op=dist.ReduceOp.SUM); return float(t.item())
+
+    dt = allmax(dt)
+    tot_rc, tot_rays, tot_los = allsum(my_rc), allsum(my_rays), allsum(my_los)
+    ms_per_step = dt / args.steps * 1e3
+    value = tot_rc / (ms_per_step / 1e3)
+
+    # ---- end-to-end through the reference-facing drop-in call, host structs in and out ----
+    e2e = None
+    tstruct = None
+    if not args.no_e2e:
+        lib = C.CDLL(os.path.join(ROOT, "jurassic-gpu_b200", "lib", f"libjurassic_b200_dropin_nd{ND_D}_ng{NG_D}.so"))
+        lib.jr_b200_init.argtypes = [C.c_void_p, C.c_void_p, C.c_int]
+        lib.jr_b200_formod_batch.argtypes = [C.c_void_p, C.POINTER(C.c_void_p), C.POINTER(C.c_void_p), C.c_int]
+        lib.jr_b200_core_context.restype = C.c_void_p
+        sys.path.insert(0, os.path.join(ROOT, "oracle"))
+        ctl_t, atm_t, obs_t, tbl_t = jr.abi.structs(ND_D, NG_D)
+        io = _StructFiller(jr, ctl_t, atm_t, obs_t)
+        c = io.ctl(ctl)
+        c.MPIlocalrank = local
+        if tbl is None:
+            tbl = jr.synth.make_tables(ctl)
+        tstruct, keep = fill_tbl_struct(tbl_t, tbl)
+        lib.jr_b200_init(C.addressof(c), C.addressof(tstruct), local)
+        atms = [io.atm(p) for p in pkgs]
+        obss = [io.obs(p) for p in pkgs]
+        ap_ = (C.c_void_p * len(pkgs))(*[C.addressof(x) for x in atms])
+        op_ = (C.c_void_p * len(pkgs))(*[C.addressof(x) for x in obss])
+        core = C.c_void_p(lib.jr_b200_core_context())
+        gather_buf = None
+
+        def e2e_step():
+            nonlocal gather_buf
+            lib.jr_b200_formod_batch(C.addressof(c), ap_, op_, len(pkgs))
+            if dist:  # radiances/transmittances of all ranks are gathered on rank 0 over NCCL
+                r, t, nr, nd = C.c_void_p(), C.c_void_p(), C.c_longlong(), C.c_int()
+                jr.load_core().jrb_staged_results(core, C.byref(r), C.byref(t), C.byref(nr), C.byref(nd))
+                nb = 2 * nr.value * nd.value * 8  # rad and tau are contiguous in the result buffer
+                mine = torch.as_tensor(CudaAlias(r.value, nb), device=torch.device("cuda", local))
+                if rank == 0 and gather_buf is None:
+                    gather_buf = [torch.empty(nb, dtype=torch.uint8, device="cuda") for _ in range(world)]
+                dist.gather(mine, gather_buf if rank == 0 else None, dst=0)
+                torch.cuda.synchronize()
+
+        for _ in range(min(args.warmup, 2)):
+            e2e_step()
+        barrier()
+        t0 = time.perf_counter()
+        for _ in range(args.steps):
+            e2e_step()
+        barrier()
+        dt_e = allmax(time.perf_counter() - t0)
+        cst = jr.abi.Stats()
+        jr.load_core().jrb_get_stats(core, C.byref(cst))
+        e2e = {"value": tot_rc / (dt_e / args.steps), "unit": "ray-channels/s", "ms_per_step": dt_e / args.steps * 1e3,
+               "h2d_bytes_per_step": int(cst.h2d_bytes), "d2h_bytes_per_step": int(cst.d2h_bytes),
+               "api": "jr_b200_formod_batch(ctl_t*, atm_t*[], obs_t*[], n) with host structs (ND=32, NG=5)"}
+        # spot check: the drop-in's host results equal the device-path results of the first package
+        ctx.fetch_staged(pkgs)
+        got = np.ctypeslib.as_array(obss[0].rad)[: pkgs[0].n_rays, : ctl.nd]
+        if not np.array_equal(got, pkgs[0].rad):
+            raise SystemExit("bench: drop-in results differ from the device path")
+        lib.jr_b200_finalize()
+
+    # ---- roofline of the dominant kernel (EGA) ----
+    sbar = tot_los / max(tot_rays, 1)
+    bytes_rc = algorithmic_bytes_per_ray_channel(sbar, ctl.ng)
+    peak, peak_src = hbm_peak()
+    ega = float(np.mean(ega_ms))
+    achieved = my_rc * bytes_rc / (ega / 1e3) / 1e9
+    traffic = None
+    tp = os.path.join(ROOT, "profiles", "ega_traffic.json")
+    if os.path.exists(tp):
+        try:
+            traffic = json.load(open(tp)).get("dram_bytes_per_launch")
+        except Exception:
+            traffic = None
+    roofline = {"bound": "hbm", "kernel": f"ega_fast_kernel<{st['ega_ngb']},{st['ega_ctm_mask']}>" if st["ega_kernel_variant"] else "ega_generic_kernel",
+                "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": traffic,
+                "peak_source": peak_src, "algorithmic_bytes_per_ray_channel": bytes_rc, "mean_los_points": sbar,
+                "kernel_ms": ega, "raytrace_ms": float(np.mean(rt_ms)), "kernel_share_of_step": ega / ms_per_step}
+
+    # ---- CPU baseline: the reference's own CPU path on the host cores (rank 0, N = 1 only) ----
+    cpu = None
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        sys.path.insert(0, os.path.join(ROOT, "oracle"))
+        import refdrv
+        budget = args.cpu_baseline_seconds
+        sample_pk = make_packages(jr, ctl, 0, 64)
+        if refdrv.reference_available(ND_D, NG_D):
+            ref = refdrv.Reference(ND_D, NG_D)
+            cc = ref.make_ctl(ctl)
+            if tstruct is None:
+                tstruct, keep = fill_tbl_struct(ref.tbl_t, tbl)
+            kind, cores = "reference", ref.threads()
+            run1 = lambda p: ref.formod_tbl(cc, ref.make_atm(p), ref.make_obs(p), C.addressof(tstruct))
+        else:
+            orc = refdrv.Oracle()
+            kind, cores = "port", orc.threads()
+            run1 = lambda p: orc.formod(ctl, tbl, copy.deepcopy(p))
+        run1(sample_pk[0])  # warm-up
+        done, t0 = 0, time.perf_counter()
+        while done < len(sample_pk) and (time.perf_counter() - t0) < budget:
+            run1(sample_pk[done]); done += 1
+        el = time.perf_counter() - t0
+        cpu = {"value": done * 1088 * ctl.nd / el, "unit": "ray-channels/s", "cores": cores, "kind": kind,
+               "sample": f"{done} Config-D packages ({done*1088*ctl.nd} ray-channels) in {el:.1f} s, formod_CPU call sequence, serial ray tracing as in the reference"}
+
+    if rank == 0:
+        out = {"metric": METRIC, "value": value, "unit": "ray-channels/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+               "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64",
+               "data": "synthetic",
+               "config": {"workload": "config D: synthetic limb sounder, 17 profiles x 64 rays per package, 32 channels, 5 gases, CO2+H2O continua",
+                          "packages_per_gpu": args.packages, "rays_per_gpu": int(my_rays), "rays_total": int(tot_rays), "channels": ctl.nd,
+                          "gases": ctl.ng, "l2_policy": "inputs larger than L2 (LOS records rewritten every step: %.1f GB)" % (my_los * 8 * 33 / 1e9),
+                          "parallelism": f"rays sharded over {world} GPU(s), tables broadcast once ({t_tables:.2f} s incl. generation)"},
+               "clocks": clocks, "e2e": e2e, "gpu_launches": int(launches), "roofline": roofline, "cpu_baseline": cpu}
+        print(json.dumps(out), flush=True)
+    ctx.close()
+    if dist:
+        dist.destroy_process_group()
+    return 0
+
+
+class _StructFiller:
+    """host structs of the reference (ctypes mirrors) from the flat containers"""
+
+    def __init__(self, jr, ctl_t, atm_t, obs_t):
+        self.ctl_t, self.atm_t, self.obs_t = ctl_t, atm_t, obs_t
+
+    def ctl(self, ctl):
+        c = self.ctl_t()
+        c.ng, c.nd, c.nw = ctl.ng, ctl.nd, ctl.nw
+        for i, e in enumerate(ctl.emitters):
+            c.emitter[i].value = e.encode()
+        for i in range(ctl.nd):
+            c.nu[i] = ctl.nu[i]; c.window[i] = int(ctl.window[i])
+        c.hydz, c.ctm_co2, c.ctm_h2o, c.ctm_n2, c.ctm_o2 = ctl.hydz, ctl.ctm_co2, ctl.ctm_h2o, ctl.ctm_n2, ctl.ctm_o2
+        c.ip, c.refrac, c.rayds, c.raydz, c.write_bbt, c.formod, c.useGPU = ctl.ip, ctl.refrac, ctl.rayds, ctl.raydz, ctl.write_bbt, ctl.formod, 1
+        return c
+
+    def atm(self, pkg):
+        a = self.atm_t()
+        n = pkg.n_atm
+        a.np = n
+        for name, src in (("time", pkg.atm_time), ("z", pkg.z), ("lon", pkg.lon), ("lat", pkg.lat), ("p", pkg.p), ("t", pkg.t)):
+            np.ctypeslib.as_array(getattr(a, name))[:n] = src
+        np.ctypeslib.as_array(a.q)[: pkg.ng, :n] = pkg.q[: pkg.ng]
+        np.ctypeslib.as_array(a.k)[: pkg.nw, :n] = pkg.k[: pkg.nw]
+        return a
+
+    def obs(self, pkg):
+        o = self.obs_t()
+        n = pkg.n_rays
+        o.nr = n
+        for name in ("time", "obsz", "obslon", "obslat", "vpz", "vplon", "vplat"):
+            np.ctypeslib.as_array(getattr(o, name))[:n] = getattr(pkg, name)
+        return o
+
+
+if __name__ == "__main__":
+    sys.exit(main())

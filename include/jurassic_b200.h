@@ -105,6 +105,9 @@ const char *jrb_last_error(const jrb_context *ctx); /* ctx may be NULL: last err
 int jrb_set_control(jrb_context *ctx, const jrb_ctl_view *ctl);
 /* pack tbl_t into per-(gas,channel) slabs and upload (requires jrb_set_control first) */
 int jrb_set_tables(jrb_context *ctx, const jrb_tbl_view *tbl);
+/* host-only (no GPU needed): properties of the packed form of a table set */
+int jrb_tables_pack_info(const jrb_tbl_view *tbl, int ng, int nd, size_t *nbytes, int *all_shared, int *monotone,
+                         unsigned long long *n_entries);
 /* multi-GPU: the packed slabs are one position-independent device blob that can be broadcast (e.g. NCCL) */
 int jrb_tables_blob(jrb_context *ctx, void **dev_ptr, size_t *nbytes);
 int jrb_tables_alloc_blob(jrb_context *ctx, size_t nbytes, void **dev_ptr); /* receiver side */

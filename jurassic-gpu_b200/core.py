@@ -40,6 +40,9 @@ def load_core():
     lib.jrb_last_error.restype = C.c_char_p
     lib.jrb_set_control.argtypes = [vp, C.POINTER(abi.CtlView)]
     lib.jrb_set_tables.argtypes = [vp, C.POINTER(abi.TblView)]
+    lib.jrb_tables_pack_info.argtypes = [C.POINTER(abi.TblView), C.c_int, C.c_int, C.POINTER(C.c_size_t),
+                                         abi.c_int_p, abi.c_int_p, C.POINTER(C.c_ulonglong)]
+    lib.jrb_tables_pack_info.restype = C.c_int
     lib.jrb_tables_blob.argtypes = [vp, C.POINTER(vp), C.POINTER(C.c_size_t)]
     lib.jrb_tables_alloc_blob.argtypes = [vp, C.c_size_t, C.POINTER(vp)]
     lib.jrb_tables_adopt_blob.argtypes = [vp]
@@ -59,7 +62,7 @@ def load_core():
     return lib
 
 
-EXPORTED_SYMBOLS = ["jrb_version", "jrb_device_count", "jrb_create", "jrb_destroy", "jrb_last_error",
+EXPORTED_SYMBOLS = ["jrb_tables_pack_info", "jrb_version", "jrb_device_count", "jrb_create", "jrb_destroy", "jrb_last_error",
                     "jrb_set_control", "jrb_set_tables", "jrb_tables_blob", "jrb_tables_alloc_blob",
                     "jrb_tables_adopt_blob", "jrb_set_kernel_variant", "jrb_formod_batch", "jrb_stage",
                     "jrb_run_staged", "jrb_fetch_staged", "jrb_staged_results", "jrb_debug_los", "jrb_get_stats"]
@@ -67,6 +70,17 @@ EXPORTED_SYMBOLS = ["jrb_version", "jrb_device_count", "jrb_create", "jrb_destro
 
 def _dp(a):
     return a.ctypes.data_as(abi.c_double_p)
+
+
+def tables_pack_info(tbl, ng, nd):
+    """Host-only: size and properties of the packed device form of `tbl` (works without a GPU)."""
+    lib = load_core()
+    v = tbl.view()
+    n, sh, mo, ne = C.c_size_t(), C.c_int(), C.c_int(), C.c_ulonglong()
+    rc = lib.jrb_tables_pack_info(C.byref(v), ng, nd, C.byref(n), C.byref(sh), C.byref(mo), C.byref(ne))
+    if rc != 0:
+        raise JrbError(f"jrb_tables_pack_info failed ({rc}): {lib.jrb_last_error(None).decode()}")
+    return {"nbytes": n.value, "all_shared": sh.value, "monotone": mo.value, "n_entries": ne.value}
 
 
 # ---------------------------------------------------------------------------------------------------------------

@@ -216,6 +216,23 @@ int jrb_set_tables(jrb_context *ctx, const jrb_tbl_view *tbl) {
   return adopt_blob_locked(ctx);
 }
 
+// host-only: pack and report the properties of the packed form (no GPU needed; used by tests of the packer)
+int jrb_tables_pack_info(const jrb_tbl_view *tbl, int ng, int nd, size_t *nbytes, int *all_shared, int *monotone,
+                         unsigned long long *n_entries) {
+  if (!tbl) return JRB_ERR_ARG;
+  std::vector<unsigned char> blob;
+  std::string err;
+  int rc = pack_tables(*tbl, ng, nd, blob, err);
+  if (rc != JRB_OK) { g_create_error = err; return rc; }
+  TblHeader h;
+  std::memcpy(&h, blob.data(), sizeof(h));
+  if (nbytes) *nbytes = blob.size();
+  if (all_shared) *all_shared = h.all_shared;
+  if (monotone) *monotone = h.monotone;
+  if (n_entries) *n_entries = h.n_entries;
+  return JRB_OK;
+}
+
 int jrb_tables_blob(jrb_context *ctx, void **dev_ptr, size_t *nbytes) {
   if (!ctx || !dev_ptr || !nbytes) return JRB_ERR_ARG;
   std::lock_guard<std::mutex> lk(ctx->mtx);
@@ -372,7 +389,9 @@ int jrb_stage(jrb_context *ctx, int npk, const jrb_atm_view *atm, const jrb_obs_
   // kernel choice + LOS buffer
   const bool fast_ok = ctx->th.all_shared && ctx->th.monotone && ega_fast_available(ng, ctx->ctm_mask);
   if (ctx->variant_req == 1 && !fast_ok)
-    return ctx->fail(JRB_ERR_STATE, "specialised kernel not applicable (channel-dependent axes, non-monotone columns, ng > 8 or mask not built)");
+    return ctx->fail(JRB_ERR_STATE, std::string("specialised kernel not applicable: shared_axes=") + std::to_string(ctx->th.all_shared) +
+                     " monotone=" + std::to_string(ctx->th.monotone) + " ng=" + std::to_string(ng) + " mask=" + std::to_string(ctx->ctm_mask) +
+                     " built=" + std::to_string((int)ega_fast_available(ng, ctx->ctm_mask)));
   ctx->use_fast = (ctx->variant_req == 0) ? 0 : (fast_ok ? 1 : 0);
   ctx->los = make_los_layout(ng, nw, ctx->use_fast);
   const size_t per_ray = (size_t)kNLOS * ctx->los.rec * 8;

@@ -1,0 +1,232 @@
+"""Parity of the CUDA path against the CPU oracle, through the C ABI (include/jurassic_b200.h).  Needs a GPU.
+
+Tolerance (north-star): <= 1e-6 relative on rad and tau in double, with the absolute floors of SURVEY.md section 8c
+for entries below the opaque cut-off; tangent points <= 1e-9 (km / deg).  Observed errors are ~1e-11.
+"""
+import copy
+import os
+
+import numpy as np
+import pytest
+
+from helpers import assert_parity, run_cuda, run_oracle
+
+pytestmark = pytest.mark.gpu
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _both(gpu_ctx_factory, oracle, ctl, tbl, pkgs, what, variants=(1, 0)):
+    ref = run_oracle(oracle, ctl, tbl, pkgs)
+    ctx = gpu_ctx_factory()
+    outs = {}
+    for v in variants:
+        mine = run_cuda(ctx, ctl, tbl, pkgs, v)
+        st = ctx.stats()
+        assert st["ega_kernel_variant"] == v and st["n_kernel_launches"] >= 2
+        for m, r in zip(mine, ref):
+            assert_parity(m, r, f"{what} variant {v}")
+        outs[v] = mine
+    return outs, ref
+
+
+def test_config_a_limb_example(jr, oracle, gpu_ctx_factory):
+    ctl = jr.synth.control_limb_example()
+    outs, ref = _both(gpu_ctx_factory, oracle, ctl, jr.synth.make_tables(ctl), [jr.synth.example_package("limb", ctl)], "A")
+    # the reference's golden geometry columns (example/limb/rad.org)
+    gold = jr.synth.read_tab(os.path.join(ROOT, "tests", "golden", "limb", "rad.org"))
+    assert np.allclose(gold[:, 7], outs[1][0].tpz, rtol=5.1e-6, atol=2e-6)
+    assert np.allclose(gold[:, 9], outs[1][0].tplat, rtol=5.1e-6, atol=2e-6)
+
+
+def test_config_b_nadir_example_bt_and_surface(jr, oracle, gpu_ctx_factory):
+    ctl = jr.synth.control_nadir_example()
+    outs, ref = _both(gpu_ctx_factory, oracle, ctl, jr.synth.make_tables(ctl), [jr.synth.example_package("nadir", ctl)], "B")
+    gold = jr.synth.read_tab(os.path.join(ROOT, "tests", "golden", "nadir", "rad.org"))
+    assert np.allclose(gold[:, 7], outs[1][0].tpz, rtol=5.1e-6, atol=2e-6)
+    assert np.allclose(gold[:, 9], outs[1][0].tplat, rtol=5.1e-6, atol=2e-6)
+
+
+def test_config_c_refspec_shape_30_gases_100_channels(jr, oracle, gpu_ctx_factory):
+    """NG=30, ND=100 (example/refspec shape): more than 8 gases -> generic kernel"""
+    gases = ["CO2", "H2O", "O3", "N2O", "CH4", "CO", "HNO3", "SO2", "F11", "CCl4"] + [f"X{i}" for i in range(20)]
+    ctl = jr.Control(gases, 2150.0 + np.arange(100))  # window with the N2 continuum
+    assert ctl.ctm_mask == 14
+    tbl = jr.synth.make_tables(ctl, skip_pairs=[(g, d) for g in range(10, 30) for d in range(0, 100, 3)])
+    pkg = jr.synth.limb_package(ctl, n_profiles=1, rays_per_profile=6, dz=11.0, seed=5)
+    for ig in range(10, 30):
+        pkg.q[ig, :] = 1e-9
+    _both(gpu_ctx_factory, oracle, ctl, tbl, [pkg], "C", variants=(0,))
+    ctx = gpu_ctx_factory()
+    ctx.set_control(ctl); ctx.set_tables(tbl); ctx.set_kernel_variant(1)
+    with pytest.raises(jr.JrbError, match="not applicable"):
+        ctx.formod_batch([copy.deepcopy(pkg)])
+
+
+def test_config_d_package(jr, oracle, gpu_ctx_factory):
+    """one full Config-D package: 17 profiles x 64 rays x 32 channels x 5 gases"""
+    ctl = jr.synth.control_config_d()
+    tbl = jr.synth.make_tables(ctl)
+    pkg = jr.synth.limb_package(ctl, seed=20240517)
+    outs, ref = _both(gpu_ctx_factory, oracle, ctl, tbl, [pkg], "D", variants=(1,))
+    assert ref[0].tau.min() < 1e-6  # covers opaque rays
+
+
+def test_config_e_slice(jr, oracle, gpu_ctx_factory):
+    """Config-E slice: 128 channels x 8 gases, all four continua, surface term"""
+    ctl = jr.synth.control_config_e()
+    assert ctl.ctm_mask == 15
+    tbl = jr.synth.make_tables(ctl)
+    pkg = jr.synth.nadir_package(ctl, n_profiles=4, rays_per_profile=17, dlat=0.7, seed=20240518)
+    _both(gpu_ctx_factory, oracle, ctl, tbl, [pkg], "E")
+
+
+@pytest.mark.parametrize("bits", range(16))
+def test_all_continuum_switches(jr, oracle, gpu_ctx_factory, bits):
+    ctl = jr.Control(["CO2", "H2O", "O3"], [700.0, 850.5, 1400.0, 1805.0, 2200.0, 2605.0],
+                     ctm_co2=(bits >> 3) & 1, ctm_h2o=(bits >> 2) & 1, ctm_n2=(bits >> 1) & 1, ctm_o2=bits & 1)
+    pkg = jr.synth.nadir_package(ctl, n_profiles=1, rays_per_profile=5, seed=bits)
+    pkg.k[0, :] = 1e-4 * np.exp(-pkg.z / 7.0)
+    _both(gpu_ctx_factory, oracle, ctl, jr.synth.make_tables(ctl), [pkg], f"ctm{bits:04b}")
+
+
+@pytest.mark.parametrize("ng", [1, 2, 3, 4, 6, 7, 8])
+def test_every_gas_count_of_the_specialised_kernel(jr, oracle, gpu_ctx_factory, ng):
+    ctl = jr.Control(jr.synth.NADIR_GASES[:ng], [690.0, 1400.0, 2200.0])
+    pkg = jr.synth.limb_package(ctl, n_profiles=1, rays_per_profile=6, dz=8.0, seed=ng)
+    _both(gpu_ctx_factory, oracle, ctl, jr.synth.make_tables(ctl), [pkg], f"ng{ng}")
+
+
+def test_quirks(jr, oracle, gpu_ctx_factory):
+    """NaN mask, missing tables, no CO2/H2O emitter, T below the table axis, observer inside, rejected rays, ground hit"""
+    ctl = jr.Control(["O3", "F11", "N2O"], [792.0, 832.0, 1000.0, 2300.0])
+    tbl = jr.synth.make_tables(ctl, skip_pairs=[(1, 0), (1, 1), (1, 2), (1, 3), (2, 2)])
+    pkg = jr.synth.limb_package(ctl, n_profiles=2, rays_per_profile=8, dz=9.0, seed=3)
+    pkg.t[:] -= 25.0
+    pkg.obsz[3] = 40.0; pkg.vpz[3] = 10.0; pkg.vplat[3] = 3.0
+    pkg.obsz[4] = -1.0
+    pkg.vpz[5] = 95.0
+    pkg.vpz[6] = -50.0; pkg.vplat[6] = 1.0
+    pkg.rad[2, 1] = np.nan; pkg.rad[9, 0] = np.inf
+    outs, ref = _both(gpu_ctx_factory, oracle, ctl, tbl, [pkg], "quirks")
+    m = outs[1][0]
+    assert np.isnan(m.rad[2, 1]) and np.isnan(m.rad[9, 0])
+    assert np.all(m.rad[4] == 0) and np.all(m.tau[4] == 1) and np.all(m.rad[5] == 0) and np.all(m.tau[5] == 1)
+    assert m.tpz[4] == pkg.vpz[4] and m.tplat[5] == pkg.vplat[5]  # rejected rays keep the view point
+
+
+def test_opaque_cutoff(jr, oracle, gpu_ctx_factory):
+    ctl = jr.synth.control_limb_example()
+    pkg = jr.synth.example_package("limb", ctl)
+    pkg.q[0, :] *= 5000.0
+    pkg.q[2, :] *= 2000.0
+    outs, ref = _both(gpu_ctx_factory, oracle, ctl, jr.synth.make_tables(ctl), [pkg], "opaque")
+    assert ref[0].tau.min() < 1e-9
+
+
+def test_channel_dependent_axes_use_generic_kernel(jr, oracle, gpu_ctx_factory):
+    ctl = jr.synth.control_limb_example()
+    tbl = jr.synth.make_tables(ctl, axis_jitter=True)
+    assert jr.core.tables_pack_info(tbl, ctl.ng, ctl.nd)["all_shared"] == 0
+    pkg = jr.synth.example_package("limb", ctl)
+    ref = run_oracle(oracle, ctl, tbl, [pkg])
+    ctx = gpu_ctx_factory()
+    mine = run_cuda(ctx, ctl, tbl, [pkg], -1)
+    assert ctx.stats()["ega_kernel_variant"] == 0
+    assert_parity(mine[0], ref[0], "jitter")
+
+
+def test_no_refraction_and_extinction_windows(jr, oracle, gpu_ctx_factory):
+    ctl = jr.Control(["CO2", "H2O"], [792.0, 832.0], refrac=0, rayds=5.0, raydz=1.0)
+    pkg = jr.synth.limb_package(ctl, n_profiles=1, rays_per_profile=10, dz=6.0, seed=11)
+    pkg.k[0, :] = 3e-4 * np.exp(-pkg.z / 6.0)
+    _both(gpu_ctx_factory, oracle, ctl, jr.synth.make_tables(ctl), [pkg], "norefrac")
+
+
+def test_hydrostatic_adjustment(jr, oracle, gpu_ctx_factory):
+    ctl = jr.synth.control_limb_example()
+    ctl.hydz = 20.0
+    pkg = jr.synth.example_package("limb", ctl)
+    outs, ref = _both(gpu_ctx_factory, oracle, ctl, jr.synth.make_tables(ctl), [pkg], "hydz", variants=(1,))
+    assert np.allclose(outs[1][0].p, ref[0].p, rtol=1e-14)  # caller's atm->p is updated like on the reference's CPU path
+
+
+def test_los_parity(jr, oracle, gpu_ctx_factory):
+    """T3: per-point LOS of the device ray tracer vs the oracle's traceray"""
+    ctl = jr.synth.control_limb_example()
+    tbl = jr.synth.make_tables(ctl)
+    pkg = jr.synth.example_package("limb", ctl)
+    ctx = gpu_ctx_factory()
+    ctx.set_control(ctl); ctx.set_tables(tbl); ctx.set_kernel_variant(0)
+    ctx.stage([copy.deepcopy(pkg)]); ctx.run_staged()
+    ng, nw = ctl.ng, ctl.nw
+    for ir in (0, 1, 20, 40, 65):
+        los_o, ts_o = oracle.traceray(ctl, copy.deepcopy(pkg), ir)
+        rec, ts = ctx.debug_los(ir)
+        assert rec.shape[0] == los_o.shape[0] and ts == pytest.approx(ts_o, rel=1e-12)
+        u0, z0 = 4 + nw, 4 + nw + ng
+        np.testing.assert_allclose(rec[:, z0:z0 + 3], los_o[:, 0:3], rtol=1e-10, atol=1e-10)       # z, lon, lat
+        np.testing.assert_allclose(rec[:, 0:2], los_o[:, 3:5], rtol=1e-10)                         # p, T
+        ds_o = los_o[:, 5]
+        np.testing.assert_allclose(rec[:, 2], ds_o, rtol=1e-9, atol=1e-12)                         # ds (trapezoid)
+        np.testing.assert_allclose(rec[:, u0:u0 + ng], los_o[:, 6 + nw + ng:], rtol=1e-9)          # column densities
+
+
+def test_batch_equals_loop_and_is_deterministic(jr, oracle, gpu_ctx_factory):
+    """T7: a batch of K packages == K single calls, bit-identical; repeated runs are bit-identical"""
+    ctl = jr.synth.control_config_d(nd=8)
+    tbl = jr.synth.make_tables(ctl)
+    pkgs = [jr.synth.limb_package(ctl, n_profiles=2, rays_per_profile=16, dz=4.0, seed=100 + i) for i in range(5)]
+    ctx = gpu_ctx_factory()
+    batch = run_cuda(ctx, ctl, tbl, pkgs, 1)
+    again = run_cuda(ctx, ctl, tbl, pkgs, 1)
+    for b, a in zip(batch, again):
+        assert np.array_equal(b.rad, a.rad) and np.array_equal(b.tau, a.tau)
+    for i, p in enumerate(pkgs):
+        one = run_cuda(ctx, ctl, tbl, [p], 1)[0]
+        assert np.array_equal(one.rad, batch[i].rad) and np.array_equal(one.tau, batch[i].tau)
+        assert np.array_equal(one.tpz, batch[i].tpz)
+
+
+def test_los_chunking_gives_identical_results(jr, gpu_ctx_factory, monkeypatch):
+    ctl = jr.synth.control_config_d(nd=8)
+    tbl = jr.synth.make_tables(ctl)
+    pkgs = [jr.synth.limb_package(ctl, n_profiles=4, rays_per_profile=64, seed=300 + i) for i in range(6)]
+    ctx = gpu_ctx_factory()
+    full = run_cuda(ctx, ctl, tbl, pkgs, 1)
+    monkeypatch.setenv("JRB_LOS_GB", "0.02")  # forces several LOS chunks (floor: 1024 rays per chunk)
+    ctx2 = gpu_ctx_factory()
+    chunked = run_cuda(ctx2, ctl, tbl, pkgs, 1)
+    assert ctx2.stats()["n_kernel_launches"] > ctx.stats()["n_kernel_launches"]
+    for a, b in zip(full, chunked):
+        assert np.array_equal(a.rad, b.rad) and np.array_equal(a.tau, b.tau)
+
+
+def test_large_batch_properties(jr, oracle, gpu_ctx_factory):
+    """Size-independent properties at a bench-like size (32 Config-D packages = 34 816 rays x 32 channels):
+    duplicated packages give bit-identical results wherever they sit in the batch, tau in [0,1], rad >= 0,
+    and a sample of rays agrees with the oracle."""
+    ctl = jr.synth.control_config_d()
+    tbl = jr.synth.make_tables(ctl)
+    base = [jr.synth.limb_package(ctl, seed=20240517 + i) for i in range(16)]
+    pkgs = base + [copy.deepcopy(p) for p in reversed(base)]
+    ctx = gpu_ctx_factory()
+    out = run_cuda(ctx, ctl, tbl, pkgs, -1)
+    st = ctx.stats()
+    assert st["ega_kernel_variant"] == 1 and st["n_rays"] == 32 * 1088
+    for i in range(16):
+        assert np.array_equal(out[i].rad, out[31 - i].rad) and np.array_equal(out[i].tau, out[31 - i].tau)
+    allrad = np.concatenate([o.rad for o in out]); alltau = np.concatenate([o.tau for o in out])
+    assert np.all(np.isfinite(allrad)) and np.all(allrad >= 0) and np.all((alltau >= 0) & (alltau <= 1))
+    # sample: 24 rays of package 7 through the oracle
+    sub = copy.deepcopy(base[7])
+    idx = np.arange(0, 1088, 46)
+    small = jr.Package(ctl.ng, ctl.nw, ctl.nd, sub.n_atm, idx.size)
+    for name in ("atm_time", "z", "lon", "lat", "p", "t", "q", "k"):
+        getattr(small, name)[...] = getattr(sub, name)
+    for name in ("time", "obsz", "obslon", "obslat", "vpz", "vplon", "vplat"):
+        getattr(small, name)[:] = getattr(sub, name)[idx]
+    oracle.formod(ctl, tbl, small)
+    got = jr.Package(ctl.ng, ctl.nw, ctl.nd, sub.n_atm, idx.size)
+    for name in ("rad", "tau", "tpz", "tplon", "tplat"):
+        getattr(got, name)[...] = getattr(out[7], name)[idx]
+    assert_parity(got, small, "large batch sample")

@@ -1,0 +1,178 @@
+"""Pins the CPU oracle (oracle/jr_oracle.c) -- CPU-only tests.
+
+1. against the reference's golden files example/{limb,nadir}/rad.org (geometry columns; the radiance columns need
+   emissivity tables that are missing from the reference checkout);
+2. against the reference itself: oracle/_ref/libjurassic_ref_nd*_ng*.so is the reference's jurassic.c + CPUdrivers.c
+   compiled unmodified (oracle/Makefile).  The restatement reproduces it bit for bit on the cases below.
+Tests of kind 2 are skipped where oracle/_ref was not built (it needs /root/reference at build time).
+"""
+import copy
+import os
+
+import numpy as np
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+# ---- 1. golden vectors -----------------------------------------------------------------------------------------
+@pytest.mark.parametrize("case", ["limb", "nadir"])
+def test_oracle_tangent_points_match_golden_rad_org(jr, oracle, case):
+    synth = jr.synth
+    ctl = synth.control_limb_example() if case == "limb" else synth.control_nadir_example()
+    tbl = synth.make_tables(ctl)
+    pkg = synth.example_package(case, ctl)
+    oracle.formod(ctl, tbl, pkg)
+    gold = synth.read_tab(os.path.join(ROOT, "tests", "golden", case, "rad.org"))
+    assert gold.shape[0] == pkg.n_rays == (66 if case == "limb" else 90)
+    # columns 1-7 are the inputs, 8-10 the tangent point; rad.org holds 6 significant digits ("%g")
+    for col, mine in ((0, pkg.time), (1, pkg.obsz), (4, pkg.vpz), (6, pkg.vplat)):
+        assert np.allclose(gold[:, col], mine, rtol=5.1e-6, atol=1e-12)
+    assert np.allclose(gold[:, 7], pkg.tpz, rtol=5.1e-6, atol=2e-6), "tangent altitude"
+    assert np.allclose(gold[:, 9], pkg.tplat, rtol=5.1e-6, atol=2e-6), "tangent latitude"
+    assert np.all(np.abs(gold[:, 8] - pkg.tplon) < 2e-6), "tangent longitude (round-off level values)"
+
+
+# ---- 2. the reference itself ---------------------------------------------------------------------------------------
+def _ref_run(refdrv, ND, NG, ctl, tbl, pkg):
+    ref = refdrv.Reference(ND, NG)
+    c, a, o = ref.make_ctl(ctl), ref.make_atm(pkg), ref.make_obs(pkg)
+    tp = ref.make_tbl(tbl)
+    ref.formod_tbl(c, a, o, tp)
+    out = copy.deepcopy(pkg)
+    full_rad, full_tau = ref.read_obs(o, out)
+    out.p[:] = np.ctypeslib.as_array(a.p)[: pkg.n_atm]
+    ref.free_tbl(tp)
+    return out, full_rad, full_tau
+
+
+def _need(refdrv, ND, NG):
+    if not refdrv.reference_available(ND, NG):
+        pytest.skip("oracle/_ref not built (needs /root/reference at build time)")
+
+
+def _same(a, b, what):
+    assert np.array_equal(np.isnan(a), np.isnan(b)), what
+    m = ~np.isnan(b)
+    assert np.array_equal(a[m], b[m]), f"{what}: max rel diff {np.max(np.abs(a[m]-b[m])/(np.abs(b[m])+1e-300)):.3e}"
+
+
+def _compare(oracle, refdrv, ND, NG, ctl, tbl, pkg, what):
+    _need(refdrv, ND, NG)
+    r, full_rad, full_tau = _ref_run(refdrv, ND, NG, ctl, tbl, pkg)
+    o = copy.deepcopy(pkg)
+    oracle.formod(ctl, tbl, o)
+    for name in ("rad", "tau", "tpz", "tplon", "tplat", "p"):
+        _same(getattr(o, name), getattr(r, name), f"{what}:{name}")
+    # all ND columns are reset by the reference, not only nd (Appendix D #1)
+    assert np.all(full_rad[:, ctl.nd:] == 0.0) and np.all(full_tau[:, ctl.nd:] == 1.0)
+    return o
+
+
+def test_oracle_equals_reference_limb_example(jr, oracle, refdrv):
+    ctl = jr.synth.control_limb_example()
+    o = _compare(oracle, refdrv, 2, 5, ctl, jr.synth.make_tables(ctl), jr.synth.example_package("limb", ctl), "limb")
+    assert o.rad.min() > 0 and 0 <= o.tau.min() and o.tau.max() <= 1
+
+
+def test_oracle_equals_reference_nadir_example_bt_and_surface(jr, oracle, refdrv):
+    ctl = jr.synth.control_nadir_example()
+    o = _compare(oracle, refdrv, 3, 1, ctl, jr.synth.make_tables(ctl), jr.synth.example_package("nadir", ctl), "nadir")
+    assert 150 < o.rad.min() and o.rad.max() < 350  # brightness temperatures [K]
+
+
+def test_oracle_equals_reference_config_d_slice(jr, oracle, refdrv):
+    ctl = jr.synth.control_config_d()
+    pkg = jr.synth.limb_package(ctl, n_profiles=2, rays_per_profile=12, dz=5.0, seed=7)
+    _compare(oracle, refdrv, 32, 5, ctl, jr.synth.make_tables(ctl), pkg, "D")
+
+
+@pytest.mark.parametrize("bits", range(16))
+def test_oracle_equals_reference_all_continuum_switches(jr, oracle, refdrv, bits):
+    """the 16 variants of src/jr_multiversion4gases.h; channels cover every continuum's range"""
+    ctl = jr.Control(["CO2", "H2O", "O3"], [700.0, 850.5, 1400.0, 1805.0, 2200.0, 2605.0],
+                     ctm_co2=(bits >> 3) & 1, ctm_h2o=(bits >> 2) & 1, ctm_n2=(bits >> 1) & 1, ctm_o2=bits & 1)
+    assert ctl.ctm_mask == bits
+    pkg = jr.synth.nadir_package(ctl, n_profiles=1, rays_per_profile=3, seed=bits)
+    pkg.k[0, :] = 1e-4 * np.exp(-pkg.z / 7.0)  # aerosol extinction
+    _compare(oracle, refdrv, 8, 3, ctl, jr.synth.make_tables(ctl), pkg, f"ctm{bits:04b}")
+
+
+def test_oracle_equals_reference_quirks(jr, oracle, refdrv):
+    """NaN mask, missing tables, gas list without CO2/H2O, T outside the table axis, observer inside the atmosphere,
+    rejected rays (Appendix D #1-6, #16)"""
+    ctl = jr.Control(["O3", "F11", "N2O"], [792.0, 832.0, 1000.0, 2300.0])  # no CO2/H2O emitter -> only N2 continuum
+    assert ctl.ctm_mask == 2
+    tbl = jr.synth.make_tables(ctl, skip_pairs=[(1, 0), (1, 1), (1, 2), (1, 3), (2, 2)])
+    pkg = jr.synth.limb_package(ctl, n_profiles=2, rays_per_profile=8, dz=9.0, seed=3)
+    pkg.t[:] -= 25.0                      # far below the table's T axis (180 K) at altitude: extrapolate + clamp
+    pkg.obsz[3] = 40.0; pkg.vpz[3] = 10.0; pkg.vplat[3] = 3.0   # observer inside the atmosphere
+    pkg.obsz[4] = -1.0                    # observer below the lowest level -> np = 0
+    pkg.vpz[5] = 95.0                     # view point above the atmosphere -> np = 0
+    pkg.vpz[6] = -50.0; pkg.vplat[6] = 1.0  # steep ray into the ground (surface term)
+    pkg.rad[2, 1] = np.nan; pkg.rad[9, 0] = np.inf
+    o = _compare(oracle, refdrv, 8, 3, ctl, tbl, pkg, "quirks")
+    assert np.isnan(o.rad[2, 1]) and np.isnan(o.rad[9, 0])
+    assert np.all(o.rad[4] == 0) and np.all(o.tau[4] == 1) and np.all(o.rad[5] == 0)
+
+
+def test_oracle_equals_reference_opaque_cutoff(jr, oracle, refdrv):
+    """strong absorbers: tau_path < 1e-9 -> factor 0, tau_gas <= 1e-50 freezes the ray (Appendix D #2, #3)"""
+    ctl = jr.synth.control_limb_example()
+    tbl = jr.synth.make_tables(ctl)
+    pkg = jr.synth.example_package("limb", ctl)
+    pkg.q[0, :] *= 5000.0
+    pkg.q[2, :] *= 2000.0
+    o = _compare(oracle, refdrv, 2, 5, ctl, tbl, pkg, "opaque")
+    assert o.tau.min() < 1e-9
+
+
+def test_oracle_equals_reference_hydrostatic(jr, oracle, refdrv):
+    ctl = jr.synth.control_limb_example()
+    ctl.hydz = 20.0
+    pkg = jr.synth.example_package("limb", ctl)
+    p_before = pkg.p.copy()
+    o = _compare(oracle, refdrv, 2, 5, ctl, jr.synth.make_tables(ctl), pkg, "hydz")
+    assert not np.array_equal(o.p, p_before) and o.p[20] == p_before[20]
+
+
+def test_reference_formod_with_ascii_tables_equals_oracle(jr, oracle, refdrv, tmp_path):
+    """the unmodified entry point formod() with tables loaded by the reference's own init_tbl from ASCII files"""
+    _need(refdrv, 2, 5)
+    ctl = jr.synth.control_limb_example()
+    tbl = jr.synth.make_tables(ctl)
+    ctl.tblbase = jr.synth.write_ascii_tables(ctl, tbl, str(tmp_path), "boxcar")
+    pkg = jr.synth.example_package("limb", ctl)
+    ref = refdrv.Reference(2, 5)
+    c, a, o = ref.make_ctl(ctl), ref.make_atm(pkg), ref.make_obs(pkg)
+    ref.formod(c, a, o)  # formod -> formod_CPU -> get_tbl -> init_tbl
+    r = copy.deepcopy(pkg)
+    ref.read_obs(o, r)
+    # tables as parsed by the reference == tables as generated (float32 payload exact; sr within summation round-off)
+    t = ref.tbl_t.from_address(ref.lib.jrref_get_tbl(__import__("ctypes").addressof(c)))
+    assert np.array_equal(np.ctypeslib.as_array(t.nu)[:5, :36, :12, :2], tbl.nu)
+    # (get_tbl mallocs tbl_t without zeroing it, Appendix D #13: compare the populated entries only)
+    pop = np.arange(200)[None, None, None, :, None] < tbl.nu[:, :, :, None, :]
+    assert np.array_equal(np.ctypeslib.as_array(t.eps)[:5, :36, :12, :200, :2][pop], tbl.eps[pop])
+    assert np.array_equal(np.ctypeslib.as_array(t.u)[:5, :36, :12, :200, :2][pop], tbl.u[pop])
+    assert np.allclose(np.ctypeslib.as_array(t.sr)[:, :2], tbl.sr, rtol=1e-13)
+    mine = copy.deepcopy(pkg)
+    oracle.formod(ctl, tbl, mine)
+    assert np.allclose(mine.rad, r.rad, rtol=1e-12) and np.allclose(mine.tau, r.tau, rtol=1e-12)
+    assert np.array_equal(mine.tpz, r.tpz)
+
+
+def test_oracle_traceray_equals_reference(jr, oracle, refdrv):
+    """LOS parity (T3): per-point z, lon, lat, p, T, ds, k, q, u and np, tsurf"""
+    _need(refdrv, 2, 5)
+    ctl = jr.synth.control_limb_example()
+    for refrac in (1, 0):
+        ctl.refrac = refrac
+        pkg = jr.synth.example_package("limb", ctl)
+        ref = refdrv.Reference(2, 5)
+        c, a, o = ref.make_ctl(ctl), ref.make_atm(pkg), ref.make_obs(pkg)
+        for ir in (0, 10, 37, 65):
+            los_r, ts_r = ref.traceray(c, a, o, ir, ctl.ng)
+            los_o, ts_o = oracle.traceray(ctl, copy.deepcopy(pkg), ir)
+            assert los_r.shape == los_o.shape and ts_r == ts_o
+            assert np.array_equal(los_r, los_o)
