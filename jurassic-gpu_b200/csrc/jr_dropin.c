@@ -9,6 +9,7 @@
 #include <jurassic_b200.h>
 #include <jurassic_b200_dropin.h>
 
+#include <dlfcn.h>
 #include <pthread.h>
 #include <stdio.h>
 #include <stdlib.h>
@@ -17,6 +18,13 @@
 
 /* provided by the reference's CPUdrivers.o when linked into a JURASSIC executable (src/jr_common.h:60-78) */
 extern tbl_t *get_tbl(ctl_t const *ctl) __attribute__((weak));
+typedef tbl_t *(*get_tbl_fn)(ctl_t const *);
+
+/* link-time weak reference first, then a run-time lookup (the reference objects may be loaded after this library) */
+static get_tbl_fn find_get_tbl(void) {
+  if (get_tbl) return get_tbl;
+  return (get_tbl_fn)dlsym(RTLD_DEFAULT, "get_tbl");
+}
 
 #define JR_FATAL(msg)                                                                          \
   do {                                                                                         \
@@ -106,8 +114,9 @@ void jr_b200_formod_batch(ctl_t const *ctl, atm_t *const atm[], obs_t *const obs
   if (npackages <= 0) return;
   pthread_mutex_lock(&g_lock); /* concurrent callers (OpenMP host threads of a retrieval) are serialised */
   if (!g_have_tables) {
-    if (!get_tbl) JR_FATAL("tables not initialised: call jr_b200_init() or link the reference's get_tbl()");
-    init_locked(ctl, get_tbl(ctl), -1);
+    get_tbl_fn const gt = find_get_tbl();
+    if (!gt) JR_FATAL("tables not initialised: call jr_b200_init() or link the reference's get_tbl()");
+    init_locked(ctl, gt(ctl), -1);
   } else {
     push_control(ctl);
   }

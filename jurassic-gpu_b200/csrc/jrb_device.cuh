@@ -90,7 +90,7 @@ __host__ __device__ inline LosLayout make_los_layout(int ng, int nw, int fast) {
   L.u0 = 4 + nw;
   L.c0 = L.u0 + ng;
   L.z0 = L.c0 + (fast ? 4 * ng : 0);
-  L.rec = L.z0 + 3;
+  L.rec = (L.z0 + 3 + 1) & ~1; // even number of doubles: records are 16-byte multiples (TMA bulk copies)
   return L;
 }
 constexpr unsigned kCellInvalid = 0xffffffffu; // "no usable table cell -> gas factor 1"

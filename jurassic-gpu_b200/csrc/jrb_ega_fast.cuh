@@ -1,23 +1,67 @@
-// jrb_ega_fast.cuh -- specialised EGA kernels, template <NGB gases held in registers, continuum MASK>.
+// jrb_ega_fast.cuh -- specialised EGA kernels, template <continuum MASK> (the 16 variants the reference stamps out
+// with src/jr_multiversion4gases.h are template instantiations here).
 //
-// Mapping: one warp = one ray x 32 consecutive channels (lane = channel).  The LOS record of a segment is read as a
-// warp-uniform broadcast; per-gas path transmittances tau_path[NGB] live in registers for the whole ray
-// (the reference keeps tau_path[NG] in local memory, src/jr_fusion_kernel.mv4g.cu:6,12-14); rad/tau are
-// accumulated in registers and stored once (the reference read-modify-writes obs_t in global memory every
-// segment, src/jr_common.h:293-300).  The 16 continuum variants of src/jr_multiversion4gases.h are the MASK
-// template parameter.  Warps fetch rays from a global work counter, so rays of different length (130..393
-// segments) balance themselves.
+// Mapping: one warp = one ray x 32 consecutive channels (lane = channel); warps fetch rays from a global work
+// counter so that rays of different length (130..393 segments) balance themselves.
 //
-// Search-free table access: every (gas, column-slot) keeps the bracket index it ended on in the previous segment
-// as a 16-bit hint.  The next lookup loads that bracket first (one aligned 16-byte load) and only walks / bisects
-// when the hint is off.  For monotone columns the index found is identical to the reference's full bisection
-// (locate_tbl_id, src/jr_common.h:116-125), so results do not depend on the hints.
+// Data movement per segment:
+//   * the ray's LOS record (p, T, ds, per-gas u / table cell / interpolation weights; <= 272 B for 5 gases) is staged
+//     into shared memory by a TMA bulk copy (cp.async.bulk + mbarrier, double buffered per warp): segment ip+1 is in
+//     flight while segment ip is computed, and every lane reads the fields as shared-memory broadcasts;
+//   * per gas, the four column descriptors are read coalesced (channel innermost), then the four hinted brackets
+//     (one aligned 16-byte load each) are issued back to back so their L2 latencies overlap.
+// State: the along-ray recurrence (rad, tau) lives in registers and is stored once per ray; the per-gas path
+// transmittances tau_path[ng] and the bracket hints live in shared memory ([gas][thread], conflict free) so that the
+// gas loop stays rolled -- an unrolled body was > 100 KB of SASS and stalled on instruction fetch (profiles/).
+//
+// Search-free table access: every (gas, column slot) keeps the bracket index it ended on in the previous segment as a
+// 16-bit hint.  The next lookup loads that bracket first and only steps / bisects when the hint is off.  For monotone
+// columns the index found equals the reference's full bisection (locate_tbl_id, src/jr_common.h:116-125), so results
+// do not depend on the hints.
 #pragma once
 #include "jrb_ega_common.cuh"
 
 namespace jrb {
 
 namespace fast {
+
+// ---- mbarrier / TMA bulk copy (PTX) -----------------------------------------------------------------------------
+__device__ __forceinline__ unsigned smem_addr(const void *p) { return (unsigned)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(unsigned long long *bar, unsigned count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_addr(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(unsigned long long *bar, unsigned bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_addr(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(unsigned long long *bar, unsigned parity) {
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "WAIT_LOOP:\n"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+      "@p bra DONE;\n"
+      "bra WAIT_LOOP;\n"
+      "DONE:\n"
+      "}\n" ::"r"(smem_addr(bar)), "r"(parity)
+      : "memory");
+}
+// global -> shared bulk copy executed by the TMA unit; completion is signalled on `bar` (SASS: UBLKCP)
+__device__ __forceinline__ void tma_load_1d(void *dst_smem, const void *src_gmem, unsigned bytes, unsigned long long *bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_addr(dst_smem)),
+               "l"(src_gmem), "r"(bytes), "r"(smem_addr(bar))
+               : "memory");
+}
+
+// ---- bracket search ------------------------------------------------------------------------------------------------
+// slow path, shared by all call sites: reference bisection restricted to [ilo, ihi]
+static __device__ __noinline__ int search_range(const float4 *__restrict__ col, int ilo, int ihi, const double x, const int on_eps) {
+  while (ihi > ilo + 1) {
+    const int i = (ihi + ilo) >> 1;
+    const float v = on_eps ? col[i].y : col[i].x;
+    if ((double)v > x) ihi = i; else ilo = i;
+  }
+  return ilo;
+}
 
 template <bool ON_EPS>
 __device__ __forceinline__ float lo_of(const float4 b) { return ON_EPS ? b.y : b.x; }
@@ -26,144 +70,164 @@ __device__ __forceinline__ float hi_of(const float4 b) { return ON_EPS ? b.w : b
 
 // Move (k, b) so that  val[k] <= x < val[k+1]  with k clipped to [0, nu-2]  (== reference bisection result).
 template <bool ON_EPS>
-__device__ __forceinline__ void relocate(const float4 *__restrict__ col, const int nu, const double x, int &k,
-                                         float4 &b) {
+__device__ __forceinline__ void relocate(const float4 *__restrict__ col, const int nu, const double x, int &k, float4 &b) {
   if (x < (double)lo_of<ON_EPS>(b)) {
-    if (k == 0) return;
-    int steps = 0;
-    do { --k; b = col[k]; ++steps; } while (k > 0 && x < (double)lo_of<ON_EPS>(b) && steps < 2);
-    if (k > 0 && x < (double)lo_of<ON_EPS>(b)) {
-      int ilo = 0, ihi = k;
-      while (ihi > ilo + 1) {
-        const int i = (ihi + ilo) >> 1;
-        const float v = ON_EPS ? col[i].y : col[i].x;
-        if ((double)v > x) ihi = i; else ilo = i;
-      }
-      k = ilo; b = col[k];
+    if (k > 0) {
+      --k; b = col[k];
+      if (k > 0 && x < (double)lo_of<ON_EPS>(b)) { k = search_range(col, 0, k, x, ON_EPS); b = col[k]; }
     }
   } else if (x >= (double)hi_of<ON_EPS>(b)) {
-    if (k >= nu - 2) return;
-    int steps = 0;
-    do { ++k; b = col[k]; ++steps; } while (k < nu - 2 && x >= (double)hi_of<ON_EPS>(b) && steps < 2);
-    if (k < nu - 2 && x >= (double)hi_of<ON_EPS>(b)) {
-      int ilo = k, ihi = nu - 1;
-      while (ihi > ilo + 1) {
-        const int i = (ihi + ilo) >> 1;
-        const float v = ON_EPS ? col[i].y : col[i].x;
-        if ((double)v > x) ihi = i; else ilo = i;
-      }
-      k = ilo; b = col[k];
+    if (k < nu - 2) {
+      ++k; b = col[k];
+      if (k < nu - 2 && x >= (double)hi_of<ON_EPS>(b)) { k = search_range(col, k, nu - 1, x, ON_EPS); b = col[k]; }
     }
   }
 }
 
-// One table column of the EGA step: u* = u(eps) (get_u, may extrapolate), then eps(u* + u_seg) clamped to [0,1]
-// (get_eps + c01, src/jr_common.h:249-257).  `hint` is updated to the bracket the lookup ended on.
-__device__ __forceinline__ double column_step(const float4 *__restrict__ brk, const uint2 c, const double eps,
-                                              const double useg, unsigned &hint) {
-  const float4 *__restrict__ col = brk + c.x;
-  const int nu = (int)c.y;
-  int k = min((int)hint, nu - 2);
-  float4 b = col[k];
+// One table column of the EGA step, starting from the prefetched bracket (k, b):
+// u* = u(eps) (get_u, may extrapolate), then eps(u* + u_seg) clamped to [0,1] (get_eps + c01, src/jr_common.h:249-257).
+__device__ __forceinline__ double column_finish(const float4 *__restrict__ col, const int nu, const double eps, const double useg,
+                                                int &k, float4 b) {
   relocate<true>(col, nu, eps, k, b);
   const double ustar = lerp_fast((double)b.y, (double)b.x, (double)b.w, (double)b.z, eps);
   const double x = ustar + useg;
   relocate<false>(col, nu, x, k, b);
-  hint = (unsigned)k;
   return clamp01(lerp_fast((double)b.x, (double)b.y, (double)b.z, (double)b.w, x));
 }
 
 } // namespace fast
 
-template <int NGB, int MASK>
-__global__ void __launch_bounds__(256, 2) ega_fast_kernel(const EgaArgs a) {
-  const int lane = threadIdx.x & 31;
-  const int ngroups = (a.nd + 31) >> 5;
-  const unsigned long long n_items = (unsigned long long)a.n_rays * ngroups;
+constexpr int kEgaBlock = 256;
+#ifndef JRB_EGA_MINBLOCKS
+#define JRB_EGA_MINBLOCKS 3 // CTAs per SM the register allocation must allow (3 x 8 warps; measured best, see profiles/)
+#endif
+
+__host__ __device__ inline size_t ega_fast_smem_bytes(int ng, int rec, int threads) {
+  const int nwarps = threads / 32;
+  return (size_t)nwarps * 2 * 8            // mbarriers
+         + (size_t)nwarps * 2 * rec * 8    // LOS record double buffers
+         + (size_t)ng * threads * 16;      // tau_path + hints
+}
+
+template <int MASK>
+__global__ void __launch_bounds__(kEgaBlock, JRB_EGA_MINBLOCKS) ega_fast_kernel(const EgaArgs a) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, nwarps = blockDim.x >> 5;
   const LosLayout L = a.los;
   const TblDev &T = a.tbl;
-  const int nd = a.nd;
+  const int nd = a.nd, ng = a.ng;
+  const unsigned rec_bytes = (unsigned)L.rec * 8u;
+
+  unsigned long long *bars = reinterpret_cast<unsigned long long *>(smem_raw) + warp * 2;
+  double *recbuf = reinterpret_cast<double *>(smem_raw + (size_t)nwarps * 16) + (size_t)warp * 2 * L.rec;
+  double *tau_s = reinterpret_cast<double *>(smem_raw + (size_t)nwarps * 16 + (size_t)nwarps * 2 * L.rec * 8) + tid;
+  unsigned long long *hint_s = reinterpret_cast<unsigned long long *>(tau_s - tid + (size_t)ng * blockDim.x) + tid;
+  const int sstride = blockDim.x;
+
+  if (lane == 0) { fast::mbar_init(&bars[0], 1); fast::mbar_init(&bars[1], 1); }
+  asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  __syncthreads();
+  unsigned parity0 = 0, parity1 = 0;
+
+  const int ngroups = (nd + 31) >> 5;
+  const unsigned long long n_items = (unsigned long long)a.n_rays * ngroups;
 
   for (;;) {
     unsigned long long item = 0;
     if (lane == 0) item = atomicAdd(a.work_counter, 1ull);
     item = __shfl_sync(0xffffffffu, item, 0);
     if (item >= n_items) break;
-    const long long ir = (long long)(item / ngroups);
-    const int grp = (int)(item - (unsigned long long)ir * ngroups);
+    // channel-group major: all warps in flight work on the same 32 channels, so the part of the tables that is hot
+    // at any time is (32 channels x ng gases), which is what has to fit into L2
+    const int grp = (int)(item / (unsigned long long)a.n_rays);
+    const long long ir = (long long)(item - (unsigned long long)grp * (unsigned long long)a.n_rays);
     const int id_raw = grp * 32 + lane;
     const bool lane_on = id_raw < nd;
     const int id = lane_on ? id_raw : nd - 1;
 
-    const double *__restrict__ rec = a.los_data + (size_t)ir * kNLOS * L.rec;
+    const double *__restrict__ rec_g = a.los_data + (size_t)ir * kNLOS * L.rec;
     const int np = a.ray_np[ir];
     const int win = a.window[id];
 
-    unsigned valid = 0; // bit ig: this (gas, channel) pair has a table (np >= 2)
-#pragma unroll
-    for (int ig = 0; ig < NGB; ig++)
-      if (ig < a.ng && T.np[ig * nd + id] >= 2) valid |= 1u << ig;
-
-    double tau_path[NGB];
-    unsigned h01[NGB], h23[NGB];
-#pragma unroll
-    for (int ig = 0; ig < NGB; ig++) { tau_path[ig] = 1.0; h01[ig] = 0; h23[ig] = 0; }
+    for (int ig = 0; ig < ng; ig++) {
+      // a (gas, channel) pair without table (np < 2) contributes the factor 1 (src/jr_common.h:240): hint = all ones
+      tau_s[ig * sstride] = 1.0;
+      hint_s[ig * sstride] = (T.np[ig * nd + id] >= 2) ? 0ull : ~0ull;
+    }
     double rad = 0.0, tau = 1.0;
     bool dead = false; // a gas went opaque (tau_path < 1e-9): nothing changes any more (src/jr_common.h:239,295)
 
-    for (int ip = 0; ip < np; ++ip, rec += L.rec) {
-      if (__all_sync(0xffffffffu, dead)) break;
+    __syncwarp();
+    if (np > 0 && lane == 0) {
+      fast::mbar_expect_tx(&bars[0], rec_bytes);
+      fast::tma_load_1d(recbuf, rec_g, rec_bytes, &bars[0]);
+    }
+    for (int ip = 0; ip < np; ++ip) {
+      const int b = ip & 1;
+      __syncwarp(); // every lane is done with the other buffer (segment ip-1)
+      const bool all_dead = __all_sync(0xffffffffu, dead);
+      if ((ip + 1 < np) && !all_dead && lane == 0) { // segment ip+1 travels while segment ip is computed
+        fast::mbar_expect_tx(&bars[b ^ 1], rec_bytes);
+        fast::tma_load_1d(recbuf + (size_t)(b ^ 1) * L.rec, rec_g + (size_t)(ip + 1) * L.rec, rec_bytes, &bars[b ^ 1]);
+      }
+      // the copy of segment ip is always in flight here (issued above one iteration earlier, or before the loop)
+      if (b == 0) { fast::mbar_wait(&bars[0], parity0); parity0 ^= 1; } else { fast::mbar_wait(&bars[1], parity1); parity1 ^= 1; }
+      if (all_dead) break; // nothing further was requested
       if (dead) continue;
-      const double p = rec[0], t = rec[1], ds = rec[2];
-      const double u_co2 = (MASK & 8) ? rec[L.u0 + a.ig_co2] : 0.0;
-      const double u_h2o = (MASK & 4) ? rec[L.u0 + a.ig_h2o] : 0.0;
-      const double beta_ds = continuum_beta_ds(MASK, a.chan, nd, id, p, t, ds, rec[4 + win], u_co2, u_h2o, rec[3]);
+
+      const double *__restrict__ R = recbuf + (size_t)b * L.rec;
+      const double p = R[0], t = R[1], ds = R[2];
+      const double u_co2 = (MASK & 8) ? R[L.u0 + a.ig_co2] : 0.0;
+      const double u_h2o = (MASK & 4) ? R[L.u0 + a.ig_h2o] : 0.0;
+      const double beta_ds = continuum_beta_ds(MASK, a.chan, nd, id, p, t, ds, R[4 + win], u_co2, u_h2o, R[3]);
 
       double tau_gas = 1.0;
-#pragma unroll
-      for (int ig = 0; ig < NGB; ig++) {
-        if (ig < a.ng) {
-          double f;
-          const double tp = tau_path[ig];
-          if (tp < 1e-9) {
-            f = 0.0;
-          } else {
-            f = 1.0;
-            const double *__restrict__ cw = rec + L.c0 + 4 * ig;
-            const unsigned cell = (unsigned)__double_as_longlong(cw[3]);
-            if (((valid >> ig) & 1u) && cell != kCellInvalid) {
-              const int ipr = cell & 0xff, it0 = (cell >> 8) & 0xff, it1 = (cell >> 16) & 0xff;
-              const size_t g0 = (((size_t)ig * T.npmax + ipr) * T.ntmax + it0) * nd + id;
-              const size_t g1 = (((size_t)ig * T.npmax + ipr + 1) * T.ntmax + it1) * nd + id;
-              const uint2 c00 = T.col[g0], c01 = T.col[g0 + nd], c10 = T.col[g1], c11 = T.col[g1 + nd];
-              if (c00.y >= 2 && c01.y >= 2 && c10.y >= 2 && c11.y >= 2) {
-                const double eps = 1 - tp, useg = rec[L.u0 + ig];
-                unsigned ha = h01[ig] & 0xffffu, hb = h01[ig] >> 16, hc = h23[ig] & 0xffffu, hd = h23[ig] >> 16;
-                const double e00 = fast::column_step(T.brk, c00, eps, useg, ha);
-                const double e01 = fast::column_step(T.brk, c01, eps, useg, hb);
-                const double e10 = fast::column_step(T.brk, c10, eps, useg, hc);
-                const double e11 = fast::column_step(T.brk, c11, eps, useg, hd);
-                h01[ig] = ha | (hb << 16);
-                h23[ig] = hc | (hd << 16);
-                const double ep0 = clamp01(fma(cw[1], e01 - e00, e00));
-                const double ep1 = clamp01(fma(cw[2], e11 - e10, e10));
-                const double ept = clamp01(fma(cw[0], ep1 - ep0, ep0));
-                f = (1. - ept) * fast_rcp(tp);
-              }
+      bool any_opaque = false;
+#pragma unroll 1
+      for (int ig = 0; ig < ng; ig++) {
+        const double tp = tau_s[ig * sstride];
+        double f;
+        if (tp < 1e-9) {
+          f = 0.0;
+          any_opaque = true;
+        } else {
+          f = 1.0;
+          const double *__restrict__ cw = R + L.c0 + 4 * ig;
+          const unsigned cell = (unsigned)__double_as_longlong(cw[3]);
+          unsigned long long h = hint_s[ig * sstride];
+          if (h != ~0ull && cell != kCellInvalid) {
+            const int ipr = cell & 0xff, it0 = (cell >> 8) & 0xff, it1 = (cell >> 16) & 0xff;
+            const size_t g0 = (((size_t)ig * T.npmax + ipr) * T.ntmax + it0) * nd + id;
+            const size_t g1 = (((size_t)ig * T.npmax + ipr + 1) * T.ntmax + it1) * nd + id;
+            const uint2 c00 = T.col[g0], c01 = T.col[g0 + nd], c10 = T.col[g1], c11 = T.col[g1 + nd];
+            if (c00.y >= 2 && c01.y >= 2 && c10.y >= 2 && c11.y >= 2) {
+              const float4 *__restrict__ p00 = T.brk + c00.x, *__restrict__ p01 = T.brk + c01.x,
+                                         *__restrict__ p10 = T.brk + c10.x, *__restrict__ p11 = T.brk + c11.x;
+              int k00 = min((int)(h & 0xffffu), (int)c00.y - 2), k01 = min((int)((h >> 16) & 0xffffu), (int)c01.y - 2),
+                  k10 = min((int)((h >> 32) & 0xffffu), (int)c10.y - 2), k11 = min((int)(h >> 48), (int)c11.y - 2);
+              // the four hinted brackets are requested back to back: their latencies overlap
+              const float4 b00 = p00[k00], b01 = p01[k01], b10 = p10[k10], b11 = p11[k11];
+              const double eps = 1 - tp, useg = R[L.u0 + ig];
+              const double e00 = fast::column_finish(p00, (int)c00.y, eps, useg, k00, b00);
+              const double e01 = fast::column_finish(p01, (int)c01.y, eps, useg, k01, b01);
+              const double e10 = fast::column_finish(p10, (int)c10.y, eps, useg, k10, b10);
+              const double e11 = fast::column_finish(p11, (int)c11.y, eps, useg, k11, b11);
+              hint_s[ig * sstride] = (unsigned long long)k00 | ((unsigned long long)k01 << 16) |
+                                     ((unsigned long long)k10 << 32) | ((unsigned long long)k11 << 48);
+              const double ep0 = clamp01(fma(cw[1], e01 - e00, e00));
+              const double ep1 = clamp01(fma(cw[2], e11 - e10, e10));
+              const double ept = clamp01(fma(cw[0], ep1 - ep0, ep0));
+              f = (1. - ept) * fast_rcp(tp);
             }
           }
-          tau_path[ig] = tp * f;
-          tau_gas *= f;
+          const double tn = tp * f;
+          tau_s[ig * sstride] = tn;
+          any_opaque |= tn < 1e-9;
         }
+        tau_gas *= f;
       }
-      if (tau_gas == 0.0) {
-        // some gas is opaque: its factor stays 0 for the rest of the ray, so tau_gas stays 0 and no
-        // further segment can change rad or tau (accumulate() requires tau_gas > 1e-50)
-        bool any_opaque = false;
-#pragma unroll
-        for (int ig = 0; ig < NGB; ig++) any_opaque |= (ig < a.ng) && (tau_path[ig] < 1e-9);
-        dead = any_opaque;
-      }
+      // an opaque gas keeps its factor 0 for the rest of the ray: tau_gas stays 0, accumulate() is skipped for good
+      if (tau_gas == 0.0 && any_opaque) dead = true;
       const double src = planck_source(T.sr, nd, id, t);
       accumulate(rad, tau, beta_ds, src, tau_gas);
     }
@@ -175,23 +239,26 @@ __global__ void __launch_bounds__(256, 2) ega_fast_kernel(const EgaArgs a) {
   }
 }
 
-template <int NGB, int MASK>
+template <int MASK>
 cudaError_t launch_ega_fast_t(const EgaArgs &a, cudaStream_t stream, int sm_count) {
-  int blocks_per_sm = 0;
-  cudaError_t e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&blocks_per_sm, ega_fast_kernel<NGB, MASK>, 256, 0);
+  const size_t smem = ega_fast_smem_bytes(a.ng, a.los.rec, kEgaBlock);
+  cudaError_t e = cudaFuncSetAttribute(ega_fast_kernel<MASK>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   if (e != cudaSuccess) return e;
-  if (blocks_per_sm < 1) blocks_per_sm = 1;
+  int blocks_per_sm = 0;
+  e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&blocks_per_sm, ega_fast_kernel<MASK>, kEgaBlock, smem);
+  if (e != cudaSuccess) return e;
+  if (blocks_per_sm < 1) return cudaErrorInvalidConfiguration;
   const int ngroups = (a.nd + 31) >> 5;
   const long long n_items = a.n_rays * ngroups;
   long long grid = (long long)sm_count * blocks_per_sm; // persistent: a whole number of CTAs per SM
-  const long long need = (n_items + 7) / 8;
+  const long long need = (n_items + (kEgaBlock / 32) - 1) / (kEgaBlock / 32);
   if (grid > need) grid = need;
   if (grid < 1) grid = 1;
-  ega_fast_kernel<NGB, MASK><<<(unsigned)grid, 256, 0, stream>>>(a);
+  ega_fast_kernel<MASK><<<(unsigned)grid, kEgaBlock, smem, stream>>>(a);
   return cudaGetLastError();
 }
 
-// one translation unit per MASK instantiates NGB = 1..8
+// one translation unit per MASK
 template <int MASK>
 cudaError_t launch_ega_fast_mask(const EgaArgs &a, cudaStream_t stream, int sm_count, int *ngb_out);
 

@@ -60,7 +60,7 @@ def make_atmosphere(pkg, gases, n_profiles, rng, perturb=True):
         pkg.p[s] = prof["p"] * (1.0 + dp)
         pkg.t[s] = prof["t"] + dt
         for ig, g in enumerate(gases):
-            pkg.q[ig, s] = prof[g]
+            pkg.q[ig, s] = prof[g] if g in prof else 1e-9  # unknown emitter: constant trace amount
         pkg.k[:, s] = 0.0
 
 

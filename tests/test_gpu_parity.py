@@ -47,7 +47,7 @@ def test_config_b_nadir_example_bt_and_surface(jr, oracle, gpu_ctx_factory):
 
 
 def test_config_c_refspec_shape_30_gases_100_channels(jr, oracle, gpu_ctx_factory):
-    """NG=30, ND=100 (example/refspec shape): more than 8 gases -> generic kernel"""
+    """NG=30, ND=100 (example/refspec shape)"""
     gases = ["CO2", "H2O", "O3", "N2O", "CH4", "CO", "HNO3", "SO2", "F11", "CCl4"] + [f"X{i}" for i in range(20)]
     ctl = jr.Control(gases, 2150.0 + np.arange(100))  # window with the N2 continuum
     assert ctl.ctm_mask == 14
@@ -55,7 +55,16 @@ def test_config_c_refspec_shape_30_gases_100_channels(jr, oracle, gpu_ctx_factor
     pkg = jr.synth.limb_package(ctl, n_profiles=1, rays_per_profile=6, dz=11.0, seed=5)
     for ig in range(10, 30):
         pkg.q[ig, :] = 1e-9
-    _both(gpu_ctx_factory, oracle, ctl, tbl, [pkg], "C", variants=(0,))
+    _both(gpu_ctx_factory, oracle, ctl, tbl, [pkg], "C")
+
+
+def test_more_than_32_gases_use_generic_kernel(jr, oracle, gpu_ctx_factory):
+    gases = [f"G{i}" for i in range(34)]
+    ctl = jr.Control(gases, [900.0, 901.0])
+    tbl = jr.synth.make_tables(ctl)
+    pkg = jr.synth.limb_package(ctl, n_profiles=1, rays_per_profile=3, dz=20.0, seed=9)
+    pkg.q[:, :] = 2e-9
+    _both(gpu_ctx_factory, oracle, ctl, tbl, [pkg], "ng34", variants=(0,))
     ctx = gpu_ctx_factory()
     ctx.set_control(ctl); ctx.set_tables(tbl); ctx.set_kernel_variant(1)
     with pytest.raises(jr.JrbError, match="not applicable"):

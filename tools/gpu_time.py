@@ -1,0 +1,24 @@
+#!/usr/bin/env python3
+"""Timing only (development helper): Config D (NPK packages) and Config E (8 packages), specialised kernel."""
+import importlib, os, sys
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+jr = importlib.import_module("jurassic-gpu_b200")
+synth = jr.synth
+
+def timing(name, ctl, tbl, pkgs, reps=3):
+    ctx = jr.Context(0); ctx.set_control(ctl); ctx.set_tables(tbl); ctx.set_kernel_variant(1); ctx.stage(pkgs)
+    best = None
+    for _ in range(reps):
+        ctx.run_staged(); st = ctx.stats()
+        if best is None or st['ms_total_device'] < best['ms_total_device']: best = st
+    rc = best['n_ray_channels']
+    print(f"[{name}] rays={best['n_rays']} rt={best['ms_raytrace']:.2f}ms ega={best['ms_ega']:.2f}ms total={best['ms_total_device']:.2f}ms "
+          f"-> total {rc/best['ms_total_device']/1e3:.2f} M/s, ega-only {rc/best['ms_ega']/1e3:.2f} M/s", flush=True)
+    ctx.close()
+
+ctl = synth.control_config_d(); tbl = synth.make_tables(ctl)
+timing("D", ctl, tbl, [synth.limb_package(ctl, seed=20240517 + i) for i in range(int(os.environ.get("NPK", "32")))])
+if os.environ.get("WITH_E", "1") == "1":
+    ctl = synth.control_config_e(); tbl = synth.make_tables(ctl)
+    timing("E", ctl, tbl, [synth.nadir_package(ctl, seed=20240518 + i) for i in range(8)])
