@@ -11,7 +11,7 @@ import numpy as np
 from . import abi
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIBDIR = os.environ.get("JRB_LIBDIR", os.path.join(_HERE, "lib"))  # override only for kernel-variant experiments
+LIBDIR = os.environ.get("JRB_LIBDIR") or os.path.join(_HERE, "lib")  # override only for kernel-variant experiments
 CORE_LIB = os.path.join(LIBDIR, "libjurassic_b200.so")
 
 _lib = None

@@ -79,10 +79,12 @@ enum ChanField {
 };
 
 // ---- LOS record ------------------------------------------------------------------------------------------------
-// doubles: [0]p [1]t [2]ds [3]q_h2o [4..4+nw)k  [U0..U0+ng)u  (fast: [C0+4*ig..) wp,wt0,wt1,cell)  [Z0..Z0+3) z,lon,lat
+// doubles: [0]p [1]t [2]ds [3]q_h2o [4..4+nw)k  [U0..U0+ng)u  (fast: [C0+4*ig..) wp,wt0,wt1,cell)
+//          tail [Z0..Z0+6): altitude z, raw step length, atmosphere level index, Cartesian x,y,z of the point
+// The EGA kernels read only the first `head` doubles of a record (everything before the tail).
 struct LosLayout {
   int nw, ng, fast;
-  int u0, c0, z0, rec; // offsets in doubles, record length
+  int u0, c0, z0, head, rec; // offsets in doubles; head = doubles staged for the EGA kernel; rec = record length
 };
 __host__ __device__ inline LosLayout make_los_layout(int ng, int nw, int fast) {
   LosLayout L;
@@ -90,9 +92,12 @@ __host__ __device__ inline LosLayout make_los_layout(int ng, int nw, int fast) {
   L.u0 = 4 + nw;
   L.c0 = L.u0 + ng;
   L.z0 = L.c0 + (fast ? 4 * ng : 0);
-  L.rec = (L.z0 + 3 + 1) & ~1; // even number of doubles: records are 16-byte multiples (TMA bulk copies)
+  L.z0 = (L.z0 + 1) & ~1;       // 16-byte multiples: the head of a record is moved by TMA bulk copies
+  L.head = L.z0;
+  L.rec = L.z0 + 6;
   return L;
 }
+enum LosTail { LT_Z = 0, LT_DSRAW = 1, LT_LEVEL = 2, LT_X = 3 };
 constexpr unsigned kCellInvalid = 0xffffffffu; // "no usable table cell -> gas factor 1"
 
 // ---- math helpers ----------------------------------------------------------------------------------------------

@@ -5,7 +5,7 @@
 // counter so that rays of different length (130..393 segments) balance themselves.
 //
 // Data movement per segment:
-//   * the ray's LOS record (p, T, ds, per-gas u / table cell / interpolation weights; <= 272 B for 5 gases) is staged
+//   * the ray's LOS record (p, T, ds, per-gas u / table cell / interpolation weights; 264 B for 5 gases) is staged
 //     into shared memory by a TMA bulk copy (cp.async.bulk + mbarrier, double buffered per warp): segment ip+1 is in
 //     flight while segment ip is computed, and every lane reads the fields as shared-memory broadcasts;
 //   * per gas, the four column descriptors are read coalesced (channel innermost), then the four hinted brackets
@@ -116,11 +116,11 @@ __global__ void __launch_bounds__(kEgaBlock, JRB_EGA_MINBLOCKS) ega_fast_kernel(
   const LosLayout L = a.los;
   const TblDev &T = a.tbl;
   const int nd = a.nd, ng = a.ng;
-  const unsigned rec_bytes = (unsigned)L.rec * 8u;
+  const unsigned rec_bytes = (unsigned)L.head * 8u; // only the head of a record is staged
 
   unsigned long long *bars = reinterpret_cast<unsigned long long *>(smem_raw) + warp * 2;
-  double *recbuf = reinterpret_cast<double *>(smem_raw + (size_t)nwarps * 16) + (size_t)warp * 2 * L.rec;
-  double *tau_s = reinterpret_cast<double *>(smem_raw + (size_t)nwarps * 16 + (size_t)nwarps * 2 * L.rec * 8) + tid;
+  double *recbuf = reinterpret_cast<double *>(smem_raw + (size_t)nwarps * 16) + (size_t)warp * 2 * L.head;
+  double *tau_s = reinterpret_cast<double *>(smem_raw + (size_t)nwarps * 16 + (size_t)nwarps * 2 * L.head * 8) + tid;
   unsigned long long *hint_s = reinterpret_cast<unsigned long long *>(tau_s - tid + (size_t)ng * blockDim.x) + tid;
   const int sstride = blockDim.x;
 
@@ -168,14 +168,14 @@ __global__ void __launch_bounds__(kEgaBlock, JRB_EGA_MINBLOCKS) ega_fast_kernel(
       const bool all_dead = __all_sync(0xffffffffu, dead);
       if ((ip + 1 < np) && !all_dead && lane == 0) { // segment ip+1 travels while segment ip is computed
         fast::mbar_expect_tx(&bars[b ^ 1], rec_bytes);
-        fast::tma_load_1d(recbuf + (size_t)(b ^ 1) * L.rec, rec_g + (size_t)(ip + 1) * L.rec, rec_bytes, &bars[b ^ 1]);
+        fast::tma_load_1d(recbuf + (size_t)(b ^ 1) * L.head, rec_g + (size_t)(ip + 1) * L.rec, rec_bytes, &bars[b ^ 1]);
       }
       // the copy of segment ip is always in flight here (issued above one iteration earlier, or before the loop)
       if (b == 0) { fast::mbar_wait(&bars[0], parity0); parity0 ^= 1; } else { fast::mbar_wait(&bars[1], parity1); parity1 ^= 1; }
       if (all_dead) break; // nothing further was requested
       if (dead) continue;
 
-      const double *__restrict__ R = recbuf + (size_t)b * L.rec;
+      const double *__restrict__ R = recbuf + (size_t)b * L.head;
       const double p = R[0], t = R[1], ds = R[2];
       const double u_co2 = (MASK & 8) ? R[L.u0 + a.ig_co2] : 0.0;
       const double u_h2o = (MASK & 4) ? R[L.u0 + a.ig_h2o] : 0.0;
@@ -241,7 +241,7 @@ __global__ void __launch_bounds__(kEgaBlock, JRB_EGA_MINBLOCKS) ega_fast_kernel(
 
 template <int MASK>
 cudaError_t launch_ega_fast_t(const EgaArgs &a, cudaStream_t stream, int sm_count) {
-  const size_t smem = ega_fast_smem_bytes(a.ng, a.los.rec, kEgaBlock);
+  const size_t smem = ega_fast_smem_bytes(a.ng, a.los.head, kEgaBlock);
   cudaError_t e = cudaFuncSetAttribute(ega_fast_kernel<MASK>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   if (e != cudaSuccess) return e;
   int blocks_per_sm = 0;

@@ -16,6 +16,9 @@ struct TraceArgs {
   const double *atm_time, *atm_z, *atm_lon, *atm_lat, *atm_p, *atm_t;
   const double *atm_q, *atm_k; // [ng][atm_stride], [nw][atm_stride]
   long long atm_stride;
+  double *atm_lnp_slope;       // [atm_stride] scratch: log(p[i+1]/p[i])/(z[i+1]-z[i]), NaN where not both positive
+  long long n_atm;
+  int prepare_atm;             // 1: (re)compute atm_lnp_slope before tracing
   // control
   int refrac, ig_h2o;
   double rayds, raydz;
@@ -23,6 +26,7 @@ struct TraceArgs {
   LosLayout los;
   double *los_data; // [n_rays][NLOS][rec]
   int *ray_np;      // [n_rays]
+  int *ray_level0;  // [n_rays] first atmosphere level of the ray's profile (relative to its package)
   double *ray_tsurf;
   double *tp;       // rows tpz, tplon, tplat ; row stride geo_stride
   TblDev tbl;       // used when los.fast
@@ -45,7 +49,8 @@ struct EgaArgs {
   unsigned long long *work_counter; // dynamic work distribution (zeroed before launch)
 };
 
-cudaError_t launch_raytrace(const TraceArgs &a, cudaStream_t stream);
+// three launches: level slopes, ray stepping (thread per ray), LOS finalisation (thread per ray x segment)
+cudaError_t launch_raytrace(const TraceArgs &a, cudaStream_t stream, int *launches);
 cudaError_t launch_ega_generic(const EgaArgs &a, cudaStream_t stream);
 // fast path: returns cudaErrorInvalidValue if (ng, ctm_mask) has no instantiation
 cudaError_t launch_ega_fast(const EgaArgs &a, cudaStream_t stream, int *ngb_out);

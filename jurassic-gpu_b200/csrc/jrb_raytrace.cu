@@ -1,13 +1,20 @@
-// jrb_raytrace.cu -- line-of-sight ray tracer + column densities (one thread per ray), sm_100a.
+// jrb_raytrace.cu -- line-of-sight ray tracer + column densities, sm_100a.
 //
 // Computes what the reference's traceray() computes (src/jr_common.h:585-711: profile selection :127-154,
 // altitude range :411-420, observer/view-point rejection :598-599, entry search :610-621, stepping loop
 // :624-691 with refraction :664-681, tangent point :502-539, trapezoid rule :437-443, column density
-// :446-453) but is organised for the device path:
-//   pass 1 walks the ray and writes raw LOS records (p, T, raw ds, q, k, z/lon/lat) to the ray's record array;
-//   pass 2 (same thread) finalises segment lengths, converts vmr to column densities and -- for tables whose
-//   (p,T) axes do not depend on the channel -- resolves the table cell and interpolation weights per gas once
-//   per segment, so that the EGA kernel does not search axes per channel.
+// :446-453), split by what is sequential and what is not:
+//
+//   atm_slopes_kernel    per atmosphere level: d ln p / dz of the exponential pressure interpolation (eip, :53-57),
+//                        so that the stepping loop needs one exp but no log and no division per interpolation;
+//   ray_step_kernel      one thread per ray, the inherently sequential part: walk the ray, per point altitude,
+//                        p, T (5 interpolations per step with refraction), raw step length, Cartesian position.
+//                        Longitude/latitude (asin, atan2) are not needed along the way -- the 1-D atmosphere is a
+//                        function of altitude only -- they are evaluated for the tangent point only;
+//   los_finalize_kernel  one thread per (ray, segment), fully parallel: vmr/extinction interpolation, trapezoid
+//                        segment lengths, column densities and -- for tables whose (p,T) axes do not depend on the
+//                        channel -- the table cell and interpolation weights per gas, so that the EGA kernel does
+//                        not search axes per channel.
 #include "jrb_internal.h"
 
 namespace jrb {
@@ -23,43 +30,59 @@ __device__ __forceinline__ void geo_to_cart(double alt, double lon, double lat, 
   x[1] = radius * clat * sin(lon * d2r);
   x[2] = radius * sin(lat * d2r);
 }
-__device__ __forceinline__ void cart_to_geo(const double x[3], double *alt, double *lon, double *lat) {
+__device__ __forceinline__ void cart_to_lonlat(const double x[3], double *lon, double *lat) {
   const double r2d = 180.0 / M_PI;
-  const double radius = norm3(x);
-  *lat = asin(x[2] / radius) * r2d;
+  *lat = asin(x[2] / norm3(x)) * r2d;
   *lon = atan2(x[1], x[0]) * r2d;
-  *alt = radius - kRE;
 }
 
-// `locate` of the reference (src/jr_common.h:87-104): ascending or descending axis
-__device__ __forceinline__ int locate_z(const double *__restrict__ zz, int n, double x) {
-  int ilo = 0, ihi = n - 1, i = (n - 1) >> 1;
-  if (zz[i] < zz[i + 1]) {
-    while (ihi > ilo + 1) { i = (ihi + ilo) >> 1; if (zz[i] > x) ihi = i; else ilo = i; }
-  } else {
-    while (ihi > ilo + 1) { i = (ihi + ilo) >> 1; if (zz[i] <= x) ihi = i; else ilo = i; }
+// One vertical profile as seen by a ray.  `locate` of the reference (src/jr_common.h:87-104) returns, for an
+// ascending axis, max{i <= n-2 : z[i] <= x} (0 if x < z[0]); for a descending one max{i <= n-2 : z[i] > x}.
+// The level found for the previous evaluation is tried first; the bisection runs only when it does not bracket x.
+struct Profile {
+  const double *__restrict__ z, *__restrict__ p, *__restrict__ t, *__restrict__ slope;
+  int n;
+  bool asc;
+
+  __device__ __forceinline__ int locate(double x, int hint) const {
+    const double zl = z[hint], zh = z[hint + 1];
+    if (asc) {
+      if ((zl <= x || hint == 0) && (zh > x || hint == n - 2)) return hint;
+    } else {
+      if ((zl > x || hint == 0) && (zh <= x || hint == n - 2)) return hint;
+    }
+    int ilo = 0, ihi = n - 1;
+    if (asc) { while (ihi > ilo + 1) { const int i = (ihi + ilo) >> 1; if (z[i] > x) ihi = i; else ilo = i; } }
+    else     { while (ihi > ilo + 1) { const int i = (ihi + ilo) >> 1; if (z[i] <= x) ihi = i; else ilo = i; } }
+    return ilo;
   }
-  return ilo;
-}
-
-// pressure (exponential) and temperature (linear) at altitude z0 (intpol_atm_1d_pt, :549-555; eip :53-57)
-__device__ __forceinline__ void interp_pt(const double *__restrict__ az, const double *__restrict__ ap,
-                                          const double *__restrict__ at, int n, double z0, double *p, double *t,
-                                          int *idx_out) {
-  const int ip = locate_z(az, n, z0);
-  const double x0 = az[ip], x1 = az[ip + 1];
-  const double y0 = ap[ip], y1 = ap[ip + 1];
-  if (y0 > 0 && y1 > 0) *p = y0 * exp(log(y1 / y0) / (x1 - x0) * (z0 - x0));
-  else *p = lerp_div(x0, y0, x1, y1, z0);
-  *t = lerp_div(x0, at[ip], x1, at[ip + 1], z0);
-  *idx_out = ip;
-}
+  // intpol_atm_1d_pt (:549-555): p exponential (eip :53-57), T linear (lip :48-50)
+  __device__ __forceinline__ void pt(double x, int &level, double *pp, double *tt) const {
+    level = locate(x, level);
+    const double x0 = z[level], dx = x - x0, s = slope[level];
+    if (s == s) *pp = p[level] * exp(s * dx);                                        // both pressures positive
+    else *pp = p[level] + dx * (p[level + 1] - p[level]) / (z[level + 1] - x0);      // linear fallback of eip
+    *tt = t[level] + dx * (t[level + 1] - t[level]) / (z[level + 1] - x0);
+  }
+};
 
 __device__ __forceinline__ double refractivity(double p, double t) { return 7.753e-05 * p / t; }
 
 } // namespace
 
-__global__ void __launch_bounds__(128) raytrace_kernel(TraceArgs a) {
+__global__ void atm_slopes_kernel(const double *__restrict__ z, const double *__restrict__ p, double *__restrict__ slope,
+                                  long long n) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  double s = __longlong_as_double(0x7ff8000000000000ll);
+  if (i + 1 < n) {
+    const double y0 = p[i], y1 = p[i + 1];
+    if (y0 > 0 && y1 > 0) s = log(y1 / y0) / (z[i + 1] - z[i]);
+  }
+  slope[i] = s;
+}
+
+__global__ void __launch_bounds__(128) ray_step_kernel(TraceArgs a) {
   const long long r = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (r >= a.n_rays) return;
 
@@ -88,18 +111,21 @@ __global__ void __launch_bounds__(128) raytrace_kernel(TraceArgs a) {
   lo = lower; hi = anp - 1;
   while (hi > lo + 1) { int i = (lo + hi) / 2; if (atime[i] > rtime) hi = i; else lo = i; }
   const int upper = (hi == anp - 1) ? anp : hi;
-  const int n = upper - lower;
-  const double *__restrict__ az = a.atm_z + abase + lower;
-  const double *__restrict__ ap = a.atm_p + abase + lower;
-  const double *__restrict__ at = a.atm_t + abase + lower;
+  Profile P;
+  P.n = upper - lower;
+  P.z = a.atm_z + abase + lower;
+  P.p = a.atm_p + abase + lower;
+  P.t = a.atm_t + abase + lower;
+  P.slope = a.atm_lnp_slope + abase + lower;
+  { const int m = (P.n - 1) >> 1; P.asc = P.z[m] < P.z[m + 1]; }
   const double *__restrict__ alon = a.atm_lon + abase + lower;
   const double *__restrict__ alat = a.atm_lat + abase + lower;
 
   // ---- altitude range of the profile (altitude_range_nn, :411-420) ----
-  double zmin = az[0], zmax = az[0];
-  for (int i = 0; i < n && alon[i] == alon[0] && alat[i] == alat[0]; ++i) {
-    zmax = fmax(zmax, az[i]);
-    zmin = fmin(zmin, az[i]);
+  double zmin = P.z[0], zmax = P.z[0];
+  for (int i = 0; i < P.n && alon[i] == alon[0] && alat[i] == alat[0]; ++i) {
+    zmax = fmax(zmax, P.z[i]);
+    zmin = fmin(zmin, P.z[i]);
   }
 
   const bool rejected = (obsz < zmin) || (vpz > zmax - 0.001);
@@ -123,48 +149,38 @@ __global__ void __launch_bounds__(128) raytrace_kernel(TraceArgs a) {
       }
     }
 
-    double z_low = 1e99, lon, lat, p, t;
-    double pz = 0, plon = 0, plat = 0; // previous point
-    int stop = 0;
+    double z_low = 1e99, p, t;
+    double xprev[3] = {0, 0, 0}, zprev = 0; // previous LOS point
+    int level = 0, stop = 0;
     for (; np < kNLOS; ++np) {
+      const double rn = norm3(x);
       double ds = a.rayds;
-      if (a.raydz > 0.0) {
-        const double inv = 1.0 / norm3(x);
+      if (a.raydz > 0.0) { // step length from the angle to the local vertical (:625-635)
+        const double inv = 1.0 / rn;
         double dot = 0.0;
         for (int i = 0; i < 3; i++) dot += ex0[i] * x[i] * inv;
         const double cosa = fabs(dot);
         if (cosa != 0.0) ds = fmin(ds, a.raydz / cosa);
       }
-      cart_to_geo(x, &z, &lon, &lat);
+      z = rn - kRE;
       if ((z < zmin) || (z > zmax)) { // left the atmosphere: clip the last segment (:637-648)
-        if (np == 0) break;           // (reference would read los[-1]; cannot happen after the entry search)
-        double xh[3];
+        if (np == 0) break;           // (the reference would read los[-1]; unreachable after the entry search)
         stop = (z < zmin) ? 2 : 1;
-        geo_to_cart(pz, plon, plat, xh);
         const double zfrac = (z < zmin) ? zmin : zmax;
-        const double frac = (zfrac - pz) / (z - pz);
-        for (int i = 0; i < 3; i++) x[i] = xh[i] + frac * (x[i] - xh[i]);
-        cart_to_geo(x, &z, &lon, &lat);
-        rec0[(size_t)(np - 1) * L.rec + 2] = ds * frac;
+        const double frac = (zfrac - zprev) / (z - zprev);
+        for (int i = 0; i < 3; i++) x[i] = xprev[i] + frac * (x[i] - xprev[i]);
+        z = norm3(x) - kRE;
+        rec0[(size_t)(np - 1) * L.rec + L.z0 + LT_DSRAW] = ds * frac;
         ds = 0.0;
       }
-      int ia;
-      interp_pt(az, ap, at, n, z, &p, &t, &ia);
+      P.pt(z, level, &p, &t);
       double *__restrict__ rec = rec0 + (size_t)np * L.rec;
-      rec[0] = p; rec[1] = t; rec[2] = ds;
-      {
-        const double x0 = az[ia], x1 = az[ia + 1];
-        for (int ig = 0; ig < L.ng; ig++) { // vmr goes to the u slot for now (intpol_atm_1d_qk, :557-567)
-          const double *__restrict__ q = a.atm_q + (size_t)ig * a.atm_stride + abase + lower;
-          rec[L.u0 + ig] = lerp_div(x0, q[ia], x1, q[ia + 1], z);
-        }
-        for (int iw = 0; iw < L.nw; iw++) {
-          const double *__restrict__ k = a.atm_k + (size_t)iw * a.atm_stride + abase + lower;
-          rec[4 + iw] = lerp_div(x0, k[ia], x1, k[ia + 1], z);
-        }
-      }
-      rec[L.z0 + 0] = z; rec[L.z0 + 1] = lon; rec[L.z0 + 2] = lat;
-      pz = z; plon = lon; plat = lat;
+      rec[0] = p; rec[1] = t;
+      double *__restrict__ tail = rec + L.z0;
+      tail[LT_Z] = z; tail[LT_DSRAW] = ds; tail[LT_LEVEL] = (double)level;
+      tail[LT_X] = x[0]; tail[LT_X + 1] = x[1]; tail[LT_X + 2] = x[2];
+      for (int i = 0; i < 3; i++) xprev[i] = x[i];
+      zprev = z;
       if (z < z_low) { z_low = z; z_low_idx = np; }
 
       if (stop) { tsurf = (stop == 2 ? t : -999.0); break; }
@@ -172,14 +188,15 @@ __global__ void __launch_bounds__(128) raytrace_kernel(TraceArgs a) {
       double nref = 1.0, ngr[3] = {0.0, 0.0, 0.0};
       if (a.refrac && z <= 60.0) { // refractivity gradient by finite differences at the half step (:664-681)
         nref += refractivity(p, t);
-        double xh[3], ph, th; int dummy;
+        double xh[3], ph, th;
+        int lv = level;
         for (int i = 0; i < 3; i++) xh[i] = x[i] + 0.5 * ds * ex0[i];
-        interp_pt(az, ap, at, n, norm3(xh) - kRE, &ph, &th, &dummy);
+        P.pt(norm3(xh) - kRE, lv, &ph, &th);
         const double n2 = refractivity(ph, th);
         for (int i = 0; i < 3; i++) {
           const double h = 0.02;
           xh[i] += h;
-          interp_pt(az, ap, at, n, norm3(xh) - kRE, &ph, &th, &dummy);
+          P.pt(norm3(xh) - kRE, lv, &ph, &th);
           ngr[i] = (refractivity(ph, th) - n2) / h;
           xh[i] -= h;
         }
@@ -193,94 +210,116 @@ __global__ void __launch_bounds__(128) raytrace_kernel(TraceArgs a) {
         ex0[i] = ex1[i];
       }
     }
-    if (np > 0 || stop) ++np; // the reference increments after the loop (:692)
-    if (np > kNLOS) np = kNLOS; // (reference: fatal "Too many LOS points" on CPU when np >= NLOS)
+    if (np > 0 || stop) ++np;   // the reference increments after the loop (:692)
+    if (np > kNLOS) np = kNLOS; // (reference: fatal "Too many LOS points" on the CPU when np >= NLOS)
   }
 
-  // ---- tangent point (before changing segment lengths; :502-539) ----
+  // ---- tangent point (from the raw step lengths; :502-539) ----
   if (np > 0) {
     const int ip = z_low_idx;
-    if (ip <= 0 || ip >= np - 1) {
-      const double *rl = rec0 + (size_t)(np - 1) * L.rec + L.z0;
-      tpz = rl[0]; tplon = rl[1]; tplat = rl[2];
+    if (ip <= 0 || ip >= np - 1) { // nadir or zenith: last point
+      const double *tl = rec0 + (size_t)(np - 1) * L.rec + L.z0;
+      tpz = tl[LT_Z];
+      cart_to_lonlat(tl + LT_X, &tplon, &tplat);
     } else {
-      const double *r0 = rec0 + (size_t)(ip - 1) * L.rec, *r1 = rec0 + (size_t)ip * L.rec,
-                   *r2 = rec0 + (size_t)(ip + 1) * L.rec;
-      const double yy0 = r0[L.z0], yy1 = r1[L.z0], yy2 = r2[L.z0];
-      const double ds0 = r1[2], ds1 = r2[2];
+      const double *t0 = rec0 + (size_t)(ip - 1) * L.rec + L.z0, *t1 = t0 + L.rec, *t2 = t1 + L.rec;
+      const double yy0 = t0[LT_Z], yy1 = t1[LT_Z], yy2 = t2[LT_Z];
+      const double ds0 = t1[LT_DSRAW], ds1 = t2[LT_DSRAW];
       const double dyy10 = yy1 - yy0, dyy21 = yy2 - yy1;
       const double x1 = sqrt(ds0 * ds0 - dyy10 * dyy10);
       const double x2 = x1 + sqrt(ds1 * ds1 - dyy21 * dyy21);
       const double dx12 = x1 - x2;
       const double qa = (dyy10 * x2 + (yy0 - yy2) * x1) / (x1 * x2 * dx12);
       const double qb = dyy10 / x1 - qa * x1;
-      const double qc = yy0;
       const double xt = -qb / (2 * qa);
-      tpz = (qa * xt + qb) * xt + qc;
-      double v[3], v0[3], v2[3], dummy;
-      geo_to_cart(r0[L.z0], r0[L.z0 + 1], r0[L.z0 + 2], v0);
-      geo_to_cart(r2[L.z0], r2[L.z0 + 1], r2[L.z0 + 2], v2);
-      for (int i = 0; i < 3; i++) v[i] = lerp_div(0.0, v0[i], x2, v2[i], xt);
-      cart_to_geo(v, &dummy, &tplon, &tplat);
-    }
-  }
-
-  // ---- pass 2: trapezoid rule, column densities, table cells ----
-  {
-    double ds_prev = 0.0;
-    for (int ip = 0; ip < np; ip++) {
-      double *__restrict__ rec = rec0 + (size_t)ip * L.rec;
-      const double ds_raw = rec[2];
-      const double ds = (ip == 0) ? 0.5 * ds_raw : 0.5 * (ds_prev + ds_raw); // (:437-443)
-      ds_prev = ds_raw;
-      rec[2] = ds;
-      const double p = rec[0], t = rec[1];
-      rec[3] = (a.ig_h2o >= 0) ? rec[L.u0 + a.ig_h2o] : 0.0;
-      for (int ig = 0; ig < L.ng; ig++) {
-        const double q = rec[L.u0 + ig];
-        rec[L.u0 + ig] = 10. * q * p / (kBoltzmann * t) * ds; // (:446-453)
-      }
-      if (L.fast) {
-        const TblDev &T = a.tbl;
-        for (int ig = 0; ig < L.ng; ig++) {
-          double *__restrict__ c = rec + L.c0 + 4 * ig;
-          unsigned cell = kCellInvalid;
-          double wp = 0, wt0 = 0, wt1 = 0;
-          const int gnp = T.gnp[ig];
-          if (gnp >= 2) {
-            const double *__restrict__ gp = T.gp + (size_t)ig * T.npmax;
-            const int ipr = bisect_asc([&](int i) { return gp[i]; }, gnp, p);
-            const int nt0 = T.gnt[ig * T.npmax + ipr], nt1 = T.gnt[ig * T.npmax + ipr + 1];
-            if (nt0 >= 2 && nt1 >= 2) {
-              const double *__restrict__ g0 = T.gt + ((size_t)ig * T.npmax + ipr) * T.ntmax;
-              const double *__restrict__ g1 = g0 + T.ntmax;
-              const int it0 = bisect_asc([&](int i) { return g0[i]; }, nt0, t);
-              const int it1 = bisect_asc([&](int i) { return g1[i]; }, nt1, t);
-              cell = (unsigned)ipr | ((unsigned)it0 << 8) | ((unsigned)it1 << 16);
-              wp = (p - gp[ipr]) / (gp[ipr + 1] - gp[ipr]);
-              wt0 = (t - g0[it0]) / (g0[it0 + 1] - g0[it0]);
-              wt1 = (t - g1[it1]) / (g1[it1 + 1] - g1[it1]);
-            }
-          }
-          c[0] = wp; c[1] = wt0; c[2] = wt1;
-          c[3] = __longlong_as_double((long long)cell);
-        }
-      }
+      tpz = (qa * xt + qb) * xt + yy0;
+      double v[3];
+      for (int i = 0; i < 3; i++) v[i] = lerp_div(0.0, t0[LT_X + i], x2, t2[LT_X + i], xt);
+      cart_to_lonlat(v, &tplon, &tplat);
     }
   }
 
   a.ray_np[r] = np;
   a.ray_tsurf[r] = tsurf;
+  a.ray_level0[r] = lower;
   a.tp[0 * a.geo_stride + r] = tpz;
   a.tp[1 * a.geo_stride + r] = tplon;
   a.tp[2 * a.geo_stride + r] = tplat;
 }
 
-cudaError_t launch_raytrace(const TraceArgs &a, cudaStream_t stream) {
-  if (a.n_rays <= 0) return cudaSuccess;
-  const int block = 128;
-  const long long grid = (a.n_rays + block - 1) / block;
-  raytrace_kernel<<<(unsigned)grid, block, 0, stream>>>(a);
+// thread per (ray, segment)
+__global__ void __launch_bounds__(256) los_finalize_kernel(TraceArgs a) {
+  const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  const long long r = idx / kNLOS;
+  const int ip = (int)(idx - r * kNLOS);
+  if (r >= a.n_rays) return;
+  const int np = a.ray_np[r];
+  if (ip >= np) return;
+  const LosLayout L = a.los;
+  double *__restrict__ rec = a.los_data + ((size_t)r * kNLOS + ip) * L.rec;
+  const double *__restrict__ tail = rec + L.z0;
+  const double p = rec[0], t = rec[1], z = tail[LT_Z];
+  // trapezoid rule on the raw step lengths (:437-443)
+  const double ds_raw = tail[LT_DSRAW];
+  const double ds = (ip == 0) ? 0.5 * ds_raw : 0.5 * (tail[LT_DSRAW - L.rec] + ds_raw);
+  rec[2] = ds;
+  // vmr / extinction at this altitude (intpol_atm_1d_qk, :557-567); same level as for p and T
+  const int pk = a.ray_pkg[r];
+  const long long base = a.pkg_atm_off[pk] + a.ray_level0[r] + (long long)tail[LT_LEVEL];
+  const double x0 = a.atm_z[base], x1 = a.atm_z[base + 1];
+  const double w = (z - x0) / (x1 - x0);
+  for (int iw = 0; iw < L.nw; iw++) {
+    const double *__restrict__ k = a.atm_k + (size_t)iw * a.atm_stride + base;
+    rec[4 + iw] = k[0] + w * (k[1] - k[0]);
+  }
+  const double dens = 10. * p / (kBoltzmann * t) * ds; // column density per unit vmr (:446-453)
+  double qh2o = 0.0;
+  for (int ig = 0; ig < L.ng; ig++) {
+    const double *__restrict__ q = a.atm_q + (size_t)ig * a.atm_stride + base;
+    const double qv = q[0] + w * (q[1] - q[0]);
+    if (ig == a.ig_h2o) qh2o = qv;
+    rec[L.u0 + ig] = qv * dens;
+  }
+  rec[3] = qh2o;
+  if (L.fast) {
+    const TblDev &T = a.tbl;
+    for (int ig = 0; ig < L.ng; ig++) {
+      double *__restrict__ c = rec + L.c0 + 4 * ig;
+      unsigned cell = kCellInvalid;
+      double wp = 0, wt0 = 0, wt1 = 0;
+      const int gnp = T.gnp[ig];
+      if (gnp >= 2) {
+        const double *__restrict__ gp = T.gp + (size_t)ig * T.npmax;
+        const int ipr = bisect_asc([&](int i) { return gp[i]; }, gnp, p);
+        const int nt0 = T.gnt[ig * T.npmax + ipr], nt1 = T.gnt[ig * T.npmax + ipr + 1];
+        if (nt0 >= 2 && nt1 >= 2) {
+          const double *__restrict__ g0 = T.gt + ((size_t)ig * T.npmax + ipr) * T.ntmax;
+          const double *__restrict__ g1 = g0 + T.ntmax;
+          const int it0 = bisect_asc([&](int i) { return g0[i]; }, nt0, t);
+          const int it1 = bisect_asc([&](int i) { return g1[i]; }, nt1, t);
+          cell = (unsigned)ipr | ((unsigned)it0 << 8) | ((unsigned)it1 << 16);
+          wp = (p - gp[ipr]) / (gp[ipr + 1] - gp[ipr]);
+          wt0 = (t - g0[it0]) / (g0[it0 + 1] - g0[it0]);
+          wt1 = (t - g1[it1]) / (g1[it1 + 1] - g1[it1]);
+        }
+      }
+      c[0] = wp; c[1] = wt0; c[2] = wt1;
+      c[3] = __longlong_as_double((long long)cell);
+    }
+  }
+}
+
+cudaError_t launch_raytrace(const TraceArgs &a, cudaStream_t stream, int *launches) {
+  if (launches) *launches = 0;
+  if (a.prepare_atm && a.n_atm > 0) {
+    atm_slopes_kernel<<<(unsigned)((a.n_atm + 255) / 256), 256, 0, stream>>>(a.atm_z, a.atm_p, a.atm_lnp_slope, a.n_atm);
+    if (launches) ++*launches;
+  }
+  if (a.n_rays <= 0) return cudaGetLastError();
+  ray_step_kernel<<<(unsigned)((a.n_rays + 127) / 128), 128, 0, stream>>>(a);
+  const long long n = a.n_rays * kNLOS;
+  los_finalize_kernel<<<(unsigned)((n + 255) / 256), 256, 0, stream>>>(a);
+  if (launches) *launches += 2;
   return cudaGetLastError();
 }
 

@@ -82,7 +82,7 @@ struct jrb_context {
   std::vector<long long> pk_ray_off;
   std::vector<std::pair<long long, int>> nan_mask; // (global ray, channel) whose input radiance was non-finite
   PinBuf h_in, h_out;
-  DevBuf d_in, d_out, d_los, d_np, d_tsurf, d_counter;
+  DevBuf d_in, d_out, d_los, d_np, d_tsurf, d_counter, d_slope, d_level0;
   // pointers into d_in / d_out
   double *geo = nullptr, *atm = nullptr;
   int *ray_pkg = nullptr, *pkg_atm_np = nullptr;
@@ -151,7 +151,7 @@ void jrb_destroy(jrb_context *ctx) {
   for (auto ev : ctx->events) cudaEventDestroy(ev);
   ctx->d_chan.release(); ctx->d_window.release(); ctx->d_blob.release();
   ctx->d_in.release(); ctx->d_out.release(); ctx->d_los.release(); ctx->d_np.release(); ctx->d_tsurf.release();
-  ctx->d_counter.release(); ctx->h_in.release(); ctx->h_out.release();
+  ctx->d_counter.release(); ctx->d_slope.release(); ctx->d_level0.release(); ctx->h_in.release(); ctx->h_out.release();
   cudaStreamDestroy(ctx->stream);
   delete ctx;
 }
@@ -385,6 +385,8 @@ int jrb_stage(jrb_context *ctx, int npk, const jrb_atm_view *atm, const jrb_obs_
   CU(ctx->d_np.ensure((size_t)(R ? R : 1) * 4));
   CU(ctx->d_tsurf.ensure((size_t)(R ? R : 1) * 8));
   CU(ctx->d_counter.ensure(256));
+  CU(ctx->d_slope.ensure((size_t)(A ? A : 1) * 8));
+  CU(ctx->d_level0.ensure((size_t)(R ? R : 1) * 4));
 
   // kernel choice + LOS buffer
   const bool fast_ok = ctx->th.all_shared && ctx->th.monotone && ega_fast_available(ng, ctx->ctm_mask);
@@ -433,15 +435,18 @@ int jrb_run_staged(jrb_context *ctx) {
     t.atm_time = ctx->atm + 0 * A; t.atm_z = ctx->atm + 1 * A; t.atm_lon = ctx->atm + 2 * A; t.atm_lat = ctx->atm + 3 * A;
     t.atm_p = ctx->atm + 4 * A; t.atm_t = ctx->atm + 5 * A; t.atm_q = ctx->atm + 6 * A; t.atm_k = ctx->atm + (size_t)(6 + ng) * A;
     t.atm_stride = A;
+    t.atm_lnp_slope = (double *)ctx->d_slope.p; t.n_atm = A; t.prepare_atm = (c == 0);
     t.refrac = ctx->refrac; t.ig_h2o = (ctx->ctm_mask & 4) ? ctx->ig_h2o : -1;
     t.rayds = ctx->rayds; t.raydz = ctx->raydz;
     t.los = ctx->los; t.los_data = (double *)ctx->d_los.p;
     t.ray_np = (int *)ctx->d_np.p + r0; t.ray_tsurf = (double *)ctx->d_tsurf.p + r0;
+    t.ray_level0 = (int *)ctx->d_level0.p + r0;
     t.tp = ctx->o_tp + r0;
     t.tbl = ctx->td;
     CU(cudaEventRecord(ctx->events[2 + 3 * c], ctx->stream));
-    CU(launch_raytrace(t, ctx->stream));
-    launches++;
+    int nl = 0;
+    CU(launch_raytrace(t, ctx->stream, &nl));
+    launches += nl;
     CU(cudaEventRecord(ctx->events[3 + 3 * c], ctx->stream));
 
     EgaArgs e;

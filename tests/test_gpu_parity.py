@@ -172,12 +172,16 @@ def test_los_parity(jr, oracle, gpu_ctx_factory):
         los_o, ts_o = oracle.traceray(ctl, copy.deepcopy(pkg), ir)
         rec, ts = ctx.debug_los(ir)
         assert rec.shape[0] == los_o.shape[0] and ts == pytest.approx(ts_o, rel=1e-12)
-        u0, z0 = 4 + nw, 4 + nw + ng
-        np.testing.assert_allclose(rec[:, z0:z0 + 3], los_o[:, 0:3], rtol=1e-10, atol=1e-10)       # z, lon, lat
+        u0, tail = 4 + nw, rec.shape[1] - 6   # record layout: csrc/jrb_device.cuh (LosLayout)
+        np.testing.assert_allclose(rec[:, tail], los_o[:, 0], rtol=1e-10, atol=1e-10)             # altitude
         np.testing.assert_allclose(rec[:, 0:2], los_o[:, 3:5], rtol=1e-10)                         # p, T
-        ds_o = los_o[:, 5]
-        np.testing.assert_allclose(rec[:, 2], ds_o, rtol=1e-9, atol=1e-12)                         # ds (trapezoid)
+        np.testing.assert_allclose(rec[:, 2], los_o[:, 5], rtol=1e-9, atol=1e-9)                   # ds (trapezoid; the clipped last step is ill-conditioned: 1e-9 km = 1 um)
+        np.testing.assert_allclose(rec[:, 4:4 + nw], los_o[:, 6:6 + nw], rtol=1e-9, atol=1e-300)   # extinction
         np.testing.assert_allclose(rec[:, u0:u0 + ng], los_o[:, 6 + nw + ng:], rtol=1e-9)          # column densities
+        # Cartesian position of the point <-> the oracle's (z, lon, lat)
+        lon, lat, zz = np.radians(los_o[:, 1]), np.radians(los_o[:, 2]), los_o[:, 0] + jr.synth.RE
+        xyz = np.stack([zz * np.cos(lat) * np.cos(lon), zz * np.cos(lat) * np.sin(lon), zz * np.sin(lat)], axis=1)
+        np.testing.assert_allclose(rec[:, tail + 3:tail + 6], xyz, rtol=0, atol=1e-8)
 
 
 def test_batch_equals_loop_and_is_deterministic(jr, oracle, gpu_ctx_factory):
