@@ -49,6 +49,16 @@ def hbm_peak():
     return 6650.0, "fallback (B200_PROFILING.md)"
 
 
+_REAL_STDOUT = None
+
+
+def emit(obj):
+    """print the result line on the real stdout"""
+    sys.stdout.flush()
+    line = (json.dumps(obj) + "\n").encode()
+    os.write(_REAL_STDOUT if _REAL_STDOUT is not None else 1, line)
+
+
 class ClockSampler:
     """nvidia-smi clocks / throttle reasons during the timed region"""
     Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
@@ -131,6 +141,7 @@ def reference_arm(args, jr):
     pkgs = make_packages(jr, ctl, 0, npk)
     if refdrv.reference_available(ND_D, NG_D):
         ref = refdrv.Reference(ND_D, NG_D)
+        ref.lib.jrref_set_threads(len(os.sched_getaffinity(0)))  # all host cores (torchrun exports OMP_NUM_THREADS=1)
         kind, cores = "reference", ref.threads()
         c = ref.make_ctl(ctl)
         tstruct, keep = fill_tbl_struct(ref.tbl_t, tbl)
@@ -157,7 +168,7 @@ def reference_arm(args, jr):
     rc = sum(p.n_rays for p in pkgs) * ctl.nd
     value = rc / dt
     sample = f"{npk} Config-D package(s) = {rc} ray-channels per step"
-    print(json.dumps({
+    emit({
         "impl": "reference", "metric": METRIC, "value": value, "unit": "ray-channels/s", "n_gpus": args.gpus, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": dt * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": "f64", "data": "synthetic",
@@ -165,7 +176,7 @@ def reference_arm(args, jr):
                    "packages_per_step": npk},
         "cpu_baseline": {"value": value, "unit": "ray-channels/s", "cores": cores, "kind": kind, "sample": sample},
         "e2e": {"value": value, "unit": "ray-channels/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
-    }), flush=True)
+    })
     return 0
 
 
@@ -182,6 +193,12 @@ def main():
     ap.add_argument("--no-e2e", action="store_true")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 0)
+
+    # libraries (NCCL, the reference's printf's) write to stdout; keep fd 1 clean for the single JSON line
+    sys.stdout.flush()
+    global _REAL_STDOUT
+    _REAL_STDOUT = os.dup(1)
+    os.dup2(2, 1)
 
     jr = importlib.import_module("jurassic-gpu_b200")
     if args.impl == "reference":
@@ -232,7 +249,8 @@ def main():
     t_tables = time.perf_counter() - t_tab0
 
     # ---- this rank's contiguous slice of packages (weak scaling: fixed work per GPU) ----
-    pkgs = make_packages(jr, ctl, rank * args.packages, args.packages)
+    first, count = jr.shard.shard_range(world * args.packages, rank, world)
+    pkgs = make_packages(jr, ctl, first, count)
     ctx.stage(pkgs)
     for _ in range(max(args.warmup, 1) if args.warmup else 0):
         ctx.run_staged()
@@ -350,6 +368,7 @@ def main():
         sample_pk = make_packages(jr, ctl, 0, 64)
         if refdrv.reference_available(ND_D, NG_D):
             ref = refdrv.Reference(ND_D, NG_D)
+            ref.lib.jrref_set_threads(len(os.sched_getaffinity(0)))
             cc = ref.make_ctl(ctl)
             if tstruct is None:
                 tstruct, keep = fill_tbl_struct(ref.tbl_t, tbl)
@@ -376,7 +395,7 @@ def main():
                           "gases": ctl.ng, "l2_policy": "inputs larger than L2 (LOS records rewritten every step: %.1f GB)" % (my_los * 8 * 33 / 1e9),
                           "parallelism": f"rays sharded over {world} GPU(s), tables broadcast once ({t_tables:.2f} s incl. generation)"},
                "clocks": clocks, "e2e": e2e, "gpu_launches": int(launches), "roofline": roofline, "cpu_baseline": cpu}
-        print(json.dumps(out), flush=True)
+        emit(out)
     ctx.close()
     if dist:
         dist.destroy_process_group()

@@ -108,6 +108,10 @@ int jrb_set_tables(jrb_context *ctx, const jrb_tbl_view *tbl);
 /* host-only (no GPU needed): properties of the packed form of a table set */
 int jrb_tables_pack_info(const jrb_tbl_view *tbl, int ng, int nd, size_t *nbytes, int *all_shared, int *monotone,
                          unsigned long long *n_entries);
+/* host-only: the packed blob itself (out == NULL: query the size); deterministic, so ranks can compare checksums */
+int jrb_tables_pack_host(const jrb_tbl_view *tbl, int ng, int nd, void *out, size_t capacity, size_t *nbytes);
+/* upload a host blob made by jrb_tables_pack_host (e.g. received from another rank) and use it */
+int jrb_tables_upload_blob(jrb_context *ctx, const void *host_blob, size_t nbytes);
 /* multi-GPU: the packed slabs are one position-independent device blob that can be broadcast (e.g. NCCL) */
 int jrb_tables_blob(jrb_context *ctx, void **dev_ptr, size_t *nbytes);
 int jrb_tables_alloc_blob(jrb_context *ctx, size_t nbytes, void **dev_ptr); /* receiver side */

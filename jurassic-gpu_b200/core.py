@@ -43,6 +43,10 @@ def load_core():
     lib.jrb_tables_pack_info.argtypes = [C.POINTER(abi.TblView), C.c_int, C.c_int, C.POINTER(C.c_size_t),
                                          abi.c_int_p, abi.c_int_p, C.POINTER(C.c_ulonglong)]
     lib.jrb_tables_pack_info.restype = C.c_int
+    lib.jrb_tables_pack_host.argtypes = [C.POINTER(abi.TblView), C.c_int, C.c_int, C.c_void_p, C.c_size_t, C.POINTER(C.c_size_t)]
+    lib.jrb_tables_pack_host.restype = C.c_int
+    lib.jrb_tables_upload_blob.argtypes = [vp, C.c_void_p, C.c_size_t]
+    lib.jrb_tables_upload_blob.restype = C.c_int
     lib.jrb_tables_blob.argtypes = [vp, C.POINTER(vp), C.POINTER(C.c_size_t)]
     lib.jrb_tables_alloc_blob.argtypes = [vp, C.c_size_t, C.POINTER(vp)]
     lib.jrb_tables_adopt_blob.argtypes = [vp]
@@ -62,7 +66,7 @@ def load_core():
     return lib
 
 
-EXPORTED_SYMBOLS = ["jrb_tables_pack_info", "jrb_version", "jrb_device_count", "jrb_create", "jrb_destroy", "jrb_last_error",
+EXPORTED_SYMBOLS = ["jrb_tables_pack_host", "jrb_tables_upload_blob", "jrb_tables_pack_info", "jrb_version", "jrb_device_count", "jrb_create", "jrb_destroy", "jrb_last_error",
                     "jrb_set_control", "jrb_set_tables", "jrb_tables_blob", "jrb_tables_alloc_blob",
                     "jrb_tables_adopt_blob", "jrb_set_kernel_variant", "jrb_formod_batch", "jrb_stage",
                     "jrb_run_staged", "jrb_fetch_staged", "jrb_staged_results", "jrb_debug_los", "jrb_get_stats"]
@@ -81,6 +85,21 @@ def tables_pack_info(tbl, ng, nd):
     if rc != 0:
         raise JrbError(f"jrb_tables_pack_info failed ({rc}): {lib.jrb_last_error(None).decode()}")
     return {"nbytes": n.value, "all_shared": sh.value, "monotone": mo.value, "n_entries": ne.value}
+
+
+def tables_pack_host(tbl, ng, nd):
+    """Host-only: the packed, position-independent table blob as a numpy uint8 array (works without a GPU)."""
+    lib = load_core()
+    v = tbl.view()
+    n = C.c_size_t()
+    rc = lib.jrb_tables_pack_host(C.byref(v), ng, nd, None, 0, C.byref(n))
+    if rc != 0:
+        raise JrbError(f"jrb_tables_pack_host failed ({rc}): {lib.jrb_last_error(None).decode()}")
+    out = np.empty(n.value, dtype=np.uint8)
+    rc = lib.jrb_tables_pack_host(C.byref(v), ng, nd, out.ctypes.data_as(C.c_void_p), out.size, C.byref(n))
+    if rc != 0:
+        raise JrbError(f"jrb_tables_pack_host failed ({rc}): {lib.jrb_last_error(None).decode()}")
+    return out
 
 
 # ---------------------------------------------------------------------------------------------------------------
@@ -253,6 +272,10 @@ class Context:
         p = C.c_void_p()
         self._check(self.lib.jrb_tables_alloc_blob(self.h, nbytes, C.byref(p)), "jrb_tables_alloc_blob")
         return p.value
+
+    def tables_upload_blob(self, blob):
+        blob = np.ascontiguousarray(blob, dtype=np.uint8)
+        self._check(self.lib.jrb_tables_upload_blob(self.h, blob.ctypes.data_as(C.c_void_p), blob.size), "jrb_tables_upload_blob")
 
     def tables_adopt_blob(self):
         self._check(self.lib.jrb_tables_adopt_blob(self.h), "jrb_tables_adopt_blob")

@@ -13,6 +13,7 @@
 #include <cstdio>
 #include <cstring>
 #include <mutex>
+#include <thread>
 
 using namespace jrb;
 
@@ -48,6 +49,18 @@ struct PinBuf {
 std::string g_create_error;
 
 inline size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
+
+// host threads for packing / scattering packages.  Launchers such as torchrun export OMP_NUM_THREADS=1, which would
+// serialise the host side of the end-to-end path, so the count is taken from JRB_HOST_THREADS or the hardware.
+inline int host_threads() {
+  static int n = 0;
+  if (n == 0) {
+    n = 8;
+    if (const char *s = getenv("JRB_HOST_THREADS")) { int v = atoi(s); if (v > 0) n = v; }
+    else { int hw = (int)std::thread::hardware_concurrency(); if (hw > 0 && hw < n) n = hw; }
+  }
+  return n;
+}
 
 } // namespace
 
@@ -233,6 +246,33 @@ int jrb_tables_pack_info(const jrb_tbl_view *tbl, int ng, int nd, size_t *nbytes
   return JRB_OK;
 }
 
+// host-only: the packed blob itself (call with out == NULL to query the size)
+int jrb_tables_pack_host(const jrb_tbl_view *tbl, int ng, int nd, void *out, size_t capacity, size_t *nbytes) {
+  if (!tbl || !nbytes) return JRB_ERR_ARG;
+  std::vector<unsigned char> blob;
+  std::string err;
+  int rc = pack_tables(*tbl, ng, nd, blob, err);
+  if (rc != JRB_OK) { g_create_error = err; return rc; }
+  *nbytes = blob.size();
+  if (out) {
+    if (capacity < blob.size()) { g_create_error = "jrb_tables_pack_host: buffer too small"; return JRB_ERR_ARG; }
+    std::memcpy(out, blob.data(), blob.size());
+  }
+  return JRB_OK;
+}
+
+// upload a blob produced by jrb_tables_pack_host (possibly on another rank) and adopt it
+int jrb_tables_upload_blob(jrb_context *ctx, const void *host_blob, size_t nbytes) {
+  if (!ctx || !host_blob || nbytes < sizeof(TblHeader)) return JRB_ERR_ARG;
+  std::lock_guard<std::mutex> lk(ctx->mtx);
+  if (!ctx->have_ctl) return ctx->fail(JRB_ERR_STATE, "jrb_set_control must be called first");
+  CU(cudaSetDevice(ctx->device));
+  CU(ctx->d_blob.ensure(nbytes));
+  ctx->blob_bytes = nbytes;
+  CU(cudaMemcpy(ctx->d_blob.p, host_blob, nbytes, cudaMemcpyHostToDevice));
+  return adopt_blob_locked(ctx);
+}
+
 int jrb_tables_blob(jrb_context *ctx, void **dev_ptr, size_t *nbytes) {
   if (!ctx || !dev_ptr || !nbytes) return JRB_ERR_ARG;
   std::lock_guard<std::mutex> lk(ctx->mtx);
@@ -342,7 +382,7 @@ int jrb_stage(jrb_context *ctx, int npk, const jrb_atm_view *atm, const jrb_obs_
 
   ctx->nan_mask.clear();
   std::vector<std::vector<std::pair<long long, int>>> masks(npk);
-#pragma omp parallel for schedule(dynamic, 4)
+#pragma omp parallel for schedule(dynamic, 4) num_threads(host_threads())
   for (int k = 0; k < npk; k++) {
     const jrb_obs_view &o = obs[k];
     const jrb_atm_view &a = atm[k];
@@ -499,7 +539,7 @@ int jrb_fetch_staged(jrb_context *ctx, int npk, const jrb_obs_view *obs) {
   double *hrad = (double *)ctx->h_out.p, *htau = hrad + (size_t)R * nd, *htp = htau + (size_t)R * nd;
   const double nan = std::nan("");
   for (auto &m : ctx->nan_mask) hrad[(size_t)m.first * nd + m.second] = nan; // apply_mask (src/jr_common.h:203-210)
-#pragma omp parallel for schedule(dynamic, 4)
+#pragma omp parallel for schedule(dynamic, 4) num_threads(host_threads())
   for (int k = 0; k < npk; k++) {
     const jrb_obs_view &o = obs[k];
     const long long r0 = ctx->pk_ray_off[k];
