@@ -33,7 +33,8 @@ struct TblHeader {
   int32_t ng, nd, npmax, ntmax;
   int32_t all_shared; // 1: every gas has channel-independent (p,T) axes -> fast kernel allowed
   int32_t monotone;   // 1: every column is non-decreasing in u and eps  -> hinted search == reference bisection
-  int32_t pad0, pad1;
+  int32_t max_nu;     // longest column (the specialised kernel packs bracket indices into 10 bits)
+  int32_t pad1;
   // byte offsets from blob start
   uint64_t off_np;      // int32  [ng][nd]
   uint64_t off_nt;      // int32  [ng][npmax][nd]

@@ -69,6 +69,9 @@ template <bool ON_EPS>
 __device__ __forceinline__ float hi_of(const float4 b) { return ON_EPS ? b.w : b.z; }
 
 // Move (k, b) so that  val[k] <= x < val[k+1]  with k clipped to [0, nu-2]  (== reference bisection result).
+// The neighbouring bracket is tried first.  Larger upward moves of the column-density lookup (long segments near the
+// tangent point add several grid steps at once) jump by the distance estimated from the local grid ratio -- the u axes
+// of JURASSIC tables are geometric -- and whatever is still not bracketed goes to the out-of-line bisection.
 template <bool ON_EPS>
 __device__ __forceinline__ void relocate(const float4 *__restrict__ col, const int nu, const double x, int &k, float4 &b) {
   if (x < (double)lo_of<ON_EPS>(b)) {
@@ -79,7 +82,19 @@ __device__ __forceinline__ void relocate(const float4 *__restrict__ col, const i
   } else if (x >= (double)hi_of<ON_EPS>(b)) {
     if (k < nu - 2) {
       ++k; b = col[k];
-      if (k < nu - 2 && x >= (double)hi_of<ON_EPS>(b)) { k = search_range(col, k, nu - 1, x, ON_EPS); b = col[k]; }
+      if (k < nu - 2 && x >= (double)hi_of<ON_EPS>(b)) {
+        if (!ON_EPS) {
+          const float l0 = __log2f(b.x), r = __log2f(b.z) - l0;
+          const float d = (r > 0.f) ? fminf((__log2f((float)x) - l0) * __frcp_rn(r), 65535.f) : 1.f;
+          const int k0 = k;
+          k = min(k0 + max((int)d, 1), nu - 2);
+          b = col[k];
+          if (x < (double)b.x) { k = search_range(col, k0, k, x, 0); b = col[k]; }
+          else if (k < nu - 2 && x >= (double)b.z) { k = search_range(col, k, nu - 1, x, 0); b = col[k]; }
+        } else {
+          k = search_range(col, k, nu - 1, x, 1); b = col[k];
+        }
+      }
     }
   }
 }
@@ -93,6 +108,39 @@ __device__ __forceinline__ double column_finish(const float4 *__restrict__ col, 
   const double x = ustar + useg;
   relocate<false>(col, nu, x, k, b);
   return clamp01(lerp_fast((double)b.x, (double)b.y, (double)b.z, (double)b.w, x));
+}
+
+// table cell of gas ig in the staged LOS record: ipr | it0 << 8 | it1 << 16, or kCellInvalid
+__device__ __forceinline__ unsigned load_cell(const double *__restrict__ R, const LosLayout &L, const int ig) {
+  return (unsigned)__double_as_longlong(R[L.c0 + 4 * ig + 3]);
+}
+
+// the four column descriptors of a cell, one 8-byte load each (coalesced over the channels of a warp)
+__device__ __forceinline__ void load_coldesc(const TblDev &T, const int ig, const unsigned cell, const int nd, const int id,
+                                             uint2 &c00, uint2 &c01, uint2 &c10, uint2 &c11) {
+  const unsigned c = (cell == kCellInvalid) ? 0u : cell; // any valid address; the result is ignored for an invalid cell
+  const int ipr = c & 0xff, it0 = (c >> 8) & 0xff, it1 = (c >> 16) & 0xff;
+  const uint2 *__restrict__ q0 = T.col + (((size_t)ig * T.npmax + ipr) * T.ntmax + it0) * nd + id;
+  const uint2 *__restrict__ q1 = T.col + (((size_t)ig * T.npmax + ipr + 1) * T.ntmax + it1) * nd + id;
+  c00 = __ldg(q0); c01 = __ldg(q0 + nd); c10 = __ldg(q1); c11 = __ldg(q1 + nd);
+}
+
+// Hints follow the COLUMN, not the slot: when the ray moves to a neighbouring (p,T) cell, every new slot inherits the
+// hint of the old slot that addressed the same column (or, failing that, the nearest one on the nearest level).
+// h = 4 x 10-bit bracket indices | cell << 40.  Returns the remapped hints (cell bits are rewritten by the caller).
+__device__ __forceinline__ unsigned long long remap_hints(const unsigned long long h, const unsigned ocell, const unsigned cell) {
+  const int oipr = ocell & 0xff, oit0 = (ocell >> 8) & 0xff, oit1 = (ocell >> 16) & 0xff;
+  const int ipr = cell & 0xff, it0 = (cell >> 8) & 0xff, it1 = (cell >> 16) & 0xff;
+  unsigned long long out = 0;
+#pragma unroll
+  for (int s = 0; s < 4; s++) {
+    const int ip = ipr + (s >> 1), it = ((s >> 1) ? it1 : it0) + (s & 1);
+    const bool upper = (ip == oipr + 1) || (ip != oipr && ip > oipr); // old level to borrow from
+    const int oit = upper ? oit1 : oit0;
+    const int sel = (upper ? 2 : 0) + (it > oit ? 1 : 0);
+    out |= ((h >> (10 * sel)) & 0x3ffull) << (10 * s);
+  }
+  return out;
 }
 
 } // namespace fast
@@ -183,8 +231,18 @@ __global__ void __launch_bounds__(kEgaBlock, JRB_EGA_MINBLOCKS) ega_fast_kernel(
 
       double tau_gas = 1.0;
       bool any_opaque = false;
+      // column descriptors of gas 0; inside the loop those of gas ig+1 are requested before gas ig is computed
+      uint2 n00, n01, n10, n11;
+      unsigned ncell = fast::load_cell(R, L, 0);
+      fast::load_coldesc(T, 0, ncell, nd, id, n00, n01, n10, n11);
 #pragma unroll 1
       for (int ig = 0; ig < ng; ig++) {
+        const uint2 c00 = n00, c01 = n01, c10 = n10, c11 = n11;
+        const unsigned cell = ncell;
+        if (ig + 1 < ng) {
+          ncell = fast::load_cell(R, L, ig + 1);
+          fast::load_coldesc(T, ig + 1, ncell, nd, id, n00, n01, n10, n11);
+        }
         const double tp = tau_s[ig * sstride];
         double f;
         if (tp < 1e-9) {
@@ -192,33 +250,28 @@ __global__ void __launch_bounds__(kEgaBlock, JRB_EGA_MINBLOCKS) ega_fast_kernel(
           any_opaque = true;
         } else {
           f = 1.0;
-          const double *__restrict__ cw = R + L.c0 + 4 * ig;
-          const unsigned cell = (unsigned)__double_as_longlong(cw[3]);
           unsigned long long h = hint_s[ig * sstride];
-          if (h != ~0ull && cell != kCellInvalid) {
-            const int ipr = cell & 0xff, it0 = (cell >> 8) & 0xff, it1 = (cell >> 16) & 0xff;
-            const size_t g0 = (((size_t)ig * T.npmax + ipr) * T.ntmax + it0) * nd + id;
-            const size_t g1 = (((size_t)ig * T.npmax + ipr + 1) * T.ntmax + it1) * nd + id;
-            const uint2 c00 = T.col[g0], c01 = T.col[g0 + nd], c10 = T.col[g1], c11 = T.col[g1 + nd];
-            if (c00.y >= 2 && c01.y >= 2 && c10.y >= 2 && c11.y >= 2) {
-              const float4 *__restrict__ p00 = T.brk + c00.x, *__restrict__ p01 = T.brk + c01.x,
-                                         *__restrict__ p10 = T.brk + c10.x, *__restrict__ p11 = T.brk + c11.x;
-              int k00 = min((int)(h & 0xffffu), (int)c00.y - 2), k01 = min((int)((h >> 16) & 0xffffu), (int)c01.y - 2),
-                  k10 = min((int)((h >> 32) & 0xffffu), (int)c10.y - 2), k11 = min((int)(h >> 48), (int)c11.y - 2);
-              // the four hinted brackets are requested back to back: their latencies overlap
-              const float4 b00 = p00[k00], b01 = p01[k01], b10 = p10[k10], b11 = p11[k11];
-              const double eps = 1 - tp, useg = R[L.u0 + ig];
-              const double e00 = fast::column_finish(p00, (int)c00.y, eps, useg, k00, b00);
-              const double e01 = fast::column_finish(p01, (int)c01.y, eps, useg, k01, b01);
-              const double e10 = fast::column_finish(p10, (int)c10.y, eps, useg, k10, b10);
-              const double e11 = fast::column_finish(p11, (int)c11.y, eps, useg, k11, b11);
-              hint_s[ig * sstride] = (unsigned long long)k00 | ((unsigned long long)k01 << 16) |
-                                     ((unsigned long long)k10 << 32) | ((unsigned long long)k11 << 48);
-              const double ep0 = clamp01(fma(cw[1], e01 - e00, e00));
-              const double ep1 = clamp01(fma(cw[2], e11 - e10, e10));
-              const double ept = clamp01(fma(cw[0], ep1 - ep0, ep0));
-              f = (1. - ept) * fast_rcp(tp);
-            }
+          if (h != ~0ull && cell != kCellInvalid && c00.y >= 2 && c01.y >= 2 && c10.y >= 2 && c11.y >= 2) {
+            const unsigned ocell = (unsigned)(h >> 40);
+            if (ocell != cell) h = fast::remap_hints(h, ocell, cell); // warp-uniform: the cell belongs to the ray
+            const float4 *__restrict__ p00 = T.brk + c00.x, *__restrict__ p01 = T.brk + c01.x,
+                                       *__restrict__ p10 = T.brk + c10.x, *__restrict__ p11 = T.brk + c11.x;
+            int k00 = min((int)(h & 0x3ffu), (int)c00.y - 2), k01 = min((int)((h >> 10) & 0x3ffu), (int)c01.y - 2),
+                k10 = min((int)((h >> 20) & 0x3ffu), (int)c10.y - 2), k11 = min((int)((h >> 30) & 0x3ffu), (int)c11.y - 2);
+            // the four hinted brackets are requested back to back: their latencies overlap
+            const float4 b00 = p00[k00], b01 = p01[k01], b10 = p10[k10], b11 = p11[k11];
+            const double *__restrict__ cw = R + L.c0 + 4 * ig;
+            const double eps = 1 - tp, useg = R[L.u0 + ig];
+            const double e00 = fast::column_finish(p00, (int)c00.y, eps, useg, k00, b00);
+            const double e01 = fast::column_finish(p01, (int)c01.y, eps, useg, k01, b01);
+            const double e10 = fast::column_finish(p10, (int)c10.y, eps, useg, k10, b10);
+            const double e11 = fast::column_finish(p11, (int)c11.y, eps, useg, k11, b11);
+            hint_s[ig * sstride] = (unsigned long long)k00 | ((unsigned long long)k01 << 10) | ((unsigned long long)k10 << 20) |
+                                   ((unsigned long long)k11 << 30) | ((unsigned long long)cell << 40);
+            const double ep0 = clamp01(fma(cw[1], e01 - e00, e00));
+            const double ep1 = clamp01(fma(cw[2], e11 - e10, e10));
+            const double ept = clamp01(fma(cw[0], ep1 - ep0, ep0));
+            f = (1. - ept) * fast_rcp(tp);
           }
           const double tn = tp * f;
           tau_s[ig * sstride] = tn;

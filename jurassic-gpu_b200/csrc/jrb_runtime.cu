@@ -429,10 +429,10 @@ int jrb_stage(jrb_context *ctx, int npk, const jrb_atm_view *atm, const jrb_obs_
   CU(ctx->d_level0.ensure((size_t)(R ? R : 1) * 4));
 
   // kernel choice + LOS buffer
-  const bool fast_ok = ctx->th.all_shared && ctx->th.monotone && ega_fast_available(ng, ctx->ctm_mask);
+  const bool fast_ok = ctx->th.all_shared && ctx->th.monotone && ctx->th.max_nu <= 1023 && ega_fast_available(ng, ctx->ctm_mask);
   if (ctx->variant_req == 1 && !fast_ok)
     return ctx->fail(JRB_ERR_STATE, std::string("specialised kernel not applicable: shared_axes=") + std::to_string(ctx->th.all_shared) +
-                     " monotone=" + std::to_string(ctx->th.monotone) + " ng=" + std::to_string(ng) + " mask=" + std::to_string(ctx->ctm_mask) +
+                     " monotone=" + std::to_string(ctx->th.monotone) + " max_nu=" + std::to_string(ctx->th.max_nu) + " ng=" + std::to_string(ng) + " mask=" + std::to_string(ctx->ctm_mask) +
                      " built=" + std::to_string((int)ega_fast_available(ng, ctx->ctm_mask)));
   ctx->use_fast = (ctx->variant_req == 0) ? 0 : (fast_ok ? 1 : 0);
   ctx->los = make_los_layout(ng, nw, ctx->use_fast);

@@ -71,6 +71,7 @@ int pack_tables(const jrb_tbl_view &v, int ng, int nd, std::vector<unsigned char
   const size_t ncol = (size_t)ng * npmax * ntmax * nd;
   std::vector<uint32_t> col_first(ncol, 0), col_nu(ncol, 0);
   uint64_t n_entries = 0;
+  int max_nu = 0;
   for (int g = 0; g < ng; g++)
     for (int d = 0; d < nd; d++) { // pair-major order: one (gas,channel) slab is contiguous
       const int np = NPv(g, d);
@@ -81,6 +82,7 @@ int pack_tables(const jrb_tbl_view &v, int ng, int nd, std::vector<unsigned char
           if (nu < 0 || nu > (int)U) { err = "pack_tables: nu out of range"; return JRB_ERR_ARG; }
           const size_t c = (((size_t)g * npmax + ip) * ntmax + it) * nd + d;
           col_nu[c] = (uint32_t)nu;
+          if (nu > max_nu) max_nu = nu;
           if (nu >= 2) { col_first[c] = (uint32_t)n_entries; n_entries += (uint64_t)nu; }
         }
       }
@@ -93,6 +95,7 @@ int pack_tables(const jrb_tbl_view &v, int ng, int nd, std::vector<unsigned char
   h.magic = kTblMagic;
   h.ng = ng; h.nd = nd; h.npmax = npmax; h.ntmax = ntmax; h.all_shared = all_shared; h.monotone = 1;
   h.n_entries = n_entries;
+  h.max_nu = max_nu;
   size_t off = align_up(sizeof(TblHeader), 256);
   auto place = [&](uint64_t &dst, size_t bytes) { dst = off; off = align_up(off + bytes, 256); };
   place(h.off_np, sizeof(int32_t) * ng * nd);
