@@ -231,18 +231,27 @@ __global__ void __launch_bounds__(kEgaBlock, JRB_EGA_MINBLOCKS) ega_fast_kernel(
 
       double tau_gas = 1.0;
       bool any_opaque = false;
-      // column descriptors of gas 0; inside the loop those of gas ig+1 are requested before gas ig is computed
       uint2 n00, n01, n10, n11;
-      unsigned ncell = fast::load_cell(R, L, 0);
+      unsigned ncell;
+#ifdef JRB_PREFETCH_NEXT_GAS
+      // column descriptors of gas 0; inside the loop those of gas ig+1 are requested before gas ig is computed
+      ncell = fast::load_cell(R, L, 0);
       fast::load_coldesc(T, 0, ncell, nd, id, n00, n01, n10, n11);
+#endif
 #pragma unroll 1
       for (int ig = 0; ig < ng; ig++) {
+#ifndef JRB_PREFETCH_NEXT_GAS
+        ncell = fast::load_cell(R, L, ig);
+        fast::load_coldesc(T, ig, ncell, nd, id, n00, n01, n10, n11);
+#endif
         const uint2 c00 = n00, c01 = n01, c10 = n10, c11 = n11;
         const unsigned cell = ncell;
+#ifdef JRB_PREFETCH_NEXT_GAS // measured: no gain at 3 CTAs/SM (profiles/README.md), costs registers
         if (ig + 1 < ng) {
           ncell = fast::load_cell(R, L, ig + 1);
           fast::load_coldesc(T, ig + 1, ncell, nd, id, n00, n01, n10, n11);
         }
+#endif
         const double tp = tau_s[ig * sstride];
         double f;
         if (tp < 1e-9) {

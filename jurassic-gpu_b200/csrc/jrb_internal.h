@@ -16,7 +16,7 @@ struct TraceArgs {
   const double *atm_time, *atm_z, *atm_lon, *atm_lat, *atm_p, *atm_t;
   const double *atm_q, *atm_k; // [ng][atm_stride], [nw][atm_stride]
   long long atm_stride;
-  double *atm_lnp_slope;       // [atm_stride] scratch: log(p[i+1]/p[i])/(z[i+1]-z[i]), NaN where not both positive
+  double *atm_lnp_slope;       // [2][atm_stride] scratch: log(p[i+1]/p[i])/(z[i+1]-z[i]) (NaN where not both positive), dT/dz
   long long n_atm;
   int prepare_atm;             // 1: (re)compute atm_lnp_slope before tracing
   // control

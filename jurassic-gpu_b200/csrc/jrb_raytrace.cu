@@ -5,7 +5,7 @@
 // :624-691 with refraction :664-681, tangent point :502-539, trapezoid rule :437-443, column density
 // :446-453), split by what is sequential and what is not:
 //
-//   atm_slopes_kernel    per atmosphere level: d ln p / dz of the exponential pressure interpolation (eip, :53-57),
+//   atm_slopes_kernel    per atmosphere level: d ln p / dz of the exponential pressure interpolation (eip, :53-57) and dT/dz,
 //                        so that the stepping loop needs one exp but no log and no division per interpolation;
 //   ray_step_kernel      one thread per ray, the inherently sequential part: walk the ray, per point altitude,
 //                        p, T (5 interpolations per step with refraction), raw step length, Cartesian position.
@@ -40,7 +40,7 @@ __device__ __forceinline__ void cart_to_lonlat(const double x[3], double *lon, d
 // ascending axis, max{i <= n-2 : z[i] <= x} (0 if x < z[0]); for a descending one max{i <= n-2 : z[i] > x}.
 // The level found for the previous evaluation is tried first; the bisection runs only when it does not bracket x.
 struct Profile {
-  const double *__restrict__ z, *__restrict__ p, *__restrict__ t, *__restrict__ slope;
+  const double *__restrict__ z, *__restrict__ p, *__restrict__ t, *__restrict__ pslope, *__restrict__ tslope;
   int n;
   bool asc;
 
@@ -56,13 +56,16 @@ struct Profile {
     else     { while (ihi > ilo + 1) { const int i = (ihi + ilo) >> 1; if (z[i] <= x) ihi = i; else ilo = i; } }
     return ilo;
   }
-  // intpol_atm_1d_pt (:549-555): p exponential (eip :53-57), T linear (lip :48-50)
+  // intpol_atm_1d_pt (:549-555): p exponential (eip :53-57), T linear (lip :48-50), with per-level slopes
+  __device__ __forceinline__ void eval(double x, int level, double *pp, double *tt) const {
+    const double dx = x - z[level], s = pslope[level];
+    if (s == s) *pp = p[level] * exp(s * dx);                                     // both pressures positive
+    else *pp = p[level] + dx * (p[level + 1] - p[level]) / (z[level + 1] - z[level]); // linear fallback of eip
+    *tt = fma(dx, tslope[level], t[level]);
+  }
   __device__ __forceinline__ void pt(double x, int &level, double *pp, double *tt) const {
     level = locate(x, level);
-    const double x0 = z[level], dx = x - x0, s = slope[level];
-    if (s == s) *pp = p[level] * exp(s * dx);                                        // both pressures positive
-    else *pp = p[level] + dx * (p[level + 1] - p[level]) / (z[level + 1] - x0);      // linear fallback of eip
-    *tt = t[level] + dx * (t[level + 1] - t[level]) / (z[level + 1] - x0);
+    eval(x, level, pp, tt);
   }
 };
 
@@ -70,16 +73,18 @@ __device__ __forceinline__ double refractivity(double p, double t) { return 7.75
 
 } // namespace
 
-__global__ void atm_slopes_kernel(const double *__restrict__ z, const double *__restrict__ p, double *__restrict__ slope,
-                                  long long n) {
+__global__ void atm_slopes_kernel(const double *__restrict__ z, const double *__restrict__ p, const double *__restrict__ t,
+                                  double *__restrict__ pslope, double *__restrict__ tslope, long long n) {
   const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n) return;
-  double s = __longlong_as_double(0x7ff8000000000000ll);
+  double sp = __longlong_as_double(0x7ff8000000000000ll), st = 0.0;
   if (i + 1 < n) {
-    const double y0 = p[i], y1 = p[i + 1];
-    if (y0 > 0 && y1 > 0) s = log(y1 / y0) / (z[i + 1] - z[i]);
+    const double y0 = p[i], y1 = p[i + 1], dz = z[i + 1] - z[i];
+    if (y0 > 0 && y1 > 0) sp = log(y1 / y0) / dz;
+    st = (t[i + 1] - t[i]) / dz;
   }
-  slope[i] = s;
+  pslope[i] = sp;
+  tslope[i] = st;
 }
 
 __global__ void __launch_bounds__(128) ray_step_kernel(TraceArgs a) {
@@ -116,7 +121,8 @@ __global__ void __launch_bounds__(128) ray_step_kernel(TraceArgs a) {
   P.z = a.atm_z + abase + lower;
   P.p = a.atm_p + abase + lower;
   P.t = a.atm_t + abase + lower;
-  P.slope = a.atm_lnp_slope + abase + lower;
+  P.pslope = a.atm_lnp_slope + abase + lower;
+  P.tslope = a.atm_lnp_slope + a.atm_stride + abase + lower;
   { const int m = (P.n - 1) >> 1; P.asc = P.z[m] < P.z[m + 1]; }
   const double *__restrict__ alon = a.atm_lon + abase + lower;
   const double *__restrict__ alat = a.atm_lat + abase + lower;
@@ -156,7 +162,7 @@ __global__ void __launch_bounds__(128) ray_step_kernel(TraceArgs a) {
       const double rn = norm3(x);
       double ds = a.rayds;
       if (a.raydz > 0.0) { // step length from the angle to the local vertical (:625-635)
-        const double inv = 1.0 / rn;
+        const double inv = fast_rcp(rn);
         double dot = 0.0;
         for (int i = 0; i < 3; i++) dot += ex0[i] * x[i] * inv;
         const double cosa = fabs(dot);
@@ -188,24 +194,29 @@ __global__ void __launch_bounds__(128) ray_step_kernel(TraceArgs a) {
       double nref = 1.0, ngr[3] = {0.0, 0.0, 0.0};
       if (a.refrac && z <= 60.0) { // refractivity gradient by finite differences at the half step (:664-681)
         nref += refractivity(p, t);
-        double xh[3], ph, th;
-        int lv = level;
+        // the four probe points (half step, and half step + h along each axis) are independent: altitudes, level
+        // searches and the exponentials are evaluated side by side
+        const double h = 0.02;
+        double xh[3], zz[4], ph[4], th[4];
+        int lv[4];
         for (int i = 0; i < 3; i++) xh[i] = x[i] + 0.5 * ds * ex0[i];
-        P.pt(norm3(xh) - kRE, lv, &ph, &th);
-        const double n2 = refractivity(ph, th);
-        for (int i = 0; i < 3; i++) {
-          const double h = 0.02;
-          xh[i] += h;
-          P.pt(norm3(xh) - kRE, lv, &ph, &th);
-          ngr[i] = (refractivity(ph, th) - n2) / h;
-          xh[i] -= h;
-        }
+        const double r2 = xh[0] * xh[0] + xh[1] * xh[1] + xh[2] * xh[2];
+        zz[0] = sqrt(r2) - kRE;
+#pragma unroll
+        for (int i = 0; i < 3; i++) zz[1 + i] = sqrt(fma(h, fma(2.0, xh[i], h), r2)) - kRE; // |xh + h e_i|
+#pragma unroll
+        for (int j = 0; j < 4; j++) lv[j] = P.locate(zz[j], level);
+#pragma unroll
+        for (int j = 0; j < 4; j++) P.eval(zz[j], lv[j], &ph[j], &th[j]);
+        const double n2 = refractivity(ph[0], th[0]);
+#pragma unroll
+        for (int i = 0; i < 3; i++) ngr[i] = (refractivity(ph[1 + i], th[1 + i]) - n2) * (1.0 / h);
       }
       double ex1[3];
       for (int i = 0; i < 3; i++) ex1[i] = ex0[i] * nref + ds * ngr[i];
-      const double n1 = norm3(ex1);
+      const double in1 = fast_rcp(norm3(ex1));
       for (int i = 0; i < 3; i++) {
-        ex1[i] /= n1;
+        ex1[i] *= in1;
         x[i] += 0.5 * ds * (ex0[i] + ex1[i]);
         ex0[i] = ex1[i];
       }
@@ -312,7 +323,8 @@ __global__ void __launch_bounds__(256) los_finalize_kernel(TraceArgs a) {
 cudaError_t launch_raytrace(const TraceArgs &a, cudaStream_t stream, int *launches) {
   if (launches) *launches = 0;
   if (a.prepare_atm && a.n_atm > 0) {
-    atm_slopes_kernel<<<(unsigned)((a.n_atm + 255) / 256), 256, 0, stream>>>(a.atm_z, a.atm_p, a.atm_lnp_slope, a.n_atm);
+    atm_slopes_kernel<<<(unsigned)((a.n_atm + 255) / 256), 256, 0, stream>>>(a.atm_z, a.atm_p, a.atm_t, a.atm_lnp_slope,
+                                                                            a.atm_lnp_slope + a.atm_stride, a.n_atm);
     if (launches) ++*launches;
   }
   if (a.n_rays <= 0) return cudaGetLastError();

@@ -425,7 +425,7 @@ int jrb_stage(jrb_context *ctx, int npk, const jrb_atm_view *atm, const jrb_obs_
   CU(ctx->d_np.ensure((size_t)(R ? R : 1) * 4));
   CU(ctx->d_tsurf.ensure((size_t)(R ? R : 1) * 8));
   CU(ctx->d_counter.ensure(256));
-  CU(ctx->d_slope.ensure((size_t)(A ? A : 1) * 8));
+  CU(ctx->d_slope.ensure((size_t)(A ? A : 1) * 16));
   CU(ctx->d_level0.ensure((size_t)(R ? R : 1) * 4));
 
   // kernel choice + LOS buffer

