@@ -44,13 +44,16 @@ struct Profile {
   int n;
   bool asc;
 
+  __device__ __forceinline__ bool brackets(double x, int i) const {
+    const double zl = z[i], zh = z[i + 1];
+    return asc ? ((zl <= x || i == 0) && (zh > x || i == n - 2)) : ((zl > x || i == 0) && (zh <= x || i == n - 2));
+  }
   __device__ __forceinline__ int locate(double x, int hint) const {
-    const double zl = z[hint], zh = z[hint + 1];
-    if (asc) {
-      if ((zl <= x || hint == 0) && (zh > x || hint == n - 2)) return hint;
-    } else {
-      if ((zl > x || hint == 0) && (zh <= x || hint == n - 2)) return hint;
-    }
+    if (brackets(x, hint)) return hint;
+    // a step moves the point by at most one level in practice: try the neighbour before bisecting
+    const bool up = asc ? (x >= z[hint + 1]) : (x < z[hint + 1]);
+    const int nb = up ? min(hint + 1, n - 2) : max(hint - 1, 0);
+    if (brackets(x, nb)) return nb;
     int ilo = 0, ihi = n - 1;
     if (asc) { while (ihi > ilo + 1) { const int i = (ihi + ilo) >> 1; if (z[i] > x) ihi = i; else ilo = i; } }
     else     { while (ihi > ilo + 1) { const int i = (ihi + ilo) >> 1; if (z[i] <= x) ihi = i; else ilo = i; } }
