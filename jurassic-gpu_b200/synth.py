@@ -233,3 +233,36 @@ def write_ascii_tables(ctl, tbl, directory, base):
                         for iu in range(n):
                             fh.write("%.17g %.17g %.9g %.9g\n" % (p, t, tbl.u[ig, ip, it, iu, d], tbl.eps[ig, ip, it, iu, d]))
     return os.path.join(directory, base)
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# ASCII inputs of the reference's command-line tools (formats: SURVEY.md Appendix B)
+def write_ctl(ctl, path, tblbase, extra=()):
+    """KEY = VALUE control file as parsed by scan_ctl (src/jurassic.c:1153-1201)."""
+    with open(path, "w") as f:
+        f.write("TBLBASE = %s\nNG = %d\n" % (tblbase, ctl.ng))
+        for i, e in enumerate(ctl.emitters):
+            f.write("EMITTER[%d] = %s\n" % (i, e))
+        f.write("ND = %d\n" % ctl.nd)
+        for i, nu in enumerate(ctl.nu):
+            f.write("NU[%d] = %.4f\n" % (i, nu))
+        f.write("REFRAC = %d\nRAYDS = %g\nRAYDZ = %g\nHYDZ = %g\nWRITE_BBT = %d\n" % (ctl.refrac, ctl.rayds, ctl.raydz, ctl.hydz, ctl.write_bbt))
+        f.write("READ_BINARY = 0\nWRITE_BINARY = 0\n")
+        for k, v in extra:
+            f.write("%s = %s\n" % (k, v))
+
+
+def write_obs_tab(pkg, path):
+    """read_obs format (src/jurassic.c:1041-1068): 10 geometry columns + rad[nd] + tau[nd] per ray."""
+    with open(path, "w") as f:
+        for r in range(pkg.n_rays):
+            cols = [pkg.time[r], pkg.obsz[r], pkg.obslon[r], pkg.obslat[r], pkg.vpz[r], pkg.vplon[r], pkg.vplat[r], 0, 0, 0]
+            f.write(" ".join("%.17g" % c for c in cols) + " " + " ".join(["0"] * (2 * pkg.nd)) + "\n")
+
+
+def write_atm_tab(pkg, path):
+    """read_atm format (src/jurassic.c:882-916): time z lon lat p T q[ng] k[nw]."""
+    with open(path, "w") as f:
+        for i in range(pkg.n_atm):
+            cols = [pkg.atm_time[i], pkg.z[i], pkg.lon[i], pkg.lat[i], pkg.p[i], pkg.t[i]] + list(pkg.q[:pkg.ng, i]) + list(pkg.k[:pkg.nw, i])
+            f.write(" ".join("%.17g" % c for c in cols) + "\n")
