@@ -105,9 +105,11 @@ const char *jrb_last_error(const jrb_context *ctx); /* ctx may be NULL: last err
 int jrb_set_control(jrb_context *ctx, const jrb_ctl_view *ctl);
 /* pack tbl_t into per-(gas,channel) slabs and upload (requires jrb_set_control first) */
 int jrb_set_tables(jrb_context *ctx, const jrb_tbl_view *tbl);
-/* host-only (no GPU needed): properties of the packed form of a table set */
+/* host-only (no GPU needed): properties of the packed form of a table set.  all_shared: the (p,T) axes of every gas do
+ * not depend on the channel; monotone: every column is non-decreasing in u and eps (both are preconditions of the
+ * specialised kernel); gas_axes_same: all gases share one (p,T) grid (one table cell per LOS segment instead of ng) */
 int jrb_tables_pack_info(const jrb_tbl_view *tbl, int ng, int nd, size_t *nbytes, int *all_shared, int *monotone,
-                         unsigned long long *n_entries);
+                         unsigned long long *n_entries, int *gas_axes_same);
 /* host-only: the packed blob itself (out == NULL: query the size); deterministic, so ranks can compare checksums */
 int jrb_tables_pack_host(const jrb_tbl_view *tbl, int ng, int nd, void *out, size_t capacity, size_t *nbytes);
 /* upload a host blob made by jrb_tables_pack_host (e.g. received from another rank) and use it */

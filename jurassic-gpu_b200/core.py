@@ -41,7 +41,7 @@ def load_core():
     lib.jrb_set_control.argtypes = [vp, C.POINTER(abi.CtlView)]
     lib.jrb_set_tables.argtypes = [vp, C.POINTER(abi.TblView)]
     lib.jrb_tables_pack_info.argtypes = [C.POINTER(abi.TblView), C.c_int, C.c_int, C.POINTER(C.c_size_t),
-                                         abi.c_int_p, abi.c_int_p, C.POINTER(C.c_ulonglong)]
+                                         abi.c_int_p, abi.c_int_p, C.POINTER(C.c_ulonglong), abi.c_int_p]
     lib.jrb_tables_pack_info.restype = C.c_int
     lib.jrb_tables_pack_host.argtypes = [C.POINTER(abi.TblView), C.c_int, C.c_int, C.c_void_p, C.c_size_t, C.POINTER(C.c_size_t)]
     lib.jrb_tables_pack_host.restype = C.c_int
@@ -80,11 +80,12 @@ def tables_pack_info(tbl, ng, nd):
     """Host-only: size and properties of the packed device form of `tbl` (works without a GPU)."""
     lib = load_core()
     v = tbl.view()
-    n, sh, mo, ne = C.c_size_t(), C.c_int(), C.c_int(), C.c_ulonglong()
-    rc = lib.jrb_tables_pack_info(C.byref(v), ng, nd, C.byref(n), C.byref(sh), C.byref(mo), C.byref(ne))
+    n, sh, mo, ne, gs = C.c_size_t(), C.c_int(), C.c_int(), C.c_ulonglong(), C.c_int()
+    rc = lib.jrb_tables_pack_info(C.byref(v), ng, nd, C.byref(n), C.byref(sh), C.byref(mo), C.byref(ne), C.byref(gs))
     if rc != 0:
         raise JrbError(f"jrb_tables_pack_info failed ({rc}): {lib.jrb_last_error(None).decode()}")
-    return {"nbytes": n.value, "all_shared": sh.value, "monotone": mo.value, "n_entries": ne.value}
+    return {"nbytes": n.value, "all_shared": sh.value, "monotone": mo.value, "n_entries": ne.value,
+            "gas_axes_same": gs.value}
 
 
 def tables_pack_host(tbl, ng, nd):

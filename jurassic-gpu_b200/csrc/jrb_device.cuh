@@ -34,7 +34,7 @@ struct TblHeader {
   int32_t all_shared; // 1: every gas has channel-independent (p,T) axes -> fast kernel allowed
   int32_t monotone;   // 1: every column is non-decreasing in u and eps  -> hinted search == reference bisection
   int32_t max_nu;     // longest column (the specialised kernel packs bracket indices into 10 bits)
-  int32_t pad1;
+  int32_t gas_axes_same; // 1: all gases that have tables share one (p,T) grid -> one table cell per LOS segment
   // byte offsets from blob start
   uint64_t off_np;      // int32  [ng][nd]
   uint64_t off_nt;      // int32  [ng][npmax][nd]
@@ -80,19 +80,21 @@ enum ChanField {
 };
 
 // ---- LOS record ------------------------------------------------------------------------------------------------
-// doubles: [0]p [1]t [2]ds [3]q_h2o [4..4+nw)k  [U0..U0+ng)u  (fast: [C0+4*ig..) wp,wt0,wt1,cell)
+// doubles: [0]p [1]t [2]ds [3]q_h2o [4..4+nw)k  [U0..U0+ng)u  (fast: {wp,wt0,wt1,cell} once, or per gas if the gases'
+//          (p,T) grids differ)
 //          tail [Z0..Z0+6): altitude z, raw step length, atmosphere level index, Cartesian x,y,z of the point
 // The EGA kernels read only the first `head` doubles of a record (everything before the tail).
 struct LosLayout {
   int nw, ng, fast;
-  int u0, c0, z0, head, rec; // offsets in doubles; head = doubles staged for the EGA kernel; rec = record length
+  int u0, c0, cstride, z0, head, rec; // offsets in doubles; cell block of gas ig at c0 + cstride*ig (cstride 0: shared)
 };
-__host__ __device__ inline LosLayout make_los_layout(int ng, int nw, int fast) {
+__host__ __device__ inline LosLayout make_los_layout(int ng, int nw, int fast, int shared_cell) {
   LosLayout L;
   L.nw = nw; L.ng = ng; L.fast = fast;
   L.u0 = 4 + nw;
   L.c0 = L.u0 + ng;
-  L.z0 = L.c0 + (fast ? 4 * ng : 0);
+  L.cstride = (fast && !shared_cell) ? 4 : 0;
+  L.z0 = L.c0 + (fast ? (shared_cell ? 4 : 4 * ng) : 0);
   L.z0 = (L.z0 + 1) & ~1;       // 16-byte multiples: the head of a record is moved by TMA bulk copies
   L.head = L.z0;
   L.rec = L.z0 + 6;

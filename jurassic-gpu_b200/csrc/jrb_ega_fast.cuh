@@ -112,7 +112,7 @@ __device__ __forceinline__ double column_finish(const float4 *__restrict__ col, 
 
 // table cell of gas ig in the staged LOS record: ipr | it0 << 8 | it1 << 16, or kCellInvalid
 __device__ __forceinline__ unsigned load_cell(const double *__restrict__ R, const LosLayout &L, const int ig) {
-  return (unsigned)__double_as_longlong(R[L.c0 + 4 * ig + 3]);
+  return (unsigned)__double_as_longlong(R[L.c0 + L.cstride * ig + 3]);
 }
 
 // the four column descriptors of a cell, one 8-byte load each (coalesced over the channels of a warp)
@@ -269,7 +269,7 @@ __global__ void __launch_bounds__(kEgaBlock, JRB_EGA_MINBLOCKS) ega_fast_kernel(
                 k10 = min((int)((h >> 20) & 0x3ffu), (int)c10.y - 2), k11 = min((int)((h >> 30) & 0x3ffu), (int)c11.y - 2);
             // the four hinted brackets are requested back to back: their latencies overlap
             const float4 b00 = p00[k00], b01 = p01[k01], b10 = p10[k10], b11 = p11[k11];
-            const double *__restrict__ cw = R + L.c0 + 4 * ig;
+            const double *__restrict__ cw = R + L.c0 + L.cstride * ig;
             const double eps = 1 - tp, useg = R[L.u0 + ig];
             const double e00 = fast::column_finish(p00, (int)c00.y, eps, useg, k00, b00);
             const double e01 = fast::column_finish(p01, (int)c01.y, eps, useg, k01, b01);

@@ -297,8 +297,11 @@ __global__ void __launch_bounds__(256) los_finalize_kernel(TraceArgs a) {
   rec[3] = qh2o;
   if (L.fast) {
     const TblDev &T = a.tbl;
-    for (int ig = 0; ig < L.ng; ig++) {
-      double *__restrict__ c = rec + L.c0 + 4 * ig;
+    const int ncell = L.cstride ? L.ng : 1; // one cell per gas, or one for all gases when they share the (p,T) grid
+    for (int ic = 0; ic < ncell; ic++) {
+      int ig = ic;
+      if (!L.cstride) { ig = 0; while (ig < L.ng - 1 && T.gnp[ig] < 2) ++ig; } // first gas that has a table
+      double *__restrict__ c = rec + L.c0 + L.cstride * ic;
       unsigned cell = kCellInvalid;
       double wp = 0, wt0 = 0, wt1 = 0;
       const int gnp = T.gnp[ig];

@@ -231,7 +231,7 @@ int jrb_set_tables(jrb_context *ctx, const jrb_tbl_view *tbl) {
 
 // host-only: pack and report the properties of the packed form (no GPU needed; used by tests of the packer)
 int jrb_tables_pack_info(const jrb_tbl_view *tbl, int ng, int nd, size_t *nbytes, int *all_shared, int *monotone,
-                         unsigned long long *n_entries) {
+                         unsigned long long *n_entries, int *gas_axes_same) {
   if (!tbl) return JRB_ERR_ARG;
   std::vector<unsigned char> blob;
   std::string err;
@@ -243,6 +243,7 @@ int jrb_tables_pack_info(const jrb_tbl_view *tbl, int ng, int nd, size_t *nbytes
   if (all_shared) *all_shared = h.all_shared;
   if (monotone) *monotone = h.monotone;
   if (n_entries) *n_entries = h.n_entries;
+  if (gas_axes_same) *gas_axes_same = h.gas_axes_same;
   return JRB_OK;
 }
 
@@ -435,7 +436,7 @@ int jrb_stage(jrb_context *ctx, int npk, const jrb_atm_view *atm, const jrb_obs_
                      " monotone=" + std::to_string(ctx->th.monotone) + " max_nu=" + std::to_string(ctx->th.max_nu) + " ng=" + std::to_string(ng) + " mask=" + std::to_string(ctx->ctm_mask) +
                      " built=" + std::to_string((int)ega_fast_available(ng, ctx->ctm_mask)));
   ctx->use_fast = (ctx->variant_req == 0) ? 0 : (fast_ok ? 1 : 0);
-  ctx->los = make_los_layout(ng, nw, ctx->use_fast);
+  ctx->los = make_los_layout(ng, nw, ctx->use_fast, ctx->th.gas_axes_same);
   const size_t per_ray = (size_t)kNLOS * ctx->los.rec * 8;
   double los_gb = 24.0;
   if (const char *s = getenv("JRB_LOS_GB")) { double v = atof(s); if (v > 0.01) los_gb = v; }

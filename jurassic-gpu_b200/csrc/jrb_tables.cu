@@ -67,6 +67,22 @@ int pack_tables(const jrb_tbl_view &v, int ng, int nd, std::vector<unsigned char
     }
   }
 
+  // --- do all gases (that have tables) share one (p,T) grid? ---
+  int gas_axes_same = all_shared;
+  {
+    int g0 = -1;
+    for (int g = 0; g < ng && gas_axes_same; g++) {
+      if (gnp[g] < 2) continue;
+      if (g0 < 0) { g0 = g; continue; }
+      if (gnp[g] != gnp[g0]) { gas_axes_same = 0; break; }
+      for (int ip = 0; ip < gnp[g] && gas_axes_same; ip++) {
+        if (gp[(size_t)g * npmax + ip] != gp[(size_t)g0 * npmax + ip] || gnt[(size_t)g * npmax + ip] != gnt[(size_t)g0 * npmax + ip]) { gas_axes_same = 0; break; }
+        for (int it = 0; it < gnt[(size_t)g * npmax + ip]; it++)
+          if (gt[((size_t)g * npmax + ip) * ntmax + it] != gt[((size_t)g0 * npmax + ip) * ntmax + it]) { gas_axes_same = 0; break; }
+      }
+    }
+  }
+
   // --- column descriptors ---
   const size_t ncol = (size_t)ng * npmax * ntmax * nd;
   std::vector<uint32_t> col_first(ncol, 0), col_nu(ncol, 0);
@@ -96,6 +112,7 @@ int pack_tables(const jrb_tbl_view &v, int ng, int nd, std::vector<unsigned char
   h.ng = ng; h.nd = nd; h.npmax = npmax; h.ntmax = ntmax; h.all_shared = all_shared; h.monotone = 1;
   h.n_entries = n_entries;
   h.max_nu = max_nu;
+  h.gas_axes_same = gas_axes_same;
   size_t off = align_up(sizeof(TblHeader), 256);
   auto place = [&](uint64_t &dst, size_t bytes) { dst = off; off = align_up(off + bytes, 256); };
   place(h.off_np, sizeof(int32_t) * ng * nd);

@@ -169,11 +169,12 @@ T_AXIS = 180.0 + 12.0 * np.arange(12)
 _U_GRID = 1e12 * 10.0 ** (0.05 * np.arange(460))
 
 
-def make_tables(ctl, skip_pairs=(), dim_u=None, axis_jitter=False):
+def make_tables(ctl, skip_pairs=(), dim_u=None, axis_jitter=False, gas_axis_shift=False):
     """Analytic emissivity tables eps(p,T,u) = 1 - exp(-k u)/2 - exp(-0.05 k u)/2 on a geometric u grid.
 
     skip_pairs: iterable of (ig, id) left without a table (-> gas factor 1, like a missing .tab file).
     axis_jitter: give every channel slightly different (p,T) axes (exercises the generic kernel).
+    gas_axis_shift: give every gas its own (channel-independent) (p,T) grid (one table cell per gas and segment).
     Values are float32 exactly as stored in tbl_t (real_tblND_t, src/jurassic.h:387).
     """
     ng, nd = ctl.ng, ctl.nd
@@ -186,8 +187,8 @@ def make_tables(ctl, skip_pairs=(), dim_u=None, axis_jitter=False):
         for d in range(nd):
             if (ig, d) in skip:
                 continue
-            pax = P_AXIS * (1.0 + (1e-3 * ((d * 7 + ig) % 5) if axis_jitter else 0.0))
-            tax = T_AXIS + (0.25 * ((d + ig) % 3) if axis_jitter else 0.0)
+            pax = P_AXIS * (1.0 + (1e-3 * ((d * 7 + ig) % 5) if axis_jitter else 0.0)) * (1.0 + (0.07 * ig if gas_axis_shift else 0.0))
+            tax = T_AXIS + (0.25 * ((d + ig) % 3) if axis_jitter else 0.0) + (1.5 * ig if gas_axis_shift else 0.0)
             kap = kappa0(gas, ig, d) * (0.3 + 0.7 * (pax[:, None] / 1013.25) ** 0.6) * (1.0 + 0.004 * (tax[None, :] - 250.0))
             ku = kap[:, :, None] * ug[None, None, :]
             eps = (1.0 - 0.5 * np.exp(-ku) - 0.5 * np.exp(-0.05 * ku)).astype(np.float32)

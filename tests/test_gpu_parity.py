@@ -144,6 +144,15 @@ def test_channel_dependent_axes_use_generic_kernel(jr, oracle, gpu_ctx_factory):
     assert_parity(mine[0], ref[0], "jitter")
 
 
+def test_gas_dependent_axes_use_per_gas_cells(jr, oracle, gpu_ctx_factory):
+    """every gas has its own (p,T) grid: the LOS records carry one table cell per gas instead of a shared one"""
+    ctl = jr.synth.control_limb_example()
+    tbl = jr.synth.make_tables(ctl, gas_axis_shift=True)
+    info = jr.core.tables_pack_info(tbl, ctl.ng, ctl.nd)
+    assert info["all_shared"] == 1 and info["gas_axes_same"] == 0
+    _both(gpu_ctx_factory, oracle, ctl, tbl, [jr.synth.example_package("limb", ctl)], "gas axes")
+
+
 def test_no_refraction_and_extinction_windows(jr, oracle, gpu_ctx_factory):
     ctl = jr.Control(["CO2", "H2O"], [792.0, 832.0], refrac=0, rayds=5.0, raydz=1.0)
     pkg = jr.synth.limb_package(ctl, n_profiles=1, rays_per_profile=10, dz=6.0, seed=11)

@@ -16,7 +16,9 @@ def test_packer_properties(jr):
     ctl = jr.synth.control_limb_example()
     tbl = jr.synth.make_tables(ctl)
     info = jr.core.tables_pack_info(tbl, ctl.ng, ctl.nd)
-    assert info["all_shared"] == 1 and info["monotone"] == 1
+    assert info["all_shared"] == 1 and info["monotone"] == 1 and info["gas_axes_same"] == 1
+    per_gas = jr.core.tables_pack_info(jr.synth.make_tables(ctl, gas_axis_shift=True), ctl.ng, ctl.nd)
+    assert per_gas["all_shared"] == 1 and per_gas["gas_axes_same"] == 0
     assert info["n_entries"] == int(tbl.nu[tbl.nu >= 2].sum())
     assert info["nbytes"] < 20e6
     # channel-dependent axes -> generic kernel
