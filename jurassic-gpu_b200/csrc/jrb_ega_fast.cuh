@@ -53,12 +53,17 @@ __device__ __forceinline__ void tma_load_1d(void *dst_smem, const void *src_gmem
 }
 
 // ---- bracket search ------------------------------------------------------------------------------------------------
-// slow path, shared by all call sites: reference bisection restricted to [ilo, ihi]
-static __device__ __noinline__ int search_range(const float4 *__restrict__ col, int ilo, int ihi, const double x, const int on_eps) {
+// Exact comparison of a double x with float table values: for any float v,  v > x  <=>  v > rd(x), where rd() rounds x
+// to float toward -infinity.  The bracket tests therefore run in single precision -- no float->double conversion per
+// tested value -- and still reproduce the reference's float-vs-double comparisons (src/jr_common.h:116-125) exactly.
+__device__ __forceinline__ float round_down(const double x) { return __double2float_rd(x); }
+
+// slow path, shared by all call sites: reference bisection restricted to [ilo, ihi]; xd = rd(x)
+static __device__ __noinline__ int search_range(const float4 *__restrict__ col, int ilo, int ihi, const float xd, const int on_eps) {
   while (ihi > ilo + 1) {
     const int i = (ihi + ilo) >> 1;
     const float v = on_eps ? col[i].y : col[i].x;
-    if ((double)v > x) ihi = i; else ilo = i;
+    if (v > xd) ihi = i; else ilo = i;
   }
   return ilo;
 }
@@ -68,31 +73,31 @@ __device__ __forceinline__ float lo_of(const float4 b) { return ON_EPS ? b.y : b
 template <bool ON_EPS>
 __device__ __forceinline__ float hi_of(const float4 b) { return ON_EPS ? b.w : b.z; }
 
-// Move (k, b) so that  val[k] <= x < val[k+1]  with k clipped to [0, nu-2]  (== reference bisection result).
+// Move (k, b) so that  val[k] <= x < val[k+1]  with k clipped to [0, nu-2]  (== reference bisection result); xd = rd(x).
 // The neighbouring bracket is tried first.  Larger upward moves of the column-density lookup (long segments near the
 // tangent point add several grid steps at once) jump by the distance estimated from the local grid ratio -- the u axes
 // of JURASSIC tables are geometric -- and whatever is still not bracketed goes to the out-of-line bisection.
 template <bool ON_EPS>
-__device__ __forceinline__ void relocate(const float4 *__restrict__ col, const int nu, const double x, int &k, float4 &b) {
-  if (x < (double)lo_of<ON_EPS>(b)) {
+__device__ __forceinline__ void relocate(const float4 *__restrict__ col, const int nu, const float xd, int &k, float4 &b) {
+  if (lo_of<ON_EPS>(b) > xd) { // x < val[k]
     if (k > 0) {
       --k; b = col[k];
-      if (k > 0 && x < (double)lo_of<ON_EPS>(b)) { k = search_range(col, 0, k, x, ON_EPS); b = col[k]; }
+      if (k > 0 && lo_of<ON_EPS>(b) > xd) { k = search_range(col, 0, k, xd, ON_EPS); b = col[k]; }
     }
-  } else if (x >= (double)hi_of<ON_EPS>(b)) {
+  } else if (hi_of<ON_EPS>(b) <= xd) { // x >= val[k+1]
     if (k < nu - 2) {
       ++k; b = col[k];
-      if (k < nu - 2 && x >= (double)hi_of<ON_EPS>(b)) {
+      if (k < nu - 2 && hi_of<ON_EPS>(b) <= xd) {
         if (!ON_EPS) {
           const float l0 = __log2f(b.x), r = __log2f(b.z) - l0;
-          const float d = (r > 0.f) ? fminf((__log2f((float)x) - l0) * __frcp_rn(r), 65535.f) : 1.f;
+          const float d = (r > 0.f) ? fminf((__log2f(xd) - l0) * __frcp_rn(r), 65535.f) : 1.f;
           const int k0 = k;
           k = min(k0 + max((int)d, 1), nu - 2);
           b = col[k];
-          if (x < (double)b.x) { k = search_range(col, k0, k, x, 0); b = col[k]; }
-          else if (k < nu - 2 && x >= (double)b.z) { k = search_range(col, k, nu - 1, x, 0); b = col[k]; }
+          if (b.x > xd) { k = search_range(col, k0, k, xd, 0); b = col[k]; }
+          else if (k < nu - 2 && b.z <= xd) { k = search_range(col, k, nu - 1, xd, 0); b = col[k]; }
         } else {
-          k = search_range(col, k, nu - 1, x, 1); b = col[k];
+          k = search_range(col, k, nu - 1, xd, 1); b = col[k];
         }
       }
     }
@@ -101,12 +106,12 @@ __device__ __forceinline__ void relocate(const float4 *__restrict__ col, const i
 
 // One table column of the EGA step, starting from the prefetched bracket (k, b):
 // u* = u(eps) (get_u, may extrapolate), then eps(u* + u_seg) clamped to [0,1] (get_eps + c01, src/jr_common.h:249-257).
-__device__ __forceinline__ double column_finish(const float4 *__restrict__ col, const int nu, const double eps, const double useg,
-                                                int &k, float4 b) {
-  relocate<true>(col, nu, eps, k, b);
+__device__ __forceinline__ double column_finish(const float4 *__restrict__ col, const int nu, const double eps, const float epsd,
+                                                const double useg, int &k, float4 b) {
+  relocate<true>(col, nu, epsd, k, b);
   const double ustar = lerp_fast((double)b.y, (double)b.x, (double)b.w, (double)b.z, eps);
   const double x = ustar + useg;
-  relocate<false>(col, nu, x, k, b);
+  relocate<false>(col, nu, round_down(x), k, b);
   return clamp01(lerp_fast((double)b.x, (double)b.y, (double)b.z, (double)b.w, x));
 }
 
@@ -120,8 +125,10 @@ __device__ __forceinline__ void load_coldesc(const TblDev &T, const int ig, cons
                                              uint2 &c00, uint2 &c01, uint2 &c10, uint2 &c11) {
   const unsigned c = (cell == kCellInvalid) ? 0u : cell; // any valid address; the result is ignored for an invalid cell
   const int ipr = c & 0xff, it0 = (c >> 8) & 0xff, it1 = (c >> 16) & 0xff;
-  const uint2 *__restrict__ q0 = T.col + (((size_t)ig * T.npmax + ipr) * T.ntmax + it0) * nd + id;
-  const uint2 *__restrict__ q1 = T.col + (((size_t)ig * T.npmax + ipr + 1) * T.ntmax + it1) * nd + id;
+  // 32-bit index arithmetic (the descriptor array has ng*npmax*ntmax*nd < 2^31 elements), one 64-bit address per level
+  const unsigned row = (unsigned)ig * (unsigned)T.npmax + (unsigned)ipr;
+  const uint2 *__restrict__ q0 = T.col + ((row * (unsigned)T.ntmax + (unsigned)it0) * (unsigned)nd + (unsigned)id);
+  const uint2 *__restrict__ q1 = T.col + (((row + 1u) * (unsigned)T.ntmax + (unsigned)it1) * (unsigned)nd + (unsigned)id);
   c00 = __ldg(q0); c01 = __ldg(q0 + nd); c10 = __ldg(q1); c11 = __ldg(q1 + nd);
 }
 
@@ -271,10 +278,11 @@ __global__ void __launch_bounds__(kEgaBlock, JRB_EGA_MINBLOCKS) ega_fast_kernel(
             const float4 b00 = p00[k00], b01 = p01[k01], b10 = p10[k10], b11 = p11[k11];
             const double *__restrict__ cw = R + L.c0 + L.cstride * ig;
             const double eps = 1 - tp, useg = R[L.u0 + ig];
-            const double e00 = fast::column_finish(p00, (int)c00.y, eps, useg, k00, b00);
-            const double e01 = fast::column_finish(p01, (int)c01.y, eps, useg, k01, b01);
-            const double e10 = fast::column_finish(p10, (int)c10.y, eps, useg, k10, b10);
-            const double e11 = fast::column_finish(p11, (int)c11.y, eps, useg, k11, b11);
+            const float epsd = fast::round_down(eps);
+            const double e00 = fast::column_finish(p00, (int)c00.y, eps, epsd, useg, k00, b00);
+            const double e01 = fast::column_finish(p01, (int)c01.y, eps, epsd, useg, k01, b01);
+            const double e10 = fast::column_finish(p10, (int)c10.y, eps, epsd, useg, k10, b10);
+            const double e11 = fast::column_finish(p11, (int)c11.y, eps, epsd, useg, k11, b11);
             hint_s[ig * sstride] = (unsigned long long)k00 | ((unsigned long long)k01 << 10) | ((unsigned long long)k10 << 20) |
                                    ((unsigned long long)k11 << 30) | ((unsigned long long)cell << 40);
             const double ep0 = clamp01(fma(cw[1], e01 - e00, e00));
