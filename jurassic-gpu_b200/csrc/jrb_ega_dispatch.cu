@@ -14,7 +14,7 @@ JRB_DECL(8) JRB_DECL(9) JRB_DECL(10) JRB_DECL(11) JRB_DECL(12) JRB_DECL(13) JRB_
 #undef JRB_DECL
 
 bool ega_fast_available(int ng, int ctm_mask) {
-  return ng >= 1 && ng <= 32 && ctm_mask >= 0 && ctm_mask < 16 && ((JRB_MASK_LIST >> ctm_mask) & 1);
+  return ng >= 0 && ng <= 32 && ctm_mask >= 0 && ctm_mask < 16 && ((JRB_MASK_LIST >> ctm_mask) & 1);
 }
 
 template <int M>

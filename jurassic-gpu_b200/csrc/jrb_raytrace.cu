@@ -297,7 +297,7 @@ __global__ void __launch_bounds__(256) los_finalize_kernel(TraceArgs a) {
   rec[3] = qh2o;
   if (L.fast) {
     const TblDev &T = a.tbl;
-    const int ncell = L.cstride ? L.ng : 1; // one cell per gas, or one for all gases when they share the (p,T) grid
+    const int ncell = L.ng == 0 ? 0 : (L.cstride ? L.ng : 1); // one cell per gas, or one for all gases sharing the (p,T) grid
     for (int ic = 0; ic < ncell; ic++) {
       int ig = ic;
       if (!L.cstride) { ig = 0; while (ig < L.ng - 1 && T.gnp[ig] < 2) ++ig; } // first gas that has a table

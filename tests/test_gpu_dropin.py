@@ -131,3 +131,34 @@ def test_dropin_uses_reference_get_tbl_when_linked(jr, refdrv, oracle, tmp_path)
     ref.read_obs(o0, r)
     assert_parity(mine, r, "dropin vs reference formod()")
     lib.jr_b200_finalize()
+
+
+def test_concurrent_formod_gpu_callers_are_serialised(jr, refdrv, oracle):
+    """several host threads calling formod_GPU at once (the reference supports this with lanes + omp critical,
+    src/GPUdrivers.cu:275-335; here a mutex serialises them) all get correct results"""
+    import threading
+    ND, NG = 2, 5
+    ctl = jr.synth.control_limb_example()
+    tbl = jr.synth.make_tables(ctl)
+    pkgs = [jr.synth.limb_package(ctl, n_profiles=1, rays_per_profile=12, dz=5.0, seed=70 + i) for i in range(6)]
+    io = StructIO(jr, refdrv, ND, NG)
+    lib = _load_dropin(jr, ND, NG)
+    c = io.r.make_ctl(ctl, useGPU=1)
+    t, keep = _tbl_struct(io, tbl)
+    assert lib.jr_b200_init(C.addressof(c), C.addressof(t), 0) == 0
+    atms = [io.r.make_atm(p) for p in pkgs]
+    obss = [io.r.make_obs(p) for p in pkgs]
+
+    def work(i):
+        for _ in range(3):
+            lib.formod_GPU(C.addressof(c), C.addressof(atms[i]), C.addressof(obss[i]))
+
+    th = [threading.Thread(target=work, args=(i,)) for i in range(len(pkgs))]
+    [x.start() for x in th]
+    [x.join() for x in th]
+    refs = run_oracle(oracle, ctl, tbl, pkgs)
+    for i, p in enumerate(pkgs):
+        mine = copy.deepcopy(p)
+        io.r.read_obs(obss[i], mine)
+        assert_parity(mine, refs[i], f"thread {i}")
+    lib.jr_b200_finalize()

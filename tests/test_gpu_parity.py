@@ -254,3 +254,25 @@ def test_large_batch_properties(jr, oracle, gpu_ctx_factory):
     for name in ("rad", "tau", "tpz", "tplon", "tplat"):
         getattr(got, name)[...] = getattr(out[7], name)[idx]
     assert_parity(got, small, "large batch sample")
+
+
+def test_edge_shapes_no_gases_odd_channel_count_empty_packages(jr, oracle, gpu_ctx_factory):
+    """ng = 0 (continua + extinction only), nd = 33 (two channel groups, the second almost empty), a package with
+    nr = 0 in the middle of a batch, and an empty batch"""
+    ctl = jr.Control([], 2140.0 + 3.0 * np.arange(33))  # N2 continuum only
+    assert ctl.ng == 0 and ctl.ctm_mask == 2
+    tbl = jr.synth.make_tables(ctl)
+    a = jr.synth.limb_package(ctl, n_profiles=1, rays_per_profile=5, dz=10.0, seed=1)
+    a.k[0, :] = 2e-4 * np.exp(-a.z / 8.0)
+    empty = jr.Package(0, 1, 33, a.n_atm, 0)
+    for name in ("atm_time", "z", "lon", "lat", "p", "t", "k"):
+        getattr(empty, name)[...] = getattr(a, name)
+    b = jr.synth.limb_package(ctl, n_profiles=1, rays_per_profile=3, dz=20.0, seed=2)
+    ref = run_oracle(oracle, ctl, tbl, [a, b])
+    ctx = gpu_ctx_factory()
+    for variant in (0, 1):
+        out = run_cuda(ctx, ctl, tbl, [a, empty, b], variant)
+        assert_parity(out[0], ref[0], f"ng0 a v{variant}")
+        assert_parity(out[2], ref[1], f"ng0 b v{variant}")
+    ctx.formod_batch([])  # empty batch is a no-op
+    assert ctx.stats()["n_rays"] == 0
