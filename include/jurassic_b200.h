@@ -60,6 +60,8 @@ typedef struct {
   double *time, *z, *lon, *lat, *p, *t; /* [np]; p is written when hydz >= 0 */
   double *q; long q_stride;             /* q[ig*q_stride + ip], ig < ng */
   double *k; long k_stride;             /* k[iw*k_stride + ip], iw < nw */
+  double **q_rows;                      /* optional: if non-NULL, profile of gas ig is q_rows[ig][ip] (q/q_stride ignored); */
+  double **k_rows;                      /* lets many atmospheres share all profiles but one (batched Jacobians)          */
 } jrb_atm_view;
 
 typedef struct {

@@ -9,6 +9,8 @@
  *   jr_b200_init           replaces  the first-call block    src/GPUdrivers.cu:275-329 (+ get_tbl_on_GPU :78-93)
  *   jr_b200_formod_batch   new: many (atm_t, obs_t) packages per call -- a single obs_t holds at most NR = 1088 rays
  *                          (src/jurassic.h:151), far too few to occupy a B200
+ *   jr_b200_kernel         replaces  kernel()                src/jurassic.c:812-857 (finite-difference Jacobian; the caller of
+ *                          formod in retrievals): all perturbed forward models of a Jacobian are one device batch
  *   jr_b200_finalize       new: releases what the reference never frees (src/GPUdrivers.cu:309)
  *
  * Error behaviour mirrors the reference: fatal conditions print a message and exit(EXIT_FAILURE) (ERRMSG,
@@ -18,6 +20,7 @@
  */
 #ifndef JURASSIC_B200_DROPIN_H
 #define JURASSIC_B200_DROPIN_H
+#include <stddef.h>
 #ifdef __cplusplus
 extern "C" {
 #endif
@@ -32,6 +35,13 @@ int jr_b200_init(ctl_t const *ctl, tbl_t const *tbl, int device);
 
 /* formod_GPU semantics for each of npackages (atm[i], obs[i]) pairs, one device batch. */
 void jr_b200_formod_batch(ctl_t const *ctl, atm_t *const atm[], obs_t *const obs[], int npackages);
+
+/* Finite-difference Jacobian, what the reference's kernel() computes (src/jurassic.c:812-857) with the 1+n forward models
+ * run as device batches.  k is row-major m x n (gsl_matrix data with tda = n): m = finite radiances of obs (obs2y order),
+ * n = retrieved state elements (atm2x order, ranges ctl->ret*_zmin/zmax).  obs holds the undisturbed result on return. */
+void jr_b200_kernel(ctl_t const *ctl, atm_t *atm, obs_t *obs, double *k, size_t m, size_t n);
+/* n (return value) and m for the above */
+size_t jr_b200_kernel_dims(ctl_t const *ctl, atm_t *atm, obs_t const *obs, size_t *m_out);
 
 void jr_b200_finalize(void);
 

@@ -65,7 +65,8 @@ class CtlView(C.Structure):
 class AtmView(C.Structure):
     _fields_ = [("np", C.c_int), ("time", c_double_p), ("z", c_double_p), ("lon", c_double_p), ("lat", c_double_p),
                 ("p", c_double_p), ("t", c_double_p), ("q", c_double_p), ("q_stride", C.c_long),
-                ("k", c_double_p), ("k_stride", C.c_long)]
+                ("k", c_double_p), ("k_stride", C.c_long), ("q_rows", C.POINTER(c_double_p)),
+                ("k_rows", C.POINTER(c_double_p))]
 
 
 class ObsView(C.Structure):

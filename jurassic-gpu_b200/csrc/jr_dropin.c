@@ -10,6 +10,7 @@
 #include <jurassic_b200_dropin.h>
 
 #include <dlfcn.h>
+#include <math.h>
 #include <pthread.h>
 #include <stdio.h>
 #include <stdlib.h>
@@ -68,6 +69,7 @@ static void fill_atm_view(atm_t *a, jrb_atm_view *v) {
   v->time = a->time; v->z = a->z; v->lon = a->lon; v->lat = a->lat; v->p = a->p; v->t = a->t;
   v->q = &a->q[0][0]; v->q_stride = NP;
   v->k = &a->k[0][0]; v->k_stride = NP;
+  v->q_rows = NULL; v->k_rows = NULL;
 }
 
 static void fill_obs_view(obs_t *o, jrb_obs_view *v) {
@@ -109,7 +111,9 @@ int jr_b200_init(ctl_t const *ctl, tbl_t const *tbl, int device) {
   return 0;
 }
 
-void jr_b200_formod_batch(ctl_t const *ctl, atm_t *const atm[], obs_t *const obs[], int npackages) {
+/* internal entry: exported names are reached through these statics so that a formod_GPU/… symbol of another library
+ * in the global scope (e.g. the CPU-only stub of the reference, src/CPUdrivers.c:156-176) can never interpose them */
+static void formod_batch_impl(ctl_t const *ctl, atm_t *const atm[], obs_t *const obs[], int npackages) {
   if (ctl->checkmode) { printf("# %s: no operation in checkmode\n", __func__); return; }
   if (npackages <= 0) return;
   pthread_mutex_lock(&g_lock); /* concurrent callers (OpenMP host threads of a retrieval) are serialised */
@@ -129,10 +133,120 @@ void jr_b200_formod_batch(ctl_t const *ctl, atm_t *const atm[], obs_t *const obs
   pthread_mutex_unlock(&g_lock);
 }
 
-void formod_GPU(ctl_t const *ctl, atm_t *atm, obs_t *obs) {
+void jr_b200_formod_batch(ctl_t const *ctl, atm_t *const atm[], obs_t *const obs[], int npackages) {
+  formod_batch_impl(ctl, atm, obs, npackages);
+}
+
+static void formod_one_impl(ctl_t const *ctl, atm_t *atm, obs_t *obs) {
   atm_t *const a[1] = {atm};
   obs_t *const o[1] = {obs};
-  jr_b200_formod_batch(ctl, a, o, 1);
+  formod_batch_impl(ctl, a, o, 1);
+}
+
+void formod_GPU(ctl_t const *ctl, atm_t *atm, obs_t *obs) { formod_one_impl(ctl, atm, obs); }
+
+/* ---- batched finite-difference Jacobian ---------------------------------------------------------
+ * What the reference's kernel() computes (src/jurassic.c:812-857): one forward model for the undisturbed atmosphere, one per
+ * state-vector element with that element perturbed, K[i][j] = (y_j[i] - y_0[i]) / h_j.  The reference issues the 1+n
+ * forward models one after the other; here the n perturbed ones are device batches: every perturbed atmosphere is a view
+ * that shares all profiles with the caller's atm_t except the single perturbed one (row-pointer form of jrb_atm_view). */
+typedef struct { double *value; int iq; int ip; } jr_state_elem;
+
+/* atm2x / atm2x_help (src/jurassic.c:1491-1513): state vector = retrieved p, T, q[ig], k[iw] inside their altitude ranges */
+static size_t state_vector(ctl_t const *ctl, atm_t *atm, jr_state_elem *e) {
+  size_t n = 0;
+#define JR_ADD(zmin, zmax, arr, code)                                                    \
+  for (int ip = 0; ip < atm->np; ip++)                                                   \
+    if (atm->z[ip] >= (zmin) && atm->z[ip] <= (zmax)) {                                  \
+      if (e) { e[n].value = (arr); e[n].iq = (code); e[n].ip = ip; }                     \
+      n++;                                                                               \
+    }
+  JR_ADD(ctl->retp_zmin, ctl->retp_zmax, atm->p, 0)
+  JR_ADD(ctl->rett_zmin, ctl->rett_zmax, atm->t, 1)
+  for (int ig = 0; ig < ctl->ng; ig++) JR_ADD(ctl->retq_zmin[ig], ctl->retq_zmax[ig], atm->q[ig], 2 + ig)
+  for (int iw = 0; iw < ctl->nw; iw++) JR_ADD(ctl->retk_zmin[iw], ctl->retk_zmax[iw], atm->k[iw], 2 + ctl->ng + iw)
+#undef JR_ADD
+  return n;
+}
+
+/* obs2y (src/jurassic.c:1528-1541): the measurement vector holds the finite radiances, ray-major */
+static size_t measurement_count(ctl_t const *ctl, obs_t const *obs) {
+  size_t m = 0;
+  for (int ir = 0; ir < obs->nr; ir++)
+    for (int id = 0; id < ctl->nd; id++) m += isfinite(obs->rad[ir][id]) ? 1 : 0;
+  return m;
+}
+
+size_t jr_b200_kernel_dims(ctl_t const *ctl, atm_t *atm, obs_t const *obs, size_t *m_out) {
+  if (m_out) *m_out = measurement_count(ctl, obs);
+  return state_vector(ctl, atm, NULL);
+}
+
+void jr_b200_kernel(ctl_t const *ctl, atm_t *atm, obs_t *obs, double *k, size_t m, size_t n) {
+  if (ctl->checkmode) { printf("# %s: no operation in checkmode\n", __func__); return; }
+  jr_state_elem *el = (jr_state_elem *)malloc(sizeof(jr_state_elem) * (n ? n : 1));
+  if (!el) JR_FATAL("Out of memory!");
+  if (state_vector(ctl, atm, el) != n) JR_FATAL("jr_b200_kernel: n does not match the state vector of ctl/atm");
+  int const nr = obs->nr, nd = ctl->nd, np = atm->np, nrow = ctl->ng + ctl->nw;
+  int const private_p = ctl->hydz >= 0; /* the hydrostatic adjustment rewrites p of every perturbed atmosphere */
+
+  /* undisturbed run: fills the caller's obs; its NaN mask is what the perturbed runs inherit (copy_obs, :168-195) */
+  formod_one_impl(ctl, atm, obs);
+  if (measurement_count(ctl, obs) != m) JR_FATAL("jr_b200_kernel: m does not match the number of finite radiances");
+  memset(k, 0, sizeof(double) * m * n);
+
+  size_t const chunk = 256; /* perturbed atmospheres per device batch */
+  size_t const nb_max = n < chunk ? (n ? n : 1) : chunk;
+  double *hs = (double *)malloc(sizeof(double) * nb_max);
+  double *prof = (double *)malloc(sizeof(double) * nb_max * (size_t)np * 2);
+  double **rows = (double **)malloc(sizeof(double *) * nb_max * (size_t)(nrow ? nrow : 1));
+  double *out = (double *)malloc(sizeof(double) * nb_max * (size_t)nr * nd * 2);
+  double *tp = (double *)malloc(sizeof(double) * nb_max * (size_t)nr * 3);
+  jrb_atm_view *av = (jrb_atm_view *)malloc(sizeof(jrb_atm_view) * nb_max);
+  jrb_obs_view *ov = (jrb_obs_view *)malloc(sizeof(jrb_obs_view) * nb_max);
+  if (!hs || !prof || !rows || !out || !tp || !av || !ov) JR_FATAL("Out of memory!");
+
+  for (size_t j0 = 0; j0 < n; j0 += chunk) {
+    size_t const nb = (n - j0 < chunk) ? n - j0 : chunk;
+    for (size_t b = 0; b < nb; b++) {
+      jr_state_elem const *e = &el[j0 + b];
+      double const x0 = e->value[e->ip];
+      double h; /* perturbation sizes of the reference (src/jurassic.c:832-836) */
+      if (e->iq == 0) h = fmax(fabs(0.01 * x0), 1e-7);
+      else if (e->iq == 1) h = 1;
+      else if (e->iq < 2 + ctl->ng) h = fmax(fabs(0.01 * x0), 1e-15);
+      else h = 1e-4;
+      hs[b] = h;
+      double *mine = prof + b * (size_t)np * 2;
+      memcpy(mine, e->value, sizeof(double) * (size_t)np);
+      mine[e->ip] = x0 + h;
+      fill_atm_view(atm, &av[b]);
+      double **r = rows + b * (size_t)(nrow ? nrow : 1);
+      for (int ig = 0; ig < ctl->ng; ig++) r[ig] = atm->q[ig];
+      for (int iw = 0; iw < ctl->nw; iw++) r[ctl->ng + iw] = atm->k[iw];
+      av[b].q_rows = r; av[b].k_rows = r + ctl->ng;
+      if (e->iq == 0) av[b].p = mine;
+      else if (e->iq == 1) av[b].t = mine;
+      else r[e->iq - 2] = mine;
+      if (private_p && e->iq != 0) { memcpy(mine + np, atm->p, sizeof(double) * (size_t)np); av[b].p = mine + np; }
+      fill_obs_view(obs, &ov[b]);
+      ov[b].rad = out + b * (size_t)nr * nd * 2; ov[b].tau = ov[b].rad + (size_t)nr * nd;
+      ov[b].row_stride = nd; ov[b].nd_reset = nd;
+      ov[b].tpz = tp + b * (size_t)nr * 3; ov[b].tplon = ov[b].tpz + nr; ov[b].tplat = ov[b].tplon + nr;
+      for (int ir = 0; ir < nr; ir++) memcpy(ov[b].rad + (size_t)ir * nd, obs->rad[ir], sizeof(double) * (size_t)nd); /* NaN mask */
+    }
+    pthread_mutex_lock(&g_lock);
+    push_control(ctl);
+    if (jrb_formod_batch(g_ctx, (int)nb, av, ov) != JRB_OK) JR_FATAL(jrb_last_error(g_ctx));
+    pthread_mutex_unlock(&g_lock);
+    for (size_t b = 0; b < nb; b++) { /* K[:, j] = (y1 - y0) / h over the finite radiances (obs2y order) */
+      size_t i = 0;
+      for (int ir = 0; ir < nr; ir++)
+        for (int id = 0; id < nd; id++)
+          if (isfinite(obs->rad[ir][id])) { k[i * n + (j0 + b)] = (ov[b].rad[(size_t)ir * nd + id] - obs->rad[ir][id]) / hs[b]; i++; }
+    }
+  }
+  free(hs); free(prof); free(rows); free(out); free(tp); free(av); free(ov); free(el);
 }
 
 void jr_b200_finalize(void) {

@@ -326,7 +326,7 @@ static void hydrostatic_host(const jrb_atm_view &a, double hydz, int ig_h2o) {
     return 9.780318 * (1. + 0.0053024 * x * x - 5.8e-6 * y * y) - 3.086e-3 * z;
   };
   auto lin = [](double x0, double y0, double x1, double y1, double x) { return y0 + (x - x0) * (y1 - y0) / (x1 - x0); };
-  const double *qh = (ig_h2o >= 0) ? a.q + (size_t)ig_h2o * a.q_stride : nullptr;
+  const double *qh = (ig_h2o >= 0) ? (a.q_rows ? a.q_rows[ig_h2o] : a.q + (size_t)ig_h2o * a.q_stride) : nullptr;
   double e = 0.;
   for (int dir = 0; dir < 2; dir++) {
     const int step = dir == 0 ? 1 : -1;
@@ -402,8 +402,10 @@ int jrb_stage(jrb_context *ctx, int npk, const jrb_atm_view *atm, const jrb_obs_
     std::memcpy(hatm + 3 * A + a0, a.lat, npb);
     std::memcpy(hatm + 4 * A + a0, a.p, npb);
     std::memcpy(hatm + 5 * A + a0, a.t, npb);
-    for (int ig = 0; ig < ng; ig++) std::memcpy(hatm + (size_t)(6 + ig) * A + a0, a.q + (size_t)ig * a.q_stride, npb);
-    for (int iw = 0; iw < nw; iw++) std::memcpy(hatm + (size_t)(6 + ng + iw) * A + a0, a.k + (size_t)iw * a.k_stride, npb);
+    for (int ig = 0; ig < ng; ig++)
+      std::memcpy(hatm + (size_t)(6 + ig) * A + a0, a.q_rows ? a.q_rows[ig] : a.q + (size_t)ig * a.q_stride, npb);
+    for (int iw = 0; iw < nw; iw++)
+      std::memcpy(hatm + (size_t)(6 + ng + iw) * A + a0, a.k_rows ? a.k_rows[iw] : a.k + (size_t)iw * a.k_stride, npb);
     hpoff[k] = a0; hpnp[k] = a.np;
     for (int ir = 0; ir < o.nr; ir++) {
       hrpk[r0 + ir] = k;

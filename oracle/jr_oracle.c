@@ -212,11 +212,11 @@ static void o_intpol_pt(const jrb_atm_view *a, int idx0, int n, double z0, doubl
 static void o_intpol_qk(const jrb_ctl_view *c, const jrb_atm_view *a, int idx0, int n, double z0, double *q, double *k) { /* :557-567 */
   const int ip = idx0 + o_locate(a->z + idx0, n, z0);
   for (int ig = 0; ig < c->ng; ig++) {
-    const double *qq = a->q + (size_t)ig * a->q_stride;
+    const double *qq = a->q_rows ? a->q_rows[ig] : a->q + (size_t)ig * a->q_stride;
     q[ig] = o_lip(a->z[ip], qq[ip], a->z[ip + 1], qq[ip + 1], z0);
   }
   for (int iw = 0; iw < c->nw; iw++) {
-    const double *kk = a->k + (size_t)iw * a->k_stride;
+    const double *kk = a->k_rows ? a->k_rows[iw] : a->k + (size_t)iw * a->k_stride;
     k[iw] = o_lip(a->z[ip], kk[ip], a->z[ip + 1], kk[ip + 1], z0);
   }
 }
@@ -349,7 +349,7 @@ static void o_hydrostatic(const jrb_ctl_view *c, const jrb_atm_view *a, int ig_h
   double dzmin = 1e99; int ipref = 0;
   for (int ip = ip0; ip < ip1; ip++) { const double dz = fabs(a->z[ip] - c->hydz); if (dz < dzmin) { dzmin = dz; ipref = ip; } }
   const double lat = a->lat[ipref], mmair = 28.96456e-3, mmh2o = 18.0153e-3;
-  const double *qh = ig_h2o >= 0 ? a->q + (size_t)ig_h2o * a->q_stride : NULL;
+  const double *qh = ig_h2o >= 0 ? (a->q_rows ? a->q_rows[ig_h2o] : a->q + (size_t)ig_h2o * a->q_stride) : NULL;
   double e = 0.;
   for (int ip = ipref + 1; ip < ip1; ip++) {
     double mean = 0.;

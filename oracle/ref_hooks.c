@@ -112,5 +112,17 @@ void jrref_formod_tbl(ctl_t const *ctl, atm_t *atm, obs_t *obs, tbl_t const *tbl
 /* unmodified entry point, tables from files via get_tbl() */
 void jrref_formod(ctl_t const *ctl, atm_t *atm, obs_t *obs) { formod(ctl, atm, obs); }
 
+/* the reference's finite-difference Jacobian kernel() (src/jurassic.c:812-857), tables via get_tbl(); k is m x n row-major */
+size_t jrref_kernel_dims(ctl_t const *ctl, atm_t const *atm, obs_t const *obs, size_t *m) {
+  *m = obs2y(ctl, obs, NULL, NULL, NULL);
+  return atm2x(ctl, atm, NULL, NULL, NULL);
+}
+void jrref_kernel(ctl_t const *ctl, atm_t *atm, obs_t *obs, double *k, size_t m, size_t n) {
+  gsl_matrix *K = gsl_matrix_alloc(m, n);
+  kernel(ctl, atm, obs, K);
+  for (size_t i = 0; i < m; i++) for (size_t j = 0; j < n; j++) k[i * n + j] = gsl_matrix_get(K, i, j);
+  gsl_matrix_free(K);
+}
+
 int jrref_max_threads(void) { return omp_get_max_threads(); }
 void jrref_set_threads(int n) { omp_set_num_threads(n); }

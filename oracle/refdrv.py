@@ -88,6 +88,9 @@ class Reference:
         lib.jrref_layout.argtypes = [C.POINTER(C.c_char_p), C.POINTER(C.c_longlong), C.c_int]
         lib.jrref_layout.restype = C.c_int
         lib.jrref_dims.argtypes = [C.POINTER(C.c_int)]
+        lib.jrref_kernel_dims.argtypes = [vp, vp, vp, C.POINTER(C.c_size_t)]
+        lib.jrref_kernel_dims.restype = C.c_size_t
+        lib.jrref_kernel.argtypes = [vp, vp, vp, abi.c_double_p, C.c_size_t, C.c_size_t]
         self.lib = lib
 
     # ---- ABI facts ----
@@ -191,6 +194,14 @@ class Reference:
         ts = C.c_double()
         n = self.lib.jrref_traceray(C.addressof(c), C.addressof(a), C.addressof(o), ir, _dp(buf), C.byref(ts))
         return buf[: n * stride].reshape(n, stride).copy(), ts.value
+
+    def kernel(self, c, a, o):
+        """the reference's finite-difference Jacobian kernel() (tables via get_tbl, i.e. from ctl.tblbase files)"""
+        m = C.c_size_t()
+        n = self.lib.jrref_kernel_dims(C.addressof(c), C.addressof(a), C.addressof(o), C.byref(m))
+        k = np.zeros((m.value, n))
+        self.lib.jrref_kernel(C.addressof(c), C.addressof(a), C.addressof(o), _dp(k), m.value, n)
+        return k
 
     def threads(self):
         return self.lib.jrref_max_threads()

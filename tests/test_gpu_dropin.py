@@ -162,3 +162,46 @@ def test_concurrent_formod_gpu_callers_are_serialised(jr, refdrv, oracle):
         io.r.read_obs(obss[i], mine)
         assert_parity(mine, refs[i], f"thread {i}")
     lib.jr_b200_finalize()
+
+
+def test_batched_jacobian_matches_reference_kernel(jr, refdrv, tmp_path):
+    """Row f1: jr_b200_kernel (all perturbed forward models as device batches) == the reference's kernel()
+    (src/jurassic.c:812-857, one formod() per state element on the CPU)"""
+    if not refdrv.reference_available(2, 5):
+        pytest.skip("oracle/_ref not built")
+    ctl = jr.synth.control_limb_example()
+    tbl = jr.synth.make_tables(ctl)
+    ctl.tblbase = jr.synth.write_ascii_tables(ctl, tbl, str(tmp_path), "boxcar")
+    pkg = jr.synth.example_package("limb", ctl)
+    ref = refdrv.Reference(2, 5, rtld_global=True)
+
+    def structs(useGPU):
+        c, a, o = ref.make_ctl(ctl, useGPU=useGPU), ref.make_atm(pkg), ref.make_obs(pkg)
+        c.retp_zmin, c.retp_zmax, c.rett_zmin, c.rett_zmax = 6.0, 9.0, 10.0, 20.0  # 4 pressures, 11 temperatures
+        for ig in range(5):
+            c.retq_zmin[ig], c.retq_zmax[ig] = -999.0, -999.0
+        c.retq_zmin[2], c.retq_zmax[2] = 15.0, 24.0                                 # 10 ozone values
+        c.retq_zmin[1], c.retq_zmax[1] = 3.0, 5.0                                   # 3 water vapour values
+        c.retk_zmin[0], c.retk_zmax[0] = 12.0, 13.0                                 # 2 extinction values
+        np.ctypeslib.as_array(o.rad)[5, 1] = np.nan                                 # one masked measurement
+        return c, a, o
+
+    c, a, o = structs(0)
+    k_ref = ref.kernel(c, a, o)
+    assert k_ref.shape == (66 * 2 - 1, 4 + 11 + 10 + 3 + 2)
+
+    lib = _load_dropin(jr, 2, 5)
+    lib.jr_b200_kernel_dims.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.POINTER(C.c_size_t)]
+    lib.jr_b200_kernel_dims.restype = C.c_size_t
+    lib.jr_b200_kernel.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, jr.abi.c_double_p, C.c_size_t, C.c_size_t]
+    c, a, o = structs(1)
+    m = C.c_size_t()
+    n = lib.jr_b200_kernel_dims(C.addressof(c), C.addressof(a), C.addressof(o), C.byref(m))
+    assert (m.value, n) == k_ref.shape
+    k = np.zeros((m.value, n))
+    lib.jr_b200_kernel(C.addressof(c), C.addressof(a), C.addressof(o), k.ctypes.data_as(jr.abi.c_double_p), m.value, n)
+    # finite differences amplify the 1e-11 forward-model differences by |y|/|dy| ~ 1e2..1e4
+    scale = np.max(np.abs(k_ref), axis=0, keepdims=True)
+    assert np.all(np.abs(k - k_ref) <= 1e-5 * np.abs(k_ref) + 1e-7 * scale), float(np.max(np.abs(k - k_ref) / (scale + 1e-300)))
+    assert np.count_nonzero(k_ref) > 300  # the Jacobian is sparse: a ray only sees levels above its tangent point
+    lib.jr_b200_finalize()
