@@ -121,6 +121,16 @@ int jrb_tables_blob(jrb_context *ctx, void **dev_ptr, size_t *nbytes);
 int jrb_tables_alloc_blob(jrb_context *ctx, size_t nbytes, void **dev_ptr); /* receiver side */
 int jrb_tables_adopt_blob(jrb_context *ctx);                                 /* after the blob has been filled */
 
+/* Native ingest of the reference's ASCII inputs "<tblbase>_<nu %.4f>_<GAS>.tab" / "<tblbase>_<nu %.4f>.filt" with the
+ * acceptance rules of init_tbl (src/jurassic.c:311-416, 612-667), into compact host arrays (no 8.8 GB tbl_t).  Host only.
+ * max_p/max_t/max_u <= 0 select the reference's TBLNP/TBLNT/TBLNU (40/30/304).  Missing .tab files are tolerated. */
+typedef struct jrb_host_tables jrb_host_tables;
+int jrb_tables_read_ascii(const char *tblbase, int ng, const char *const *emitters, int nd, const double *nu, int max_p,
+                          int max_t, int max_u, jrb_host_tables **out);
+int jrb_host_tables_view(const jrb_host_tables *t, jrb_tbl_view *view, int *n_missing);
+void jrb_host_tables_free(jrb_host_tables *t);
+const char *jrb_ingest_last_error(void);
+
 /* select kernel: -1 auto, 0 force generic, 1 force fast (fails if tables do not allow it) */
 int jrb_set_kernel_variant(jrb_context *ctx, int variant);
 

@@ -33,6 +33,10 @@ void formod_GPU(ctl_t const *ctl, atm_t *atm, obs_t *obs);
  * device < 0 selects ctl->MPIlocalrank like the reference (src/GPUdrivers.cu:288). Returns 0 or exits. */
 int jr_b200_init(ctl_t const *ctl, tbl_t const *tbl, int device);
 
+/* The same with tables read natively from "<ctl->tblbase>_<nu>_<GAS>.tab" / ".filt" (parsing rules of init_tbl,
+ * src/jurassic.c:311-416, 612-667) -- no tbl_t is ever allocated on the host. */
+int jr_b200_init_from_files(ctl_t const *ctl, int device);
+
 /* formod_GPU semantics for each of npackages (atm[i], obs[i]) pairs, one device batch. */
 void jr_b200_formod_batch(ctl_t const *ctl, atm_t *const atm[], obs_t *const obs[], int npackages);
 

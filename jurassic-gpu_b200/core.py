@@ -47,6 +47,14 @@ def load_core():
     lib.jrb_tables_pack_host.restype = C.c_int
     lib.jrb_tables_upload_blob.argtypes = [vp, C.c_void_p, C.c_size_t]
     lib.jrb_tables_upload_blob.restype = C.c_int
+    lib.jrb_tables_read_ascii.argtypes = [C.c_char_p, C.c_int, C.POINTER(C.c_char_p), C.c_int, abi.c_double_p, C.c_int, C.c_int,
+                                          C.c_int, C.POINTER(vp)]
+    lib.jrb_tables_read_ascii.restype = C.c_int
+    lib.jrb_host_tables_view.argtypes = [vp, C.POINTER(abi.TblView), abi.c_int_p]
+    lib.jrb_host_tables_view.restype = C.c_int
+    lib.jrb_host_tables_free.argtypes = [vp]
+    lib.jrb_host_tables_free.restype = None
+    lib.jrb_ingest_last_error.restype = C.c_char_p
     lib.jrb_tables_blob.argtypes = [vp, C.POINTER(vp), C.POINTER(C.c_size_t)]
     lib.jrb_tables_alloc_blob.argtypes = [vp, C.c_size_t, C.POINTER(vp)]
     lib.jrb_tables_adopt_blob.argtypes = [vp]
@@ -66,7 +74,8 @@ def load_core():
     return lib
 
 
-EXPORTED_SYMBOLS = ["jrb_tables_pack_host", "jrb_tables_upload_blob", "jrb_tables_pack_info", "jrb_version", "jrb_device_count", "jrb_create", "jrb_destroy", "jrb_last_error",
+EXPORTED_SYMBOLS = ["jrb_tables_read_ascii", "jrb_host_tables_view", "jrb_host_tables_free", "jrb_ingest_last_error",
+                    "jrb_tables_pack_host", "jrb_tables_upload_blob", "jrb_tables_pack_info", "jrb_version", "jrb_device_count", "jrb_create", "jrb_destroy", "jrb_last_error",
                     "jrb_set_control", "jrb_set_tables", "jrb_tables_blob", "jrb_tables_alloc_blob",
                     "jrb_tables_adopt_blob", "jrb_set_kernel_variant", "jrb_formod_batch", "jrb_stage",
                     "jrb_run_staged", "jrb_fetch_staged", "jrb_staged_results", "jrb_debug_los", "jrb_get_stats"]
@@ -86,6 +95,26 @@ def tables_pack_info(tbl, ng, nd):
         raise JrbError(f"jrb_tables_pack_info failed ({rc}): {lib.jrb_last_error(None).decode()}")
     return {"nbytes": n.value, "all_shared": sh.value, "monotone": mo.value, "n_entries": ne.value,
             "gas_axes_same": gs.value}
+
+
+def read_ascii_tables(ctl, tblbase):
+    """Native ingest of the reference's ASCII .tab/.filt files -> Tables container (host only, no GPU needed)."""
+    lib = load_core()
+    names = (C.c_char_p * max(ctl.ng, 1))(*[e.encode() for e in ctl.emitters])
+    h = C.c_void_p()
+    rc = lib.jrb_tables_read_ascii(tblbase.encode(), ctl.ng, names, ctl.nd, _dp(ctl.nu), 0, 0, 0, C.byref(h))
+    if rc != 0:
+        raise JrbError(f"jrb_tables_read_ascii failed ({rc}): {lib.jrb_ingest_last_error().decode()}")
+    v, miss = abi.TblView(), C.c_int()
+    lib.jrb_host_tables_view(h, C.byref(v), C.byref(miss))
+    t = Tables(v.dim_g, v.dim_d, v.dim_p, v.dim_t, v.dim_u)
+    for name in ("np", "nt", "nu", "p", "t", "u", "eps", "sr", "st"):
+        dst = getattr(t, name)
+        src = np.ctypeslib.as_array(getattr(v, name), shape=dst.shape)
+        dst[...] = src
+    lib.jrb_host_tables_free(h)
+    t.n_missing = miss.value
+    return t
 
 
 def tables_pack_host(tbl, ng, nd):

@@ -103,6 +103,32 @@ static void init_locked(ctl_t const *ctl, tbl_t const *tbl, int device) {
   g_have_tables = 1;
 }
 
+/* tables straight from the ASCII .tab/.filt files below ctl->tblbase, without the reference's init_tbl / 8.8 GB tbl_t */
+int jr_b200_init_from_files(ctl_t const *ctl, int device) {
+  if (!ctl) JR_FATAL("jr_b200_init_from_files: NULL argument");
+  char const *names[NG > 0 ? NG : 1];
+  for (int ig = 0; ig < ctl->ng; ig++) names[ig] = ctl->emitter[ig];
+  jrb_host_tables *ht = NULL;
+  if (jrb_tables_read_ascii(ctl->tblbase, ctl->ng, names, ctl->nd, ctl->nu, TBLNP, TBLNT, TBLNU, &ht) != JRB_OK)
+    JR_FATAL(jrb_ingest_last_error());
+  jrb_tbl_view tv;
+  int missing = 0;
+  jrb_host_tables_view(ht, &tv, &missing);
+  if (missing > 0) printf("Warning! %d files were not found!\n", missing); /* like init_tbl (src/jurassic.c:424-427) */
+  pthread_mutex_lock(&g_lock);
+  if (!g_ctx) {
+    if (device < 0) device = ctl->MPIlocalrank;
+    if (jrb_device_count() < 1) JR_FATAL("no CUDA device available (there is no CPU fallback in this library)");
+    if (jrb_create(&g_ctx, device) != JRB_OK) JR_FATAL(jrb_last_error(NULL));
+  }
+  push_control(ctl);
+  if (jrb_set_tables(g_ctx, &tv) != JRB_OK) JR_FATAL(jrb_last_error(g_ctx));
+  g_have_tables = 1;
+  pthread_mutex_unlock(&g_lock);
+  jrb_host_tables_free(ht);
+  return 0;
+}
+
 int jr_b200_init(ctl_t const *ctl, tbl_t const *tbl, int device) {
   if (!ctl || !tbl) JR_FATAL("jr_b200_init: NULL argument");
   pthread_mutex_lock(&g_lock);
