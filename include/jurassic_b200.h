@@ -92,8 +92,8 @@ typedef struct {
   long long n_kernel_launches;                                /* kernels of this library launched by the last run */
   float ms_raytrace, ms_ega, ms_total_device;                 /* CUDA-event times of the last run (device path) */
   long long h2d_bytes, d2h_bytes;                             /* of the last stage / fetch */
-  int ega_kernel_variant;                                     /* 0 generic, 1 fast (templated) */
-  int ega_ngb, ega_ctm_mask;
+  int ega_kernel_variant;                                     /* 0 generic, 1 specialised (template <continuum mask>) */
+  int ega_ngb, ega_ctm_mask;                                  /* gases handled by the specialised kernel; continuum mask */
   long long table_blob_bytes;
 } jrb_stats;
 

@@ -5,17 +5,18 @@
 // counter so that rays of different length (130..393 segments) balance themselves.
 //
 // Data movement per segment:
-//   * the ray's LOS record (p, T, ds, per-gas u / table cell / interpolation weights; 264 B for 5 gases) is staged
-//     into shared memory by a TMA bulk copy (cp.async.bulk + mbarrier, double buffered per warp): segment ip+1 is in
+//   * the head of the ray's LOS record (p, T, ds, extinction, per-gas u, table cell + interpolation weights; 112 B for
+//     5 gases sharing one (p,T) grid) is staged into shared memory by a TMA bulk copy (cp.async.bulk + mbarrier, double buffered per warp): segment ip+1 is in
 //     flight while segment ip is computed, and every lane reads the fields as shared-memory broadcasts;
 //   * per gas, the four column descriptors are read coalesced (channel innermost), then the four hinted brackets
-//     (one aligned 16-byte load each) are issued back to back so their L2 latencies overlap.
+//     (one aligned 16-byte load each) are requested back to back so their L2 latencies overlap.
 // State: the along-ray recurrence (rad, tau) lives in registers and is stored once per ray; the per-gas path
 // transmittances tau_path[ng] and the bracket hints live in shared memory ([gas][thread], conflict free) so that the
 // gas loop stays rolled -- an unrolled body was > 100 KB of SASS and stalled on instruction fetch (profiles/).
 //
 // Search-free table access: every (gas, column slot) keeps the bracket index it ended on in the previous segment as a
-// 16-bit hint.  The next lookup loads that bracket first and only steps / bisects when the hint is off.  For monotone
+// 10-bit hint (remapped by column identity when the ray moves to a neighbouring (p,T) cell).  The next lookup loads that
+// bracket first and only steps / jumps / bisects when the hint is off.  For monotone
 // columns the index found equals the reference's full bisection (locate_tbl_id, src/jr_common.h:116-125), so results
 // do not depend on the hints.
 #pragma once

@@ -1,7 +1,7 @@
 // jrb_ega_generic.cu -- reference-semantics EGA kernel: any number of gases, per-channel (p,T) axes, plain
 // bisections exactly as locate_id/locate_tbl_id (src/jr_common.h:106-125).  One thread per (ray, channel).
 // It is the fallback for table sets the specialised kernels do not accept (channel-dependent axes, non-monotone
-// columns, ng > 8) and doubles as an on-device cross-check of the specialised kernels.
+// columns, columns longer than 1023 entries, ng > 32) and doubles as an on-device cross-check of the specialised kernels.
 #include "jrb_ega_common.cuh"
 #include <jurassic_b200.h>
 

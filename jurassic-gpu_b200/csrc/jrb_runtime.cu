@@ -440,8 +440,16 @@ int jrb_stage(jrb_context *ctx, int npk, const jrb_atm_view *atm, const jrb_obs_
   ctx->use_fast = (ctx->variant_req == 0) ? 0 : (fast_ok ? 1 : 0);
   ctx->los = make_los_layout(ng, nw, ctx->use_fast, ctx->th.gas_axes_same);
   const size_t per_ray = (size_t)kNLOS * ctx->los.rec * 8;
+  // LOS scratch: JRB_LOS_GB (default 24 GB), but never more than half of what is free on the device right now
   double los_gb = 24.0;
   if (const char *s = getenv("JRB_LOS_GB")) { double v = atof(s); if (v > 0.01) los_gb = v; }
+  {
+    size_t free_b = 0, total_b = 0;
+    if (cudaMemGetInfo(&free_b, &total_b) == cudaSuccess) {
+      const double avail = 0.5 * ((double)free_b + (double)ctx->d_los.cap) / 1e9;
+      if (avail < los_gb) los_gb = avail;
+    }
+  }
   long long chunk = (long long)(los_gb * 1e9 / (double)per_ray);
   if (chunk < 1024) chunk = 1024;
   if (chunk > R) chunk = R;
