@@ -17,6 +17,7 @@ e2e   : the same through the reference-facing call jr_b200_formod_batch(ctl_t*, 
 """
 import argparse
 import copy
+import gc
 import ctypes as C
 import importlib
 import json
@@ -274,6 +275,8 @@ def main():
     for _ in range(max(args.warmup, 1) if args.warmup else 0):
         ctx.run_staged()
     sampler = ClockSampler(local)
+    gc.collect()
+    gc.disable()  # no collector pauses inside the timed regions
     barrier()
     sampler.start()
     ega_ms, rt_ms, launches = [], [], 0
@@ -344,14 +347,23 @@ def main():
             e2e_step()
         barrier()
         t0 = time.perf_counter()
+        per_step = []
         for _ in range(args.steps):
+            ts = time.perf_counter()
             e2e_step()
+            per_step.append((time.perf_counter() - ts) * 1e3)
+        t_loop = time.perf_counter() - t0
         barrier()
         dt_e = allmax(time.perf_counter() - t0)
+        if os.environ.get("JRB_DEBUG_TIMING"):
+            print(f"[bench] e2e steps {['%.1f' % x for x in per_step]} ms, loop {t_loop*1e3:.1f} ms, with barrier {dt_e*1e3:.1f} ms", file=sys.stderr)
         cst = jr.abi.Stats()
         jr.load_core().jrb_get_stats(core, C.byref(cst))
         e2e = {"value": tot_rc / (dt_e / args.steps), "unit": "ray-channels/s", "ms_per_step": dt_e / args.steps * 1e3,
                "h2d_bytes_per_step": int(cst.h2d_bytes), "d2h_bytes_per_step": int(cst.d2h_bytes),
+               "ms_per_step_min": float(min(per_step)), "ms_per_step_max": float(max(per_step)),
+               "host_ms": {"pack": cst.host_ms_pack, "h2d": cst.host_ms_h2d, "device": cst.ms_total_device, "d2h": cst.host_ms_d2h,
+                           "scatter": cst.host_ms_scatter},
                "api": "jr_b200_formod_batch(ctl_t*, atm_t*[], obs_t*[], n) with host structs (ND=32, NG=5)"}
         # spot check: the drop-in's host results equal the device-path results of the first package
         ctx.fetch_staged(pkgs)

@@ -95,6 +95,7 @@ typedef struct {
   int ega_kernel_variant;                                     /* 0 generic, 1 specialised (template <continuum mask>) */
   int ega_ngb, ega_ctm_mask;                                  /* gases handled by the specialised kernel; continuum mask */
   long long table_blob_bytes;
+  float host_ms_pack, host_ms_h2d, host_ms_d2h, host_ms_scatter; /* wall-clock phases of the last stage / fetch */
 } jrb_stats;
 
 typedef struct jrb_context jrb_context;

@@ -88,4 +88,5 @@ class Stats(C.Structure):
                 ("n_los_points", C.c_longlong), ("n_kernel_launches", C.c_longlong), ("ms_raytrace", C.c_float),
                 ("ms_ega", C.c_float), ("ms_total_device", C.c_float), ("h2d_bytes", C.c_longlong),
                 ("d2h_bytes", C.c_longlong), ("ega_kernel_variant", C.c_int), ("ega_ngb", C.c_int),
-                ("ega_ctm_mask", C.c_int), ("table_blob_bytes", C.c_longlong)]
+                ("ega_ctm_mask", C.c_int), ("table_blob_bytes", C.c_longlong), ("host_ms_pack", C.c_float),
+                ("host_ms_h2d", C.c_float), ("host_ms_d2h", C.c_float), ("host_ms_scatter", C.c_float)]

@@ -16,6 +16,7 @@
 #include <stdlib.h>
 #include <string.h>
 #include <strings.h>
+#include <time.h>
 
 /* provided by the reference's CPUdrivers.o when linked into a JURASSIC executable (src/jr_common.h:60-78) */
 extern tbl_t *get_tbl(ctl_t const *ctl) __attribute__((weak));
@@ -142,6 +143,8 @@ int jr_b200_init(ctl_t const *ctl, tbl_t const *tbl, int device) {
 static void formod_batch_impl(ctl_t const *ctl, atm_t *const atm[], obs_t *const obs[], int npackages) {
   if (ctl->checkmode) { printf("# %s: no operation in checkmode\n", __func__); return; }
   if (npackages <= 0) return;
+  struct timespec ts0, ts1, ts2;
+  clock_gettime(CLOCK_MONOTONIC, &ts0);
   pthread_mutex_lock(&g_lock); /* concurrent callers (OpenMP host threads of a retrieval) are serialised */
   if (!g_have_tables) {
     get_tbl_fn const gt = find_get_tbl();
@@ -154,9 +157,15 @@ static void formod_batch_impl(ctl_t const *ctl, atm_t *const atm[], obs_t *const
   jrb_obs_view *ov = (jrb_obs_view *)malloc(sizeof(jrb_obs_view) * (size_t)npackages);
   if (!av || !ov) JR_FATAL("Out of memory!");
   for (int i = 0; i < npackages; i++) { fill_atm_view(atm[i], &av[i]); fill_obs_view(obs[i], &ov[i]); }
+  clock_gettime(CLOCK_MONOTONIC, &ts1);
   if (jrb_formod_batch(g_ctx, npackages, av, ov) != JRB_OK) JR_FATAL(jrb_last_error(g_ctx));
   free(av); free(ov);
   pthread_mutex_unlock(&g_lock);
+  if (getenv("JRB_DEBUG_TIMING")) {
+    clock_gettime(CLOCK_MONOTONIC, &ts2);
+    fprintf(stderr, "[jr_dropin] prepare %.2f ms, core call %.2f ms\n", (ts1.tv_sec - ts0.tv_sec) * 1e3 + (ts1.tv_nsec - ts0.tv_nsec) * 1e-6,
+            (ts2.tv_sec - ts1.tv_sec) * 1e3 + (ts2.tv_nsec - ts1.tv_nsec) * 1e-6);
+  }
 }
 
 void jr_b200_formod_batch(ctl_t const *ctl, atm_t *const atm[], obs_t *const obs[], int npackages) {

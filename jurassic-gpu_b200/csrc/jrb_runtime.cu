@@ -13,6 +13,7 @@
 #include <cstdio>
 #include <cstring>
 #include <mutex>
+#include <chrono>
 #include <thread>
 
 using namespace jrb;
@@ -49,6 +50,9 @@ struct PinBuf {
 std::string g_create_error;
 
 inline size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
+inline double now_ms() {
+  return std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now().time_since_epoch()).count();
+}
 
 // host threads for packing / scattering packages.  Launchers such as torchrun export OMP_NUM_THREADS=1, which would
 // serialise the host side of the end-to-end path, so the count is taken from JRB_HOST_THREADS or the hardware.
@@ -381,6 +385,7 @@ int jrb_stage(jrb_context *ctx, int npk, const jrb_atm_view *atm, const jrb_obs_
   long long *hpoff = (long long *)(H + off_poff);
   int *hrpk = (int *)(H + off_rpk), *hpnp = (int *)(H + off_pnp);
 
+  const double t_pack0 = now_ms();
   ctx->nan_mask.clear();
   std::vector<std::vector<std::pair<long long, int>>> masks(npk);
 #pragma omp parallel for schedule(dynamic, 4) num_threads(host_threads())
@@ -416,6 +421,7 @@ int jrb_stage(jrb_context *ctx, int npk, const jrb_atm_view *atm, const jrb_obs_
   }
   for (int k = 0; k < npk; k++) ctx->nan_mask.insert(ctx->nan_mask.end(), masks[k].begin(), masks[k].end());
 
+  const double t_pack1 = now_ms();
   CU(cudaMemcpyAsync(ctx->d_in.p, H, in_bytes, cudaMemcpyHostToDevice, ctx->stream));
   unsigned char *Dv = (unsigned char *)ctx->d_in.p;
   ctx->geo = (double *)(Dv + off_geo); ctx->atm = (double *)(Dv + off_atm);
@@ -457,6 +463,8 @@ int jrb_stage(jrb_context *ctx, int npk, const jrb_atm_view *atm, const jrb_obs_
   CU(ctx->d_los.ensure((size_t)(chunk ? chunk : 1) * per_ray));
 
   CU(cudaStreamSynchronize(ctx->stream));
+  ctx->stats.host_ms_pack = (float)(t_pack1 - t_pack0);
+  ctx->stats.host_ms_h2d = (float)(now_ms() - t_pack1);
   ctx->stats.h2d_bytes = (long long)in_bytes;
   ctx->stats.n_packages = npk; ctx->stats.n_rays = R; ctx->stats.n_ray_channels = R * nd;
   ctx->staged = true; ctx->ran = false; ctx->np_fetched = false;
@@ -545,8 +553,10 @@ int jrb_fetch_staged(jrb_context *ctx, int npk, const jrb_obs_view *obs) {
   const int nd = ctx->nd;
   const size_t out_bytes = ((size_t)2 * R * nd + 3 * (size_t)R) * 8;
   CU(ctx->h_out.ensure(out_bytes + 256));
+  const double t_d2h0 = now_ms();
   CU(cudaMemcpyAsync(ctx->h_out.p, ctx->d_out.p, out_bytes, cudaMemcpyDeviceToHost, ctx->stream));
   CU(cudaStreamSynchronize(ctx->stream));
+  const double t_d2h1 = now_ms();
   double *hrad = (double *)ctx->h_out.p, *htau = hrad + (size_t)R * nd, *htp = htau + (size_t)R * nd;
   const double nan = std::nan("");
   for (auto &m : ctx->nan_mask) hrad[(size_t)m.first * nd + m.second] = nan; // apply_mask (src/jr_common.h:203-210)
@@ -569,15 +579,25 @@ int jrb_fetch_staged(jrb_context *ctx, int npk, const jrb_obs_view *obs) {
   for (int k = 0; k < npk; k++)
     if (obs[k].nr != ctx->pk_nr[k]) return ctx->fail(JRB_ERR_ARG, "obs[k].nr changed between stage and fetch");
   ctx->stats.d2h_bytes = (long long)out_bytes;
+  ctx->stats.host_ms_d2h = (float)(t_d2h1 - t_d2h0);
+  ctx->stats.host_ms_scatter = (float)(now_ms() - t_d2h1);
   return JRB_OK;
 }
 
 int jrb_formod_batch(jrb_context *ctx, int npk, const jrb_atm_view *atm, const jrb_obs_view *obs) {
+  const double t0 = now_ms();
   int rc = jrb_stage(ctx, npk, atm, obs);
   if (rc != JRB_OK) return rc;
+  const double t1 = now_ms();
   rc = jrb_run_staged(ctx);
   if (rc != JRB_OK) return rc;
-  return jrb_fetch_staged(ctx, npk, obs);
+  const double t2 = now_ms();
+  rc = jrb_fetch_staged(ctx, npk, obs);
+  if (getenv("JRB_DEBUG_TIMING"))
+    fprintf(stderr, "[jrb] stage %.2f ms  run %.2f ms  fetch %.2f ms (pack %.2f h2d %.2f dev %.2f d2h %.2f scatter %.2f)\n", t1 - t0,
+            t2 - t1, now_ms() - t2, ctx->stats.host_ms_pack, ctx->stats.host_ms_h2d, ctx->stats.ms_total_device, ctx->stats.host_ms_d2h,
+            ctx->stats.host_ms_scatter);
+  return rc;
 }
 
 int jrb_staged_results(jrb_context *ctx, double **rad_dev, double **tau_dev, long long *n_rays, int *nd) {
