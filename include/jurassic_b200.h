@@ -96,6 +96,7 @@ typedef struct {
   int ega_ngb, ega_ctm_mask;                                  /* gases handled by the specialised kernel; continuum mask */
   long long table_blob_bytes;
   float host_ms_pack, host_ms_h2d, host_ms_d2h, host_ms_scatter; /* wall-clock phases of the last stage / fetch */
+  int n_chunks, pipelined; /* LOS chunks of the last run; 1 if the tracer of chunk c+1 ran beside the EGA kernel of chunk c */
 } jrb_stats;
 
 typedef struct jrb_context jrb_context;

@@ -89,4 +89,5 @@ class Stats(C.Structure):
                 ("ms_ega", C.c_float), ("ms_total_device", C.c_float), ("h2d_bytes", C.c_longlong),
                 ("d2h_bytes", C.c_longlong), ("ega_kernel_variant", C.c_int), ("ega_ngb", C.c_int),
                 ("ega_ctm_mask", C.c_int), ("table_blob_bytes", C.c_longlong), ("host_ms_pack", C.c_float),
-                ("host_ms_h2d", C.c_float), ("host_ms_d2h", C.c_float), ("host_ms_scatter", C.c_float)]
+                ("host_ms_h2d", C.c_float), ("host_ms_d2h", C.c_float), ("host_ms_scatter", C.c_float),
+                ("n_chunks", C.c_int), ("pipelined", C.c_int)]

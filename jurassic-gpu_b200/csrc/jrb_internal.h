@@ -19,6 +19,7 @@ struct TraceArgs {
   double *atm_lnp_slope;       // [2][atm_stride] scratch: log(p[i+1]/p[i])/(z[i+1]-z[i]) (NaN where not both positive), dT/dz
   long long n_atm;
   int prepare_atm;             // 1: (re)compute atm_lnp_slope before tracing
+  int small_blocks;            // 1: 32/64-thread CTAs that fit beside the resident EGA CTAs (pipelined chunks)
   // control
   int refrac, ig_h2o;
   double rayds, raydz;

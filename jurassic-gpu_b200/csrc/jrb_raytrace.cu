@@ -334,9 +334,12 @@ cudaError_t launch_raytrace(const TraceArgs &a, cudaStream_t stream, int *launch
     if (launches) ++*launches;
   }
   if (a.n_rays <= 0) return cudaGetLastError();
-  ray_step_kernel<<<(unsigned)((a.n_rays + 127) / 128), 128, 0, stream>>>(a);
+  // pipelined chunks run beside the persistent EGA CTAs of the previous chunk, which leave ~4 K registers per SM:
+  // one-warp ray CTAs (104 regs x 32) and two-warp finalisation CTAs (48 regs x 64) fit into that remainder
+  const int bs = a.small_blocks ? 32 : 128, bf = a.small_blocks ? 64 : 256;
+  ray_step_kernel<<<(unsigned)((a.n_rays + bs - 1) / bs), bs, 0, stream>>>(a);
   const long long n = a.n_rays * kNLOS;
-  los_finalize_kernel<<<(unsigned)((n + 255) / 256), 256, 0, stream>>>(a);
+  los_finalize_kernel<<<(unsigned)((n + bf - 1) / bf), bf, 0, stream>>>(a);
   if (launches) *launches += 2;
   return cudaGetLastError();
 }

@@ -106,6 +106,8 @@ struct jrb_context {
   long long *pkg_atm_off = nullptr;
   double *o_rad = nullptr, *o_tau = nullptr, *o_tp = nullptr;
   long long chunk_rays = 0;
+  int nbuf = 1;                 // LOS buffers: 1 = chunks run back to back, 3 = tracer(c+1) overlaps EGA(c)
+  cudaStream_t s_trace = nullptr, s_ega[2] = {nullptr, nullptr};
   LosLayout los;
   int use_fast = 0;
   std::vector<cudaEvent_t> events;
@@ -156,6 +158,13 @@ int jrb_create(jrb_context **out, int device) {
   cudaDeviceGetAttribute(&ctx->sm_count, cudaDevAttrMultiProcessorCount, device);
   e = cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking);
   if (e != cudaSuccess) { g_create_error = std::string("cudaStreamCreate: ") + cudaGetErrorString(e); delete ctx; return JRB_ERR_CUDA; }
+  int lo_prio = 0, hi_prio = 0;
+  cudaDeviceGetStreamPriorityRange(&lo_prio, &hi_prio);
+  if (cudaStreamCreateWithPriority(&ctx->s_trace, cudaStreamNonBlocking, hi_prio) != cudaSuccess ||
+      cudaStreamCreateWithFlags(&ctx->s_ega[0], cudaStreamNonBlocking) != cudaSuccess ||
+      cudaStreamCreateWithFlags(&ctx->s_ega[1], cudaStreamNonBlocking) != cudaSuccess) {
+    g_create_error = "cudaStreamCreate failed"; delete ctx; return JRB_ERR_CUDA;
+  }
   std::memset(&ctx->stats, 0, sizeof(ctx->stats));
   *out = ctx;
   return JRB_OK;
@@ -170,6 +179,8 @@ void jrb_destroy(jrb_context *ctx) {
   ctx->d_in.release(); ctx->d_out.release(); ctx->d_los.release(); ctx->d_np.release(); ctx->d_tsurf.release();
   ctx->d_counter.release(); ctx->d_slope.release(); ctx->d_level0.release(); ctx->h_in.release(); ctx->h_out.release();
   cudaStreamDestroy(ctx->stream);
+  if (ctx->s_trace) cudaStreamDestroy(ctx->s_trace);
+  for (auto st : ctx->s_ega) if (st) cudaStreamDestroy(st);
   delete ctx;
 }
 
@@ -433,7 +444,6 @@ int jrb_stage(jrb_context *ctx, int npk, const jrb_atm_view *atm, const jrb_obs_
   ctx->o_rad = (double *)ctx->d_out.p; ctx->o_tau = ctx->o_rad + (size_t)R * nd; ctx->o_tp = ctx->o_tau + (size_t)R * nd;
   CU(ctx->d_np.ensure((size_t)(R ? R : 1) * 4));
   CU(ctx->d_tsurf.ensure((size_t)(R ? R : 1) * 8));
-  CU(ctx->d_counter.ensure(256));
   CU(ctx->d_slope.ensure((size_t)(A ? A : 1) * 16));
   CU(ctx->d_level0.ensure((size_t)(R ? R : 1) * 4));
 
@@ -456,11 +466,28 @@ int jrb_stage(jrb_context *ctx, int npk, const jrb_atm_view *atm, const jrb_obs_
       if (avail < los_gb) los_gb = avail;
     }
   }
+  // Chunking.  By default a batch is one chunk (or as many as the LOS scratch limit requires), run back to back.
+  // JRB_PIPELINE=1 cuts large batches into ~8 chunks held in 3 rotating LOS buffers so that the (latency-bound, low
+  // occupancy) tracer kernels of chunk c+1 run beside the EGA kernel of chunk c.  Measured on B200 (profiles/README.md):
+  // the extra EGA kernel tails cost more than the hidden tracer time (143.4 vs 138.3 ms), hence opt-in.
   long long chunk = (long long)(los_gb * 1e9 / (double)per_ray);
+  ctx->nbuf = 1;
+  const char *pipe_env = getenv("JRB_PIPELINE");
+  const bool want_pipe = pipe_env && atoi(pipe_env) != 0;
+  if (want_pipe && R >= 32768) {
+    long long pc = (R + 7) / 8;
+    if (pc < 8192) pc = 8192;
+    if (pc * 3 > chunk) pc = chunk / 3;
+    if (pc >= 4096) { chunk = pc; ctx->nbuf = 3; }
+  }
   if (chunk < 1024) chunk = 1024;
   if (chunk > R) chunk = R;
   ctx->chunk_rays = chunk;
-  CU(ctx->d_los.ensure((size_t)(chunk ? chunk : 1) * per_ray));
+  CU(ctx->d_los.ensure((size_t)(chunk ? chunk : 1) * per_ray * ctx->nbuf));
+  {
+    const long long nch = R > 0 ? (R + chunk - 1) / chunk : 1;
+    CU(ctx->d_counter.ensure((size_t)nch * 8 + 256));
+  }
 
   CU(cudaStreamSynchronize(ctx->stream));
   ctx->stats.host_ms_pack = (float)(t_pack1 - t_pack0);
@@ -479,13 +506,22 @@ int jrb_run_staged(jrb_context *ctx) {
   const long long R = ctx->n_rays, A = ctx->n_atm;
   const int ng = ctx->ng, nd = ctx->nd, nw = ctx->nw;
   const long long nchunks = R > 0 ? (R + ctx->chunk_rays - 1) / ctx->chunk_rays : 0;
-  const size_t need_ev = 2 + 3 * (size_t)nchunks;
+  const bool pipe = ctx->nbuf > 1 && nchunks > 1;
+  // events: [0] start, [1] end, per chunk: tracer start / tracer done / EGA start / EGA done
+  const size_t need_ev = 2 + 4 * (size_t)nchunks;
   while (ctx->events.size() < need_ev) { cudaEvent_t ev; CU(cudaEventCreate(&ev)); ctx->events.push_back(ev); }
+  auto EV = [&](long long c, int k) { return ctx->events[2 + 4 * (size_t)c + k]; };
+  const size_t per_ray = (size_t)kNLOS * ctx->los.rec;
   long long launches = 0;
   int ngb = ng;
+  cudaStream_t st_tr = pipe ? ctx->s_trace : ctx->stream;
   CU(cudaEventRecord(ctx->events[0], ctx->stream));
+  if (pipe) CU(cudaStreamWaitEvent(st_tr, ctx->events[0], 0));
+  if (ctx->use_fast && nchunks > 0) CU(cudaMemsetAsync(ctx->d_counter.p, 0, (size_t)nchunks * 8, st_tr));
   for (long long c = 0; c < nchunks; c++) {
     const long long r0 = c * ctx->chunk_rays, r1 = std::min(R, r0 + ctx->chunk_rays);
+    double *los_buf = (double *)ctx->d_los.p + (size_t)(c % ctx->nbuf) * (size_t)ctx->chunk_rays * per_ray;
+    cudaStream_t st_e = pipe ? ctx->s_ega[c & 1] : ctx->stream;
     TraceArgs t;
     t.n_rays = r1 - r0;
     t.geo = ctx->geo + r0; t.geo_stride = R;
@@ -495,48 +531,54 @@ int jrb_run_staged(jrb_context *ctx) {
     t.atm_p = ctx->atm + 4 * A; t.atm_t = ctx->atm + 5 * A; t.atm_q = ctx->atm + 6 * A; t.atm_k = ctx->atm + (size_t)(6 + ng) * A;
     t.atm_stride = A;
     t.atm_lnp_slope = (double *)ctx->d_slope.p; t.n_atm = A; t.prepare_atm = (c == 0);
+    t.small_blocks = pipe && c > 0;
     t.refrac = ctx->refrac; t.ig_h2o = (ctx->ctm_mask & 4) ? ctx->ig_h2o : -1;
     t.rayds = ctx->rayds; t.raydz = ctx->raydz;
-    t.los = ctx->los; t.los_data = (double *)ctx->d_los.p;
+    t.los = ctx->los; t.los_data = los_buf;
     t.ray_np = (int *)ctx->d_np.p + r0; t.ray_tsurf = (double *)ctx->d_tsurf.p + r0;
     t.ray_level0 = (int *)ctx->d_level0.p + r0;
     t.tp = ctx->o_tp + r0;
     t.tbl = ctx->td;
-    CU(cudaEventRecord(ctx->events[2 + 3 * c], ctx->stream));
+    if (pipe && c >= ctx->nbuf) CU(cudaStreamWaitEvent(st_tr, EV(c - ctx->nbuf, 3), 0)); // LOS buffer free again
+    CU(cudaEventRecord(EV(c, 0), st_tr));
     int nl = 0;
-    CU(launch_raytrace(t, ctx->stream, &nl));
+    CU(launch_raytrace(t, st_tr, &nl));
     launches += nl;
-    CU(cudaEventRecord(ctx->events[3 + 3 * c], ctx->stream));
+    CU(cudaEventRecord(EV(c, 1), st_tr));
 
     EgaArgs e;
     e.n_rays = r1 - r0; e.ng = ng; e.nd = nd; e.nw = nw;
     e.ctm_mask = ctx->ctm_mask; e.ig_co2 = ctx->ig_co2 >= 0 ? ctx->ig_co2 : 0; e.ig_h2o = ctx->ig_h2o >= 0 ? ctx->ig_h2o : 0;
     e.write_bbt = ctx->write_bbt;
-    e.los = ctx->los; e.los_data = (const double *)ctx->d_los.p;
+    e.los = ctx->los; e.los_data = los_buf;
     e.ray_np = (const int *)ctx->d_np.p + r0; e.ray_tsurf = (const double *)ctx->d_tsurf.p + r0;
     e.chan = (const double *)ctx->d_chan.p; e.window = (const int *)ctx->d_window.p;
     e.tbl = ctx->td;
     e.rad = ctx->o_rad + (size_t)r0 * nd; e.tau = ctx->o_tau + (size_t)r0 * nd;
-    e.work_counter = (unsigned long long *)ctx->d_counter.p;
-    if (ctx->use_fast) {
-      CU(cudaMemsetAsync(ctx->d_counter.p, 0, 8, ctx->stream));
-      CU(launch_ega_fast(e, ctx->stream, &ngb));
-    } else {
-      CU(launch_ega_generic(e, ctx->stream));
-    }
+    e.work_counter = (unsigned long long *)ctx->d_counter.p + c;
+    if (pipe) CU(cudaStreamWaitEvent(st_e, EV(c, 1), 0));
+    CU(cudaEventRecord(EV(c, 2), st_e));
+    if (ctx->use_fast) CU(launch_ega_fast(e, st_e, &ngb));
+    else CU(launch_ega_generic(e, st_e));
     launches++;
-    CU(cudaEventRecord(ctx->events[4 + 3 * c], ctx->stream));
+    CU(cudaEventRecord(EV(c, 3), st_e));
+  }
+  if (pipe) {
+    CU(cudaStreamWaitEvent(ctx->stream, EV(nchunks - 1, 3), 0));
+    if (nchunks > 1) CU(cudaStreamWaitEvent(ctx->stream, EV(nchunks - 2, 3), 0));
   }
   CU(cudaEventRecord(ctx->events[1], ctx->stream));
   CU(cudaStreamSynchronize(ctx->stream));
   float ms_rt = 0, ms_ega = 0, ms_tot = 0, ms;
   for (long long c = 0; c < nchunks; c++) {
-    CU(cudaEventElapsedTime(&ms, ctx->events[2 + 3 * c], ctx->events[3 + 3 * c])); ms_rt += ms;
-    CU(cudaEventElapsedTime(&ms, ctx->events[3 + 3 * c], ctx->events[4 + 3 * c])); ms_ega += ms;
+    CU(cudaEventElapsedTime(&ms, EV(c, 0), EV(c, 1))); ms_rt += ms;
+    CU(cudaEventElapsedTime(&ms, EV(c, 2), EV(c, 3))); ms_ega += ms;
   }
   CU(cudaEventElapsedTime(&ms_tot, ctx->events[0], ctx->events[1]));
+  // with pipelined chunks the per-kernel spans overlap each other: ms_raytrace + ms_ega may exceed ms_total_device
   ctx->stats.ms_raytrace = ms_rt; ctx->stats.ms_ega = ms_ega; ctx->stats.ms_total_device = ms_tot;
   ctx->stats.n_kernel_launches = launches;
+  ctx->stats.n_chunks = (int)nchunks; ctx->stats.pipelined = pipe ? 1 : 0;
   ctx->stats.ega_kernel_variant = ctx->use_fast; ctx->stats.ega_ngb = ctx->use_fast ? ngb : 0;
   ctx->stats.ega_ctm_mask = ctx->ctm_mask;
   ctx->ran = true; ctx->np_fetched = false;
@@ -617,24 +659,12 @@ int jrb_debug_los(jrb_context *ctx, long long ray, double *out, int max_doubles,
   std::lock_guard<std::mutex> lk(ctx->mtx);
   if (!ctx->ran) return ctx->fail(JRB_ERR_STATE, "jrb_run_staged has not completed");
   if (ray < 0 || ray >= ctx->n_rays) return ctx->fail(JRB_ERR_ARG, "ray out of range");
-  if (ctx->chunk_rays < ctx->n_rays) {
-    // only the last chunk's LOS is still resident
-    const long long last0 = (ctx->n_rays - 1) / ctx->chunk_rays * ctx->chunk_rays;
-    if (ray < last0) return ctx->fail(JRB_ERR_STATE, "LOS of this ray was overwritten by a later chunk");
-    ray -= last0;
-    CU(cudaSetDevice(ctx->device));
-    int np = 0;
-    CU(cudaMemcpy(&np, (int *)ctx->d_np.p + last0 + ray, 4, cudaMemcpyDeviceToHost));
-    if (tsurf_out) CU(cudaMemcpy(tsurf_out, (double *)ctx->d_tsurf.p + last0 + ray, 8, cudaMemcpyDeviceToHost));
-    if (np_out) *np_out = np;
-    if (rec_doubles) *rec_doubles = ctx->los.rec;
-    const size_t n = (size_t)np * ctx->los.rec;
-    if (out) {
-      if ((size_t)max_doubles < n) return ctx->fail(JRB_ERR_ARG, "output buffer too small");
-      CU(cudaMemcpy(out, (double *)ctx->d_los.p + (size_t)ray * kNLOS * ctx->los.rec, n * 8, cudaMemcpyDeviceToHost));
-    }
-    return JRB_OK;
-  }
+  const long long nchunks = (ctx->n_rays + ctx->chunk_rays - 1) / ctx->chunk_rays;
+  const long long c = ray / ctx->chunk_rays;
+  if (c < nchunks - ctx->nbuf) return ctx->fail(JRB_ERR_STATE, "LOS of this ray was overwritten by a later chunk");
+  const size_t per_ray = (size_t)kNLOS * ctx->los.rec;
+  const double *src = (const double *)ctx->d_los.p + (size_t)(c % ctx->nbuf) * (size_t)ctx->chunk_rays * per_ray +
+                      (size_t)(ray - c * ctx->chunk_rays) * per_ray;
   CU(cudaSetDevice(ctx->device));
   int np = 0;
   CU(cudaMemcpy(&np, (int *)ctx->d_np.p + ray, 4, cudaMemcpyDeviceToHost));
@@ -644,7 +674,7 @@ int jrb_debug_los(jrb_context *ctx, long long ray, double *out, int max_doubles,
   const size_t n = (size_t)np * ctx->los.rec;
   if (out) {
     if ((size_t)max_doubles < n) return ctx->fail(JRB_ERR_ARG, "output buffer too small");
-    CU(cudaMemcpy(out, (double *)ctx->d_los.p + (size_t)ray * kNLOS * ctx->los.rec, n * 8, cudaMemcpyDeviceToHost));
+    CU(cudaMemcpy(out, src, n * 8, cudaMemcpyDeviceToHost));
   }
   return JRB_OK;
 }

@@ -225,6 +225,23 @@ def test_los_chunking_gives_identical_results(jr, gpu_ctx_factory, monkeypatch):
         assert np.array_equal(a.rad, b.rad) and np.array_equal(a.tau, b.tau)
 
 
+def test_pipelined_chunks_give_identical_results(jr, gpu_ctx_factory, monkeypatch):
+    """JRB_PIPELINE=1: tracer of chunk c+1 beside the EGA kernel of chunk c on separate streams, 3 rotating LOS buffers"""
+    ctl = jr.synth.control_config_d(nd=4)
+    tbl = jr.synth.make_tables(ctl)
+    pkgs = [jr.synth.limb_package(ctl, seed=500 + i) for i in range(34)]  # 36 992 rays >= the pipelining threshold
+    ctx = gpu_ctx_factory()
+    plain = run_cuda(ctx, ctl, tbl, pkgs, 1)
+    assert ctx.stats()["pipelined"] == 0
+    monkeypatch.setenv("JRB_PIPELINE", "1")
+    ctx2 = gpu_ctx_factory()
+    piped = run_cuda(ctx2, ctl, tbl, pkgs, 1)
+    st = ctx2.stats()
+    assert st["pipelined"] == 1 and st["n_chunks"] >= 4
+    for a, b in zip(plain, piped):
+        assert np.array_equal(a.rad, b.rad) and np.array_equal(a.tau, b.tau) and np.array_equal(a.tpz, b.tpz)
+
+
 def test_large_batch_properties(jr, oracle, gpu_ctx_factory):
     """Size-independent properties at a bench-like size (32 Config-D packages = 34 816 rays x 32 channels):
     duplicated packages give bit-identical results wherever they sit in the batch, tau in [0,1], rad >= 0,
