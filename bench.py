@@ -379,8 +379,8 @@ def main():
     ega = float(np.mean(ega_ms))
     achieved = my_rc * bytes_rc / (ega / 1e3) / 1e9
     traffic = None
-    tp = os.path.join(ROOT, "profiles", "ega_traffic.json")
-    if os.path.exists(tp):
+    tp = os.path.join(ROOT, "profiles", "ega_traffic.json")  # from one ncu --set full capture of this workload's launch
+    if os.path.exists(tp) and args.config == "d" and args.packages == WORKLOADS["d"]["packages"]:
         try:
             traffic = json.load(open(tp)).get("dram_bytes_per_launch")
         except Exception:
