@@ -1,7 +1,8 @@
 #!/usr/bin/env python3
-"""Quick GPU sanity run: CUDA vs CPU oracle on small cases + first timings (development helper)."""
+"""Quick GPU sanity run: CUDA vs CPU oracle on small cases + first timings (development helper; lives under tests/
+because it uses the oracle as checker)."""
 import copy, importlib, os, sys, time
-ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 sys.path.insert(0, ROOT); sys.path.insert(0, os.path.join(ROOT, "oracle"))
 import numpy as np
 jr = importlib.import_module("jurassic-gpu_b200")
