@@ -364,7 +364,7 @@ def main():
                "ms_per_step_min": float(min(per_step)), "ms_per_step_max": float(max(per_step)),
                "host_ms": {"pack": cst.host_ms_pack, "h2d": cst.host_ms_h2d, "device": cst.ms_total_device, "d2h": cst.host_ms_d2h,
                            "scatter": cst.host_ms_scatter},
-               "api": "jr_b200_formod_batch(ctl_t*, atm_t*[], obs_t*[], n) with host structs (ND=32, NG=5)"}
+               "api": f"jr_b200_formod_batch(ctl_t*, atm_t*[], obs_t*[], n) with host structs (ND={ND_D}, NG={NG_D})"}
         # spot check: the drop-in's host results equal the device-path results of the first package
         ctx.fetch_staged(pkgs)
         got = np.ctypeslib.as_array(obss[0].rad)[: pkgs[0].n_rays, : ctl.nd]
