@@ -158,14 +158,20 @@ constexpr int kEgaBlock = 256;
 #define JRB_EGA_MINBLOCKS 3 // CTAs per SM the register allocation must allow (3 x 8 warps; measured best, see profiles/)
 #endif
 
-__host__ __device__ inline size_t ega_fast_smem_bytes(int ng, int rec, int threads) {
+// rays per warp: 1 for nd > 16; for fewer channels a warp takes floor(32/nd) whole rays (lane = ray_in_warp * nd + channel)
+__host__ __device__ inline int ega_rays_per_warp(int nd) { return nd > 16 ? 1 : 32 / nd; }
+
+__host__ __device__ inline size_t ega_fast_smem_bytes(int ng, int rec, int threads, int rpw) {
   const int nwarps = threads / 32;
-  return (size_t)nwarps * 2 * 8            // mbarriers
-         + (size_t)nwarps * 2 * rec * 8    // LOS record double buffers
-         + (size_t)ng * threads * 16;      // tau_path + hints
+  return (size_t)nwarps * 2 * 8                  // mbarriers
+         + (size_t)nwarps * 2 * rpw * rec * 8    // LOS record double buffers (one record per ray of the warp)
+         + (size_t)ng * threads * 16;            // tau_path + hints
 }
 
-template <int MASK>
+// MULTI = false: one ray per warp, lane = channel of a 32-channel group (nd > 16).
+// MULTI = true : nd <= 16, floor(32/nd) rays per warp so that few-channel instruments (the reference's own examples have
+//                2 and 3 channels) do not leave 90 % of the lanes idle; every ray of the warp gets its own staged record.
+template <int MASK, bool MULTI>
 __global__ void __launch_bounds__(kEgaBlock, JRB_EGA_MINBLOCKS) ega_fast_kernel(const EgaArgs a) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, nwarps = blockDim.x >> 5;
@@ -174,9 +180,11 @@ __global__ void __launch_bounds__(kEgaBlock, JRB_EGA_MINBLOCKS) ega_fast_kernel(
   const int nd = a.nd, ng = a.ng;
   const unsigned rec_bytes = (unsigned)L.head * 8u; // only the head of a record is staged
 
+  const int rpw = MULTI ? 32 / nd : 1;          // rays per warp
+  const int bufstride = rpw * L.head;           // doubles per record buffer of a warp
   unsigned long long *bars = reinterpret_cast<unsigned long long *>(smem_raw) + warp * 2;
-  double *recbuf = reinterpret_cast<double *>(smem_raw + (size_t)nwarps * 16) + (size_t)warp * 2 * L.head;
-  double *tau_s = reinterpret_cast<double *>(smem_raw + (size_t)nwarps * 16 + (size_t)nwarps * 2 * L.head * 8) + tid;
+  double *recbuf = reinterpret_cast<double *>(smem_raw + (size_t)nwarps * 16) + (size_t)warp * 2 * bufstride;
+  double *tau_s = reinterpret_cast<double *>(smem_raw + (size_t)nwarps * 16 + (size_t)nwarps * 2 * bufstride * 8) + tid;
   unsigned long long *hint_s = reinterpret_cast<unsigned long long *>(tau_s - tid + (size_t)ng * blockDim.x) + tid;
   const int sstride = blockDim.x;
 
@@ -186,23 +194,36 @@ __global__ void __launch_bounds__(kEgaBlock, JRB_EGA_MINBLOCKS) ega_fast_kernel(
   unsigned parity0 = 0, parity1 = 0;
 
   const int ngroups = (nd + 31) >> 5;
-  const unsigned long long n_items = (unsigned long long)a.n_rays * ngroups;
+  const unsigned long long n_items = MULTI ? (unsigned long long)((a.n_rays + rpw - 1) / rpw) : (unsigned long long)a.n_rays * ngroups;
+  const int sub = MULTI ? lane / nd : 0;        // ray of this lane within the warp
 
   for (;;) {
     unsigned long long item = 0;
     if (lane == 0) item = atomicAdd(a.work_counter, 1ull);
     item = __shfl_sync(0xffffffffu, item, 0);
     if (item >= n_items) break;
-    // channel-group major: all warps in flight work on the same 32 channels, so the part of the tables that is hot
-    // at any time is (32 channels x ng gases), which is what has to fit into L2
-    const int grp = (int)(item / (unsigned long long)a.n_rays);
-    const long long ir = (long long)(item - (unsigned long long)grp * (unsigned long long)a.n_rays);
-    const int id_raw = grp * 32 + lane;
-    const bool lane_on = id_raw < nd;
-    const int id = lane_on ? id_raw : nd - 1;
+    long long ir;
+    int id;
+    bool lane_on;
+    if (MULTI) {
+      ir = (long long)item * rpw + sub;
+      lane_on = sub < rpw && ir < a.n_rays;
+      if (!lane_on) ir = a.n_rays - 1; // idle lanes shadow a valid ray and never store
+      id = lane_on ? lane - sub * nd : 0;
+    } else {
+      // channel-group major: all warps in flight work on the same 32 channels, so the part of the tables that is hot
+      // at any time is (32 channels x ng gases), which is what has to fit into L2
+      const int grp = (int)(item / (unsigned long long)a.n_rays);
+      ir = (long long)(item - (unsigned long long)grp * (unsigned long long)a.n_rays);
+      const int id_raw = grp * 32 + lane;
+      lane_on = id_raw < nd;
+      id = lane_on ? id_raw : nd - 1;
+    }
 
     const double *__restrict__ rec_g = a.los_data + (size_t)ir * kNLOS * L.rec;
-    const int np = a.ray_np[ir];
+    const int np = lane_on || !MULTI ? a.ray_np[ir] : 0;       // segments of this lane's ray
+    const int np_max = MULTI ? __reduce_max_sync(0xffffffffu, np) : np;
+    const bool head_lane = MULTI ? (lane_on && id == 0) : (lane == 0); // issues the record copies of its ray
     const int win = a.window[id];
 
     for (int ig = 0; ig < ng; ig++) {
@@ -214,24 +235,36 @@ __global__ void __launch_bounds__(kEgaBlock, JRB_EGA_MINBLOCKS) ega_fast_kernel(
     bool dead = false; // a gas went opaque (tau_path < 1e-9): nothing changes any more (src/jr_common.h:239,295)
 
     __syncwarp();
-    if (np > 0 && lane == 0) {
-      fast::mbar_expect_tx(&bars[0], rec_bytes);
-      fast::tma_load_1d(recbuf, rec_g, rec_bytes, &bars[0]);
+    // one copy per ray of the warp and segment; the barrier of a buffer expects the bytes of all copies aimed at it
+    {
+      const unsigned cnt = MULTI ? __popc(__ballot_sync(0xffffffffu, head_lane && np > 0)) : (np > 0 ? 1u : 0u);
+      if (cnt && lane == 0) fast::mbar_expect_tx(&bars[0], cnt * rec_bytes);
+      __syncwarp();
+      if (head_lane && np > 0) fast::tma_load_1d(recbuf + (size_t)sub * L.head, rec_g, rec_bytes, &bars[0]);
     }
-    for (int ip = 0; ip < np; ++ip) {
+    for (int ip = 0; ip < np_max; ++ip) {
       const int b = ip & 1;
       __syncwarp(); // every lane is done with the other buffer (segment ip-1)
-      const bool all_dead = __all_sync(0xffffffffu, dead);
-      if ((ip + 1 < np) && !all_dead && lane == 0) { // segment ip+1 travels while segment ip is computed
-        fast::mbar_expect_tx(&bars[b ^ 1], rec_bytes);
-        fast::tma_load_1d(recbuf + (size_t)(b ^ 1) * L.head, rec_g + (size_t)(ip + 1) * L.rec, rec_bytes, &bars[b ^ 1]);
+      const bool all_dead = __all_sync(0xffffffffu, dead || ip >= np);
+      {
+        const bool want = !all_dead && head_lane && (ip + 1 < np); // segment ip+1 travels while segment ip is computed
+        const unsigned cnt = MULTI ? __popc(__ballot_sync(0xffffffffu, want)) : (want ? 1u : 0u);
+        if (MULTI) {
+          if (cnt && lane == 0) fast::mbar_expect_tx(&bars[b ^ 1], cnt * rec_bytes);
+          __syncwarp();
+        } else if (want) {
+          fast::mbar_expect_tx(&bars[b ^ 1], rec_bytes);
+        }
+        if (want)
+          fast::tma_load_1d(recbuf + (size_t)(b ^ 1) * bufstride + (size_t)sub * L.head, rec_g + (size_t)(ip + 1) * L.rec, rec_bytes,
+                            &bars[b ^ 1]);
       }
-      // the copy of segment ip is always in flight here (issued above one iteration earlier, or before the loop)
+      // the copies of segment ip are always in flight here (issued above one iteration earlier, or before the loop)
       if (b == 0) { fast::mbar_wait(&bars[0], parity0); parity0 ^= 1; } else { fast::mbar_wait(&bars[1], parity1); parity1 ^= 1; }
       if (all_dead) break; // nothing further was requested
-      if (dead) continue;
+      if (dead || ip >= np) continue;
 
-      const double *__restrict__ R = recbuf + (size_t)b * L.head;
+      const double *__restrict__ R = recbuf + (size_t)b * bufstride + (size_t)sub * L.head;
       const double p = R[0], t = R[1], ds = R[2];
       const double u_co2 = (MASK & 8) ? R[L.u0 + a.ig_co2] : 0.0;
       const double u_h2o = (MASK & 4) ? R[L.u0 + a.ig_h2o] : 0.0;
@@ -270,7 +303,7 @@ __global__ void __launch_bounds__(kEgaBlock, JRB_EGA_MINBLOCKS) ega_fast_kernel(
           unsigned long long h = hint_s[ig * sstride];
           if (h != ~0ull && cell != kCellInvalid && c00.y >= 2 && c01.y >= 2 && c10.y >= 2 && c11.y >= 2) {
             const unsigned ocell = (unsigned)(h >> 40);
-            if (ocell != cell) h = fast::remap_hints(h, ocell, cell); // warp-uniform: the cell belongs to the ray
+            if (ocell != cell) h = fast::remap_hints(h, ocell, cell); // uniform per ray: the cell belongs to the ray
             const float4 *__restrict__ p00 = T.brk + c00.x, *__restrict__ p01 = T.brk + c01.x,
                                        *__restrict__ p10 = T.brk + c10.x, *__restrict__ p11 = T.brk + c11.x;
             int k00 = min((int)(h & 0x3ffu), (int)c00.y - 2), k01 = min((int)((h >> 10) & 0x3ffu), (int)c01.y - 2),
@@ -310,23 +343,29 @@ __global__ void __launch_bounds__(kEgaBlock, JRB_EGA_MINBLOCKS) ega_fast_kernel(
   }
 }
 
-template <int MASK>
-cudaError_t launch_ega_fast_t(const EgaArgs &a, cudaStream_t stream, int sm_count) {
-  const size_t smem = ega_fast_smem_bytes(a.ng, a.los.head, kEgaBlock);
-  cudaError_t e = cudaFuncSetAttribute(ega_fast_kernel<MASK>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+template <int MASK, bool MULTI>
+cudaError_t launch_ega_fast_tm(const EgaArgs &a, cudaStream_t stream, int sm_count) {
+  const int rpw = MULTI ? ega_rays_per_warp(a.nd) : 1;
+  const size_t smem = ega_fast_smem_bytes(a.ng, a.los.head, kEgaBlock, rpw);
+  cudaError_t e = cudaFuncSetAttribute(ega_fast_kernel<MASK, MULTI>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   if (e != cudaSuccess) return e;
   int blocks_per_sm = 0;
-  e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&blocks_per_sm, ega_fast_kernel<MASK>, kEgaBlock, smem);
+  e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&blocks_per_sm, ega_fast_kernel<MASK, MULTI>, kEgaBlock, smem);
   if (e != cudaSuccess) return e;
   if (blocks_per_sm < 1) return cudaErrorInvalidConfiguration;
   const int ngroups = (a.nd + 31) >> 5;
-  const long long n_items = a.n_rays * ngroups;
+  const long long n_items = MULTI ? (a.n_rays + rpw - 1) / rpw : a.n_rays * ngroups;
   long long grid = (long long)sm_count * blocks_per_sm; // persistent: a whole number of CTAs per SM
   const long long need = (n_items + (kEgaBlock / 32) - 1) / (kEgaBlock / 32);
   if (grid > need) grid = need;
   if (grid < 1) grid = 1;
-  ega_fast_kernel<MASK><<<(unsigned)grid, kEgaBlock, smem, stream>>>(a);
+  ega_fast_kernel<MASK, MULTI><<<(unsigned)grid, kEgaBlock, smem, stream>>>(a);
   return cudaGetLastError();
+}
+
+template <int MASK>
+cudaError_t launch_ega_fast_t(const EgaArgs &a, cudaStream_t stream, int sm_count) {
+  return a.nd <= 16 ? launch_ega_fast_tm<MASK, true>(a, stream, sm_count) : launch_ega_fast_tm<MASK, false>(a, stream, sm_count);
 }
 
 // one translation unit per MASK

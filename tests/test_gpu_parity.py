@@ -293,3 +293,16 @@ def test_edge_shapes_no_gases_odd_channel_count_empty_packages(jr, oracle, gpu_c
         assert_parity(out[2], ref[1], f"ng0 b v{variant}")
     ctx.formod_batch([])  # empty batch is a no-op
     assert ctx.stats()["n_rays"] == 0
+
+
+@pytest.mark.parametrize("nd", [1, 2, 3, 5, 7, 11, 16, 17])
+def test_few_channels_pack_several_rays_per_warp(jr, oracle, gpu_ctx_factory, nd):
+    """nd <= 16: floor(32/nd) rays share a warp (lane = ray_in_warp*nd + channel); rays of different length, opaque rays,
+    rejected rays and a ray count that is not a multiple of the rays per warp"""
+    ctl = jr.Control(jr.synth.LIMB_GASES, 780.0 + 4.0 * np.arange(nd))
+    tbl = jr.synth.make_tables(ctl)
+    pkg = jr.synth.limb_package(ctl, n_profiles=2, rays_per_profile=23, dz=2.7, seed=nd)
+    pkg.q[0, :] *= 40.0          # some channels of the low rays go opaque
+    pkg.vpz[7] = 95.0            # rejected ray (np = 0) inside a warp
+    pkg.vpz[30] = -20.0          # ray into the ground
+    _both(gpu_ctx_factory, oracle, ctl, tbl, [pkg], f"nd{nd}")
