@@ -22,3 +22,7 @@ timing("D", ctl, tbl, [synth.limb_package(ctl, seed=20240517 + i) for i in range
 if os.environ.get("WITH_E", "1") == "1":
     ctl = synth.control_config_e(); tbl = synth.make_tables(ctl)
     timing("E", ctl, tbl, [synth.nadir_package(ctl, seed=20240518 + i) for i in range(8)])
+if os.environ.get("WITH_A", "0") == "1":
+    ctl = synth.control_limb_example(); tbl = synth.make_tables(ctl)
+    timing("A-like nd=2", ctl, tbl, [synth.limb_package(ctl, seed=20240517 + i) for i in range(32)])
+
