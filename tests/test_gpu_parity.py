@@ -306,3 +306,34 @@ def test_few_channels_pack_several_rays_per_warp(jr, oracle, gpu_ctx_factory, nd
     pkg.vpz[7] = 95.0            # rejected ray (np = 0) inside a warp
     pkg.vpz[30] = -20.0          # ray into the ground
     _both(gpu_ctx_factory, oracle, ctl, tbl, [pkg], f"nd{nd}")
+
+
+def test_random_geometries_and_descending_atmosphere(jr, oracle, gpu_ctx_factory):
+    """randomised rays: space-borne limb and nadir-slant views, observers inside the atmosphere looking up, down and
+    sideways; the same atmosphere stored bottom-up and top-down (the reference's `locate` handles both orders)"""
+    rng = np.random.default_rng(42)
+    ctl = jr.Control(["CO2", "H2O", "O3"], [700.0, 792.0, 1400.0, 2200.0])
+    tbl = jr.synth.make_tables(ctl)
+    n = 96
+    pkg = jr.synth.limb_package(ctl, n_profiles=1, rays_per_profile=n, seed=8)
+    kind = rng.integers(0, 4, n)
+    for r in range(n):
+        if kind[r] == 0:      # limb from orbit
+            pkg.obsz[r] = rng.uniform(300, 900); pkg.vpz[r] = rng.uniform(2, 80)
+            pkg.vplat[r] = np.degrees(np.arccos((jr.synth.RE + pkg.vpz[r]) / (jr.synth.RE + pkg.obsz[r])))
+        elif kind[r] == 1:    # nadir / slant from orbit to the ground
+            pkg.obsz[r] = rng.uniform(300, 900); pkg.vpz[r] = 0.0; pkg.vplat[r] = rng.uniform(-15, 15); pkg.vplon[r] = rng.uniform(-5, 5)
+        elif kind[r] == 2:    # aircraft / balloon looking up or sideways
+            pkg.obsz[r] = rng.uniform(8, 40); pkg.vpz[r] = rng.uniform(pkg.obsz[r] - 3, 85); pkg.vplat[r] = rng.uniform(0.2, 4)
+        else:                 # aircraft looking down
+            pkg.obsz[r] = rng.uniform(8, 40); pkg.vpz[r] = rng.uniform(0.0, pkg.obsz[r] - 1); pkg.vplat[r] = rng.uniform(0.0, 2)
+    pkg.k[0, :] = 1e-4 * np.exp(-pkg.z / 7.0)
+    flipped = copy.deepcopy(pkg)
+    for name in ("atm_time", "z", "lon", "lat", "p", "t"):
+        getattr(flipped, name)[:] = getattr(pkg, name)[::-1]
+    flipped.q[:, :] = pkg.q[:, ::-1]
+    flipped.k[:, :] = pkg.k[:, ::-1]
+    outs, ref = _both(gpu_ctx_factory, oracle, ctl, tbl, [pkg, flipped], "random geometry")
+    # bottom-up and top-down storage describe the same atmosphere
+    assert np.allclose(ref[0].rad, ref[1].rad, rtol=1e-9) and np.allclose(outs[1][0].rad, outs[1][1].rad, rtol=1e-9)
+    assert (ref[0].tau < 1).any() and (ref[0].rad > 0).any()
