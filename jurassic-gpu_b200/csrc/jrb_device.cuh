@@ -32,7 +32,7 @@ struct TblHeader {
   uint64_t nbytes;  // total blob size
   int32_t ng, nd, npmax, ntmax;
   int32_t all_shared; // 1: every gas has channel-independent (p,T) axes -> fast kernel allowed
-  int32_t monotone;   // 1: every column is non-decreasing in u and eps  -> hinted search == reference bisection
+  int32_t monotone;   // 1: every column is non-decreasing in u and eps; otherwise the offending columns carry kColNonMonotone
   int32_t max_nu;     // longest column (the specialised kernel packs bracket indices into 10 bits)
   int32_t gas_axes_same; // 1: all gases that have tables share one (p,T) grid -> one table cell per LOS segment
   // byte offsets from blob start
@@ -101,6 +101,9 @@ __host__ __device__ inline LosLayout make_los_layout(int ng, int nw, int fast, i
   return L;
 }
 enum LosTail { LT_Z = 0, LT_DSRAW = 1, LT_LEVEL = 2, LT_X = 3 };
+// column descriptor {first bracket, nu}: top bit of nu marks a column that is not monotone in u or eps; its lookups use the
+// reference's plain bisection over the whole column instead of the hinted search (whose equivalence needs sorted data)
+constexpr unsigned kColNonMonotone = 0x80000000u;
 constexpr unsigned kCellInvalid = 0xffffffffu; // "no usable table cell -> gas factor 1"
 
 // ---- math helpers ----------------------------------------------------------------------------------------------

@@ -116,6 +116,19 @@ __device__ __forceinline__ double column_finish(const float4 *__restrict__ col, 
   return clamp01(lerp_fast((double)b.x, (double)b.y, (double)b.z, (double)b.w, x));
 }
 
+// The same for a cell that contains a column which is not sorted in u or eps (flagged at pack time): the reference's
+// plain bisection over the whole column, out of line -- sorted columns give the same result either way.
+static __device__ __noinline__ double column_finish_bisect(const float4 *__restrict__ col, const int nu, const double eps,
+                                                           const double useg) {
+  int k = search_range(col, 0, nu - 1, round_down(eps), 1);
+  float4 b = col[k];
+  const double ustar = lerp_fast((double)b.y, (double)b.x, (double)b.w, (double)b.z, eps);
+  const double x = ustar + useg;
+  k = search_range(col, 0, nu - 1, round_down(x), 0);
+  b = col[k];
+  return clamp01(lerp_fast((double)b.x, (double)b.y, (double)b.z, (double)b.w, x));
+}
+
 // table cell of gas ig in the staged LOS record: ipr | it0 << 8 | it1 << 16, or kCellInvalid
 __device__ __forceinline__ unsigned load_cell(const double *__restrict__ R, const LosLayout &L, const int ig) {
   return (unsigned)__double_as_longlong(R[L.c0 + L.cstride * ig + 3]);
@@ -171,7 +184,10 @@ __host__ __device__ inline size_t ega_fast_smem_bytes(int ng, int rec, int threa
 // MULTI = false: one ray per warp, lane = channel of a 32-channel group (nd > 16).
 // MULTI = true : nd <= 16, floor(32/nd) rays per warp so that few-channel instruments (the reference's own examples have
 //                2 and 3 channels) do not leave 90 % of the lanes idle; every ray of the warp gets its own staged record.
-template <int MASK, bool MULTI>
+// ROBUST = true: the table set contains columns that are not sorted in u or eps (flagged kColNonMonotone at pack time);
+//                cells touching such a column are evaluated with the reference's plain bisection.  The ROBUST = false
+//                instantiation is used for fully sorted table sets and carries no trace of this.
+template <int MASK, bool MULTI, bool ROBUST>
 __global__ void __launch_bounds__(kEgaBlock, JRB_EGA_MINBLOCKS) ega_fast_kernel(const EgaArgs a) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, nwarps = blockDim.x >> 5;
@@ -301,22 +317,33 @@ __global__ void __launch_bounds__(kEgaBlock, JRB_EGA_MINBLOCKS) ega_fast_kernel(
         } else {
           f = 1.0;
           unsigned long long h = hint_s[ig * sstride];
-          if (h != ~0ull && cell != kCellInvalid && c00.y >= 2 && c01.y >= 2 && c10.y >= 2 && c11.y >= 2) {
+          const unsigned unsorted = ROBUST ? ((c00.y | c01.y | c10.y | c11.y) & kColNonMonotone) : 0u;
+          const unsigned nmask = ROBUST ? ~kColNonMonotone : ~0u;
+          const unsigned n00u = c00.y & nmask, n01u = c01.y & nmask, n10u = c10.y & nmask, n11u = c11.y & nmask;
+          if (h != ~0ull && cell != kCellInvalid && n00u >= 2 && n01u >= 2 && n10u >= 2 && n11u >= 2) {
             const unsigned ocell = (unsigned)(h >> 40);
             if (ocell != cell) h = fast::remap_hints(h, ocell, cell); // uniform per ray: the cell belongs to the ray
             const float4 *__restrict__ p00 = T.brk + c00.x, *__restrict__ p01 = T.brk + c01.x,
                                        *__restrict__ p10 = T.brk + c10.x, *__restrict__ p11 = T.brk + c11.x;
-            int k00 = min((int)(h & 0x3ffu), (int)c00.y - 2), k01 = min((int)((h >> 10) & 0x3ffu), (int)c01.y - 2),
-                k10 = min((int)((h >> 20) & 0x3ffu), (int)c10.y - 2), k11 = min((int)((h >> 30) & 0x3ffu), (int)c11.y - 2);
-            // the four hinted brackets are requested back to back: their latencies overlap
-            const float4 b00 = p00[k00], b01 = p01[k01], b10 = p10[k10], b11 = p11[k11];
+            int k00 = min((int)(h & 0x3ffu), (int)n00u - 2), k01 = min((int)((h >> 10) & 0x3ffu), (int)n01u - 2),
+                k10 = min((int)((h >> 20) & 0x3ffu), (int)n10u - 2), k11 = min((int)((h >> 30) & 0x3ffu), (int)n11u - 2);
             const double *__restrict__ cw = R + L.c0 + L.cstride * ig;
             const double eps = 1 - tp, useg = R[L.u0 + ig];
-            const float epsd = fast::round_down(eps);
-            const double e00 = fast::column_finish(p00, (int)c00.y, eps, epsd, useg, k00, b00);
-            const double e01 = fast::column_finish(p01, (int)c01.y, eps, epsd, useg, k01, b01);
-            const double e10 = fast::column_finish(p10, (int)c10.y, eps, epsd, useg, k10, b10);
-            const double e11 = fast::column_finish(p11, (int)c11.y, eps, epsd, useg, k11, b11);
+            double e00, e01, e10, e11;
+            if (!ROBUST || !unsorted) {
+              // the four hinted brackets are requested back to back: their latencies overlap
+              const float4 b00 = p00[k00], b01 = p01[k01], b10 = p10[k10], b11 = p11[k11];
+              const float epsd = fast::round_down(eps);
+              e00 = fast::column_finish(p00, (int)n00u, eps, epsd, useg, k00, b00);
+              e01 = fast::column_finish(p01, (int)n01u, eps, epsd, useg, k01, b01);
+              e10 = fast::column_finish(p10, (int)n10u, eps, epsd, useg, k10, b10);
+              e11 = fast::column_finish(p11, (int)n11u, eps, epsd, useg, k11, b11);
+            } else {
+              e00 = fast::column_finish_bisect(p00, (int)n00u, eps, useg); // (hints keep their old values)
+              e01 = fast::column_finish_bisect(p01, (int)n01u, eps, useg); // (hints keep their old values)
+              e10 = fast::column_finish_bisect(p10, (int)n10u, eps, useg); // (hints keep their old values)
+              e11 = fast::column_finish_bisect(p11, (int)n11u, eps, useg); // (hints keep their old values)
+            }
             hint_s[ig * sstride] = (unsigned long long)k00 | ((unsigned long long)k01 << 10) | ((unsigned long long)k10 << 20) |
                                    ((unsigned long long)k11 << 30) | ((unsigned long long)cell << 40);
             const double ep0 = clamp01(fma(cw[1], e01 - e00, e00));
@@ -343,14 +370,14 @@ __global__ void __launch_bounds__(kEgaBlock, JRB_EGA_MINBLOCKS) ega_fast_kernel(
   }
 }
 
-template <int MASK, bool MULTI>
+template <int MASK, bool MULTI, bool ROBUST>
 cudaError_t launch_ega_fast_tm(const EgaArgs &a, cudaStream_t stream, int sm_count) {
   const int rpw = MULTI ? ega_rays_per_warp(a.nd) : 1;
   const size_t smem = ega_fast_smem_bytes(a.ng, a.los.head, kEgaBlock, rpw);
-  cudaError_t e = cudaFuncSetAttribute(ega_fast_kernel<MASK, MULTI>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  cudaError_t e = cudaFuncSetAttribute(ega_fast_kernel<MASK, MULTI, ROBUST>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   if (e != cudaSuccess) return e;
   int blocks_per_sm = 0;
-  e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&blocks_per_sm, ega_fast_kernel<MASK, MULTI>, kEgaBlock, smem);
+  e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&blocks_per_sm, ega_fast_kernel<MASK, MULTI, ROBUST>, kEgaBlock, smem);
   if (e != cudaSuccess) return e;
   if (blocks_per_sm < 1) return cudaErrorInvalidConfiguration;
   const int ngroups = (a.nd + 31) >> 5;
@@ -359,13 +386,15 @@ cudaError_t launch_ega_fast_tm(const EgaArgs &a, cudaStream_t stream, int sm_cou
   const long long need = (n_items + (kEgaBlock / 32) - 1) / (kEgaBlock / 32);
   if (grid > need) grid = need;
   if (grid < 1) grid = 1;
-  ega_fast_kernel<MASK, MULTI><<<(unsigned)grid, kEgaBlock, smem, stream>>>(a);
+  ega_fast_kernel<MASK, MULTI, ROBUST><<<(unsigned)grid, kEgaBlock, smem, stream>>>(a);
   return cudaGetLastError();
 }
 
 template <int MASK>
 cudaError_t launch_ega_fast_t(const EgaArgs &a, cudaStream_t stream, int sm_count) {
-  return a.nd <= 16 ? launch_ega_fast_tm<MASK, true>(a, stream, sm_count) : launch_ega_fast_tm<MASK, false>(a, stream, sm_count);
+  if (a.unsorted_columns)
+    return a.nd <= 16 ? launch_ega_fast_tm<MASK, true, true>(a, stream, sm_count) : launch_ega_fast_tm<MASK, false, true>(a, stream, sm_count);
+  return a.nd <= 16 ? launch_ega_fast_tm<MASK, true, false>(a, stream, sm_count) : launch_ega_fast_tm<MASK, false, false>(a, stream, sm_count);
 }
 
 // one translation unit per MASK

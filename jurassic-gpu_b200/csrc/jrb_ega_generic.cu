@@ -1,7 +1,7 @@
 // jrb_ega_generic.cu -- reference-semantics EGA kernel: any number of gases, per-channel (p,T) axes, plain
 // bisections exactly as locate_id/locate_tbl_id (src/jr_common.h:106-125).  One thread per (ray, channel).
-// It is the fallback for table sets the specialised kernels do not accept (channel-dependent axes, non-monotone
-// columns, columns longer than 1023 entries, ng > 32) and doubles as an on-device cross-check of the specialised kernels.
+// It is the fallback for table sets the specialised kernels do not accept (channel-dependent axes, columns longer
+// than 1023 entries, ng > 32) and doubles as an on-device cross-check of the specialised kernels.
 #include "jrb_ega_common.cuh"
 #include <jurassic_b200.h>
 
@@ -13,7 +13,7 @@ struct Column { unsigned first, nu; };
 
 __device__ __forceinline__ Column load_col(const TblDev &T, int ig, int ip, int it, int id) {
   const uint2 c = T.col[(((size_t)ig * T.npmax + ip) * T.ntmax + it) * T.nd + id];
-  return Column{c.x, c.y};
+  return Column{c.x, c.y & ~kColNonMonotone};
 }
 
 // get_u (src/jr_common.h:179-185): column density giving emissivity `eps` in this column (may extrapolate)

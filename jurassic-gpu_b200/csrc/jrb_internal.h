@@ -39,6 +39,7 @@ struct EgaArgs {
   int ctm_mask;       // CO2*8 + H2O*4 + N2*2 + O2 (fourbit, src/CPUdrivers.c:130-134)
   int ig_co2, ig_h2o;
   int write_bbt;
+  int unsorted_columns; // the table set has columns flagged kColNonMonotone -> ROBUST kernel instantiation
   LosLayout los;
   const double *los_data;
   const int *ray_np;

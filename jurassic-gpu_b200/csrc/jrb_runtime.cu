@@ -448,7 +448,7 @@ int jrb_stage(jrb_context *ctx, int npk, const jrb_atm_view *atm, const jrb_obs_
   CU(ctx->d_level0.ensure((size_t)(R ? R : 1) * 4));
 
   // kernel choice + LOS buffer
-  const bool fast_ok = ctx->th.all_shared && ctx->th.monotone && ctx->th.max_nu <= 1023 && ega_fast_available(ng, ctx->ctm_mask);
+  const bool fast_ok = ctx->th.all_shared && ctx->th.max_nu <= 1023 && ega_fast_available(ng, ctx->ctm_mask);
   if (ctx->variant_req == 1 && !fast_ok)
     return ctx->fail(JRB_ERR_STATE, std::string("specialised kernel not applicable: shared_axes=") + std::to_string(ctx->th.all_shared) +
                      " monotone=" + std::to_string(ctx->th.monotone) + " max_nu=" + std::to_string(ctx->th.max_nu) + " ng=" + std::to_string(ng) + " mask=" + std::to_string(ctx->ctm_mask) +
@@ -550,6 +550,7 @@ int jrb_run_staged(jrb_context *ctx) {
     e.n_rays = r1 - r0; e.ng = ng; e.nd = nd; e.nw = nw;
     e.ctm_mask = ctx->ctm_mask; e.ig_co2 = ctx->ig_co2 >= 0 ? ctx->ig_co2 : 0; e.ig_h2o = ctx->ig_h2o >= 0 ? ctx->ig_h2o : 0;
     e.write_bbt = ctx->write_bbt;
+    e.unsorted_columns = ctx->th.monotone ? 0 : 1;
     e.los = ctx->los; e.los_data = los_buf;
     e.ray_np = (const int *)ctx->d_np.p + r0; e.ray_tsurf = (const double *)ctx->d_tsurf.p + r0;
     e.chan = (const double *)ctx->d_chan.p; e.window = (const int *)ctx->d_window.p;

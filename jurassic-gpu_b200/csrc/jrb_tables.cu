@@ -172,7 +172,11 @@ int pack_tables(const jrb_tbl_view &v, int ng, int nd, std::vector<unsigned char
             if (iu + 1 < nu) {
               const float u1 = v.u[srcn + d], e1 = v.eps[srcn + d];
               b[2] = u1; b[3] = e1;
-              if (!(u1 >= u0) || !(e1 >= e0)) monotone = 0;
+              if (!(u1 >= u0) || !(e1 >= e0)) { // the column is searched by full bisection on the device (flag = top bit of nu)
+                monotone = 0;
+#pragma omp atomic
+                o_col[2 * (cbase + d) + 1] |= kColNonMonotone;
+              }
             } else { b[2] = u0; b[3] = e0; }
           }
         }

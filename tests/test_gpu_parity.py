@@ -337,3 +337,23 @@ def test_random_geometries_and_descending_atmosphere(jr, oracle, gpu_ctx_factory
     # bottom-up and top-down storage describe the same atmosphere
     assert np.allclose(ref[0].rad, ref[1].rad, rtol=1e-9) and np.allclose(outs[1][0].rad, outs[1][1].rad, rtol=1e-9)
     assert (ref[0].tau < 1).any() and (ref[0].rad > 0).any()
+
+
+def test_non_monotone_columns_are_bisected_like_the_reference(jr, oracle, gpu_ctx_factory):
+    """a column that is not sorted in eps / u (possible after init_tbl's overwrite quirk, src/jurassic.c:369-384) is
+    flagged at pack time and searched with the reference's plain bisection; all other columns keep the hinted search"""
+    ctl = jr.synth.control_limb_example()
+    tbl = jr.synth.make_tables(ctl)
+    bad = copy.deepcopy(tbl)
+    for ip in range(8, 30):          # damage the columns the rays actually cross
+        for it in range(0, 12, 2):
+            n = bad.nu[0, ip, it, 0]
+            k = n // 2
+            bad.eps[0, ip, it, k, 0], bad.eps[0, ip, it, k + 1, 0] = bad.eps[0, ip, it, k + 1, 0], bad.eps[0, ip, it, k, 0]
+            bad.u[2, ip, it, k + 3, 1] = bad.u[2, ip, it, k + 1, 1]
+    info = jr.core.tables_pack_info(bad, ctl.ng, ctl.nd)
+    assert info["monotone"] == 0 and info["all_shared"] == 1
+    pkg = jr.synth.example_package("limb", ctl)
+    outs, ref = _both(gpu_ctx_factory, oracle, ctl, bad, [pkg], "non-monotone")
+    good = run_oracle(oracle, ctl, tbl, [pkg])[0]
+    assert not np.allclose(good.rad, ref[0].rad, rtol=1e-9)  # the damaged entries are really used
