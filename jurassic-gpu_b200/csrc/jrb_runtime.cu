@@ -456,15 +456,18 @@ int jrb_stage(jrb_context *ctx, int npk, const jrb_atm_view *atm, const jrb_obs_
   ctx->use_fast = (ctx->variant_req == 0) ? 0 : (fast_ok ? 1 : 0);
   ctx->los = make_los_layout(ng, nw, ctx->use_fast, ctx->th.gas_axes_same);
   const size_t per_ray = (size_t)kNLOS * ctx->los.rec * 8;
-  // LOS scratch: JRB_LOS_GB (default 24 GB), but never more than half of what is free on the device right now
+  // LOS scratch: JRB_LOS_GB (default 24 GB), but never more than half of what is free on the device.  The driver is only
+  // asked (cudaMemGetInfo takes a device-wide lock and was seen to stall for tens of ms) when the buffer has to grow.
   double los_gb = 24.0;
   if (const char *s = getenv("JRB_LOS_GB")) { double v = atof(s); if (v > 0.01) los_gb = v; }
-  {
+  if ((double)R * (double)per_ray > (double)ctx->d_los.cap) {
     size_t free_b = 0, total_b = 0;
     if (cudaMemGetInfo(&free_b, &total_b) == cudaSuccess) {
       const double avail = 0.5 * ((double)free_b + (double)ctx->d_los.cap) / 1e9;
       if (avail < los_gb) los_gb = avail;
     }
+  } else if ((double)ctx->d_los.cap / 1e9 < los_gb) {
+    los_gb = (double)ctx->d_los.cap / 1e9 + 1e-9; // the existing buffer is enough for the whole batch
   }
   // Chunking.  By default a batch is one chunk (or as many as the LOS scratch limit requires), run back to back.
   // JRB_PIPELINE=1 cuts large batches into ~8 chunks held in 3 rotating LOS buffers so that the (latency-bound, low
