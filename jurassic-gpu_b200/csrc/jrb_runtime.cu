@@ -61,7 +61,13 @@ inline int host_threads() {
   if (n == 0) {
     n = 8;
     if (const char *s = getenv("JRB_HOST_THREADS")) { int v = atoi(s); if (v > 0) n = v; }
-    else { int hw = (int)std::thread::hardware_concurrency(); if (hw > 0 && hw < n) n = hw; }
+    else {
+      int hw = (int)std::thread::hardware_concurrency();
+      // one process per GPU: share the cores with the other ranks of this node (torchrun exports LOCAL_WORLD_SIZE)
+      if (const char *w = getenv("LOCAL_WORLD_SIZE")) { int lw = atoi(w); if (lw > 1 && hw > 0) hw = hw / lw; }
+      if (hw > 0 && hw < n) n = hw;
+      if (n < 1) n = 1;
+    }
   }
   return n;
 }
