@@ -432,8 +432,12 @@ int jrb_stage(jrb_context *ctx, int npk, const jrb_atm_view *atm, const jrb_obs_
     for (int ir = 0; ir < o.nr; ir++) {
       hrpk[r0 + ir] = k;
       const double *row = o.rad + (size_t)ir * o.row_stride; // save_mask (src/jr_common.h:193-200)
-      for (int id = 0; id < nd; id++)
-        if (!std::isfinite(row[id])) masks[k].push_back({r0 + ir, id});
+      // a row is finite iff its sum of (x - x) is 0; only rows that fail this cheap test are inspected element-wise
+      double probe = 0.0;
+      for (int id = 0; id < nd; id++) probe += row[id] - row[id];
+      if (probe != 0.0 || probe != probe)
+        for (int id = 0; id < nd; id++)
+          if (!std::isfinite(row[id])) masks[k].push_back({r0 + ir, id});
     }
   }
   for (int k = 0; k < npk; k++) ctx->nan_mask.insert(ctx->nan_mask.end(), masks[k].begin(), masks[k].end());
@@ -621,11 +625,16 @@ int jrb_fetch_staged(jrb_context *ctx, int npk, const jrb_obs_view *obs) {
     std::memcpy(o.tpz, htp + 0 * R + r0, (size_t)nr * 8);
     std::memcpy(o.tplon, htp + 1 * R + r0, (size_t)nr * 8);
     std::memcpy(o.tplat, htp + 2 * R + r0, (size_t)nr * 8);
-    for (int ir = 0; ir < nr; ir++) {
-      double *rr = o.rad + (size_t)ir * o.row_stride, *tt = o.tau + (size_t)ir * o.row_stride;
-      std::memcpy(rr, hrad + (size_t)(r0 + ir) * nd, (size_t)nd * 8);
-      std::memcpy(tt, htau + (size_t)(r0 + ir) * nd, (size_t)nd * 8);
-      for (int id = nd; id < o.nd_reset; id++) { rr[id] = 0.0; tt[id] = 1.0; } // all ND columns are reset (src/CPUdrivers.c:58-60)
+    if (o.row_stride == nd) { // nd == ND: the package's rad / tau blocks are contiguous, one copy each
+      std::memcpy(o.rad, hrad + (size_t)r0 * nd, (size_t)nr * nd * 8);
+      std::memcpy(o.tau, htau + (size_t)r0 * nd, (size_t)nr * nd * 8);
+    } else {
+      for (int ir = 0; ir < nr; ir++) {
+        double *rr = o.rad + (size_t)ir * o.row_stride, *tt = o.tau + (size_t)ir * o.row_stride;
+        std::memcpy(rr, hrad + (size_t)(r0 + ir) * nd, (size_t)nd * 8);
+        std::memcpy(tt, htau + (size_t)(r0 + ir) * nd, (size_t)nd * 8);
+        for (int id = nd; id < o.nd_reset; id++) { rr[id] = 0.0; tt[id] = 1.0; } // all ND columns are reset (src/CPUdrivers.c:58-60)
+      }
     }
   }
   for (int k = 0; k < npk; k++)
