@@ -166,7 +166,10 @@ __device__ __forceinline__ unsigned long long remap_hints(const unsigned long lo
 
 } // namespace fast
 
-constexpr int kEgaBlock = 256;
+#ifndef JRB_EGA_BLOCK
+#define JRB_EGA_BLOCK 256
+#endif
+constexpr int kEgaBlock = JRB_EGA_BLOCK;
 #ifndef JRB_EGA_MINBLOCKS
 #define JRB_EGA_MINBLOCKS 3 // CTAs per SM the register allocation must allow (3 x 8 warps; measured best, see profiles/)
 #endif
