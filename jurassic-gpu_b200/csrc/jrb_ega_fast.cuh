@@ -110,10 +110,15 @@ __device__ __forceinline__ void relocate(const float4 *__restrict__ col, const i
 __device__ __forceinline__ double column_finish(const float4 *__restrict__ col, const int nu, const double eps, const float epsd,
                                                 const double useg, int &k, float4 b) {
   relocate<true>(col, nu, epsd, k, b);
-  const double ustar = lerp_fast((double)b.y, (double)b.x, (double)b.w, (double)b.z, eps);
-  const double x = ustar + useg;
-  relocate<false>(col, nu, round_down(x), k, b);
-  return clamp01(lerp_fast((double)b.x, (double)b.y, (double)b.z, (double)b.w, x));
+  // the bracket is widened to double once; the second stage reuses it unless the column-density lookup moves on
+  double u0 = (double)b.x, e0 = (double)b.y, u1 = (double)b.z, e1 = (double)b.w;
+  const double x = lerp_fast(e0, u0, e1, u1, eps) + useg;
+  const float xd = round_down(x);
+  if (b.x > xd || b.z <= xd) {
+    relocate<false>(col, nu, xd, k, b);
+    u0 = (double)b.x; e0 = (double)b.y; u1 = (double)b.z; e1 = (double)b.w;
+  }
+  return clamp01(lerp_fast(u0, e0, u1, e1, x));
 }
 
 // The same for a cell that contains a column which is not sorted in u or eps (flagged at pack time): the reference's
