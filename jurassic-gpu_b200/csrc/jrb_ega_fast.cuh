@@ -21,6 +21,7 @@
 // do not depend on the hints.
 #pragma once
 #include "jrb_ega_common.cuh"
+#include <cstdlib>
 
 namespace jrb {
 
@@ -388,6 +389,7 @@ cudaError_t launch_ega_fast_tm(const EgaArgs &a, cudaStream_t stream, int sm_cou
   e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&blocks_per_sm, ega_fast_kernel<MASK, MULTI, ROBUST>, kEgaBlock, smem);
   if (e != cudaSuccess) return e;
   if (blocks_per_sm < 1) return cudaErrorInvalidConfiguration;
+  if (const char *s = getenv("JRB_EGA_CTAS_PER_SM")) { const int v = atoi(s); if (v >= 1 && v < blocks_per_sm) blocks_per_sm = v; } // occupancy experiments
   const int ngroups = (a.nd + 31) >> 5;
   const long long n_items = MULTI ? (a.n_rays + rpw - 1) / rpw : a.n_rays * ngroups;
   long long grid = (long long)sm_count * blocks_per_sm; // persistent: a whole number of CTAs per SM
