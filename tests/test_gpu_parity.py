@@ -357,3 +357,25 @@ def test_non_monotone_columns_are_bisected_like_the_reference(jr, oracle, gpu_ct
     outs, ref = _both(gpu_ctx_factory, oracle, ctl, bad, [pkg], "non-monotone")
     good = run_oracle(oracle, ctl, tbl, [pkg])[0]
     assert not np.allclose(good.rad, ref[0].rad, rtol=1e-9)  # the damaged entries are really used
+
+
+def test_sharding_over_contexts_is_bit_identical(jr, gpu_ctx_factory):
+    """T8: contiguous package slices processed by separate contexts (= ranks, one per GPU in production) give exactly
+    the results of a single context processing everything; tables reach the second context as the packed blob"""
+    ctl = jr.synth.control_config_d(nd=8)
+    tbl = jr.synth.make_tables(ctl)
+    pkgs = [jr.synth.limb_package(ctl, n_profiles=2, rays_per_profile=32, seed=700 + i) for i in range(7)]
+    one = gpu_ctx_factory()
+    whole = run_cuda(one, ctl, tbl, pkgs, -1)
+    blob = jr.core.tables_pack_host(tbl, ctl.ng, ctl.nd)
+    got = []
+    for rank in range(3):
+        first, count = jr.shard.shard_range(len(pkgs), rank, 3)
+        ctx = gpu_ctx_factory()
+        ctx.set_control(ctl)
+        ctx.tables_upload_blob(blob)            # what a rank receives from the broadcast
+        part = [copy.deepcopy(p) for p in pkgs[first:first + count]]
+        ctx.formod_batch(part)
+        got += part
+    for a, b in zip(whole, got):
+        assert np.array_equal(a.rad, b.rad) and np.array_equal(a.tau, b.tau) and np.array_equal(a.tplat, b.tplat)
