@@ -136,6 +136,13 @@ const char *jrb_ingest_last_error(void);
 /* select kernel: -1 auto, 0 force generic, 1 force fast (fails if tables do not allow it) */
 int jrb_set_kernel_variant(jrb_context *ctx, int variant);
 
+/* Optional epilogue: field-of-view convolution.  With n > 0 every later run returns what the reference's
+ * formod(ctl,atm,obs); formod_fov(ctl,obs); (src/jurassic.c:214-258) returns: rad/tau of a ray become the w-weighted mean
+ * of the pencil-beam values interpolated in view-point altitude at vpz + dz[i] over the rays of the same package and time
+ * within +-NFOV(5) ray indices.  dz/w are the two columns of the ctl->fov shape file (n <= NSHAPE = 2048).  A ray with
+ * fewer than two such neighbours makes the run fail ("Cannot apply FOV convolution!").  n = 0 switches it off. */
+int jrb_set_fov(jrb_context *ctx, int n, const double *dz, const double *w);
+
 /* complete forward model for npk packages, host buffers in and out (H2D + kernels + D2H, synchronous) */
 int jrb_formod_batch(jrb_context *ctx, int npk, const jrb_atm_view *atm, const jrb_obs_view *obs);
 

@@ -11,6 +11,7 @@
  *                          (src/jurassic.h:151), far too few to occupy a B200
  *   jr_b200_kernel         replaces  kernel()                src/jurassic.c:812-857 (finite-difference Jacobian; the caller of
  *                          formod in retrievals): all perturbed forward models of a Jacobian are one device batch
+ *   jr_b200_formod_fov_batch  replaces  formod() + formod_fov()  src/jurassic.c:214-258 (FOV convolution as a device epilogue)
  *   jr_b200_finalize       new: releases what the reference never frees (src/GPUdrivers.cu:309)
  *
  * Error behaviour mirrors the reference: fatal conditions print a message and exit(EXIT_FAILURE) (ERRMSG,
@@ -46,6 +47,11 @@ void jr_b200_formod_batch(ctl_t const *ctl, atm_t *const atm[], obs_t *const obs
 void jr_b200_kernel(ctl_t const *ctl, atm_t *atm, obs_t *obs, double *k, size_t m, size_t n);
 /* n (return value) and m for the above */
 size_t jr_b200_kernel_dims(ctl_t const *ctl, atm_t *atm, obs_t const *obs, size_t *m_out);
+
+/* Per package what the reference's  formod(ctl, atm, obs); formod_fov(ctl, obs);  (src/jurassic.c:214-258) return: the
+ * forward model followed by the field-of-view convolution with the shape file ctl->fov ("-": no convolution), the
+ * convolution running on the device on the resident results.  formod_GPU itself ignores ctl->fov, like formod(). */
+void jr_b200_formod_fov_batch(ctl_t const *ctl, atm_t *const atm[], obs_t *const obs[], int npackages);
 
 void jr_b200_finalize(void);
 

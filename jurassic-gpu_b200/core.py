@@ -59,6 +59,7 @@ def load_core():
     lib.jrb_tables_alloc_blob.argtypes = [vp, C.c_size_t, C.POINTER(vp)]
     lib.jrb_tables_adopt_blob.argtypes = [vp]
     lib.jrb_set_kernel_variant.argtypes = [vp, C.c_int]
+    lib.jrb_set_fov.argtypes = [vp, C.c_int, abi.c_double_p, abi.c_double_p]
     lib.jrb_formod_batch.argtypes = [vp, C.c_int, C.POINTER(abi.AtmView), C.POINTER(abi.ObsView)]
     lib.jrb_stage.argtypes = [vp, C.c_int, C.POINTER(abi.AtmView), C.POINTER(abi.ObsView)]
     lib.jrb_run_staged.argtypes = [vp]
@@ -67,7 +68,7 @@ def load_core():
     lib.jrb_debug_los.argtypes = [vp, C.c_longlong, abi.c_double_p, C.c_int, abi.c_int_p, abi.c_int_p, abi.c_double_p]
     lib.jrb_get_stats.argtypes = [vp, C.POINTER(abi.Stats)]
     for f in ("jrb_create", "jrb_set_control", "jrb_set_tables", "jrb_tables_blob", "jrb_tables_alloc_blob",
-              "jrb_tables_adopt_blob", "jrb_set_kernel_variant", "jrb_formod_batch", "jrb_stage", "jrb_run_staged",
+              "jrb_tables_adopt_blob", "jrb_set_kernel_variant", "jrb_set_fov", "jrb_formod_batch", "jrb_stage", "jrb_run_staged",
               "jrb_fetch_staged", "jrb_staged_results", "jrb_debug_los", "jrb_get_stats"):
         getattr(lib, f).restype = C.c_int
     _lib = lib
@@ -77,7 +78,7 @@ def load_core():
 EXPORTED_SYMBOLS = ["jrb_tables_read_ascii", "jrb_host_tables_view", "jrb_host_tables_free", "jrb_ingest_last_error",
                     "jrb_tables_pack_host", "jrb_tables_upload_blob", "jrb_tables_pack_info", "jrb_version", "jrb_device_count", "jrb_create", "jrb_destroy", "jrb_last_error",
                     "jrb_set_control", "jrb_set_tables", "jrb_tables_blob", "jrb_tables_alloc_blob",
-                    "jrb_tables_adopt_blob", "jrb_set_kernel_variant", "jrb_formod_batch", "jrb_stage",
+                    "jrb_tables_adopt_blob", "jrb_set_kernel_variant", "jrb_set_fov", "jrb_formod_batch", "jrb_stage",
                     "jrb_run_staged", "jrb_fetch_staged", "jrb_staged_results", "jrb_debug_los", "jrb_get_stats"]
 
 
@@ -292,6 +293,15 @@ class Context:
 
     def set_kernel_variant(self, variant):
         self._check(self.lib.jrb_set_kernel_variant(self.h, variant), "jrb_set_kernel_variant")
+
+    def set_fov(self, dz=None, w=None):
+        """field-of-view epilogue (formod_fov, src/jurassic.c:214-258): shape offsets dz [km] and weights w; None = off"""
+        if dz is None or len(dz) == 0:
+            self._check(self.lib.jrb_set_fov(self.h, 0, None, None), "jrb_set_fov")
+            return
+        dz, w = np.ascontiguousarray(dz, dtype=np.float64), np.ascontiguousarray(w, dtype=np.float64)
+        assert dz.shape == w.shape and dz.ndim == 1
+        self._check(self.lib.jrb_set_fov(self.h, len(dz), _dp(dz), _dp(w)), "jrb_set_fov")
 
     def tables_blob(self):
         p, n = C.c_void_p(), C.c_size_t()

@@ -138,9 +138,38 @@ int jr_b200_init(ctl_t const *ctl, tbl_t const *tbl, int device) {
   return 0;
 }
 
+/* FOV shape file of ctl->fov, parsed like read_shape (src/jurassic.c:1134-1150); kept for the last file name seen */
+static void push_fov(ctl_t const *ctl, int enable) {
+  static char loaded[LEN] = "";
+  static double dz[NSHAPE], w[NSHAPE];
+  static int n = 0;
+  if (!enable || ctl->fov[0] == '-') { /* "-": do not take the FOV into account (src/jurassic.c:219) */
+    if (jrb_set_fov(g_ctx, 0, NULL, NULL) != JRB_OK) JR_FATAL(jrb_last_error(g_ctx));
+    return;
+  }
+  if (strncmp(loaded, ctl->fov, LEN) != 0) {
+    printf("Read shape function: %s\n", ctl->fov);
+    FILE *in = fopen(ctl->fov, "r");
+    if (!in) JR_FATAL("Cannot open file!");
+    char line[LEN];
+    n = 0;
+    while (fgets(line, LEN, in)) {
+      double a, b;
+      if (sscanf(line, "%lg %lg", &a, &b) == 2) {
+        if (n >= NSHAPE) JR_FATAL("Too many data points!");
+        dz[n] = a; w[n] = b; n++;
+      }
+    }
+    fclose(in);
+    if (n < 1) JR_FATAL("Could not read any data!");
+    strncpy(loaded, ctl->fov, LEN - 1);
+  }
+  if (jrb_set_fov(g_ctx, n, dz, w) != JRB_OK) JR_FATAL(jrb_last_error(g_ctx));
+}
+
 /* internal entry: exported names are reached through these statics so that a formod_GPU/… symbol of another library
  * in the global scope (e.g. the CPU-only stub of the reference, src/CPUdrivers.c:156-176) can never interpose them */
-static void formod_batch_impl(ctl_t const *ctl, atm_t *const atm[], obs_t *const obs[], int npackages) {
+static void formod_batch_impl(ctl_t const *ctl, atm_t *const atm[], obs_t *const obs[], int npackages, int fov) {
   if (ctl->checkmode) { printf("# %s: no operation in checkmode\n", __func__); return; }
   if (npackages <= 0) return;
   struct timespec ts0, ts1, ts2;
@@ -153,6 +182,7 @@ static void formod_batch_impl(ctl_t const *ctl, atm_t *const atm[], obs_t *const
   } else {
     push_control(ctl);
   }
+  push_fov(ctl, fov);
   jrb_atm_view *av = (jrb_atm_view *)malloc(sizeof(jrb_atm_view) * (size_t)npackages);
   jrb_obs_view *ov = (jrb_obs_view *)malloc(sizeof(jrb_obs_view) * (size_t)npackages);
   if (!av || !ov) JR_FATAL("Out of memory!");
@@ -169,13 +199,18 @@ static void formod_batch_impl(ctl_t const *ctl, atm_t *const atm[], obs_t *const
 }
 
 void jr_b200_formod_batch(ctl_t const *ctl, atm_t *const atm[], obs_t *const obs[], int npackages) {
-  formod_batch_impl(ctl, atm, obs, npackages);
+  formod_batch_impl(ctl, atm, obs, npackages, 0);
+}
+
+/* per package: formod(ctl, atm, obs); formod_fov(ctl, obs); with the convolution as a device epilogue */
+void jr_b200_formod_fov_batch(ctl_t const *ctl, atm_t *const atm[], obs_t *const obs[], int npackages) {
+  formod_batch_impl(ctl, atm, obs, npackages, 1);
 }
 
 static void formod_one_impl(ctl_t const *ctl, atm_t *atm, obs_t *obs) {
   atm_t *const a[1] = {atm};
   obs_t *const o[1] = {obs};
-  formod_batch_impl(ctl, a, o, 1);
+  formod_batch_impl(ctl, a, o, 1, 0);
 }
 
 void formod_GPU(ctl_t const *ctl, atm_t *atm, obs_t *obs) { formod_one_impl(ctl, atm, obs); }
@@ -272,6 +307,7 @@ void jr_b200_kernel(ctl_t const *ctl, atm_t *atm, obs_t *obs, double *k, size_t 
     }
     pthread_mutex_lock(&g_lock);
     push_control(ctl);
+    push_fov(ctl, 0);
     if (jrb_formod_batch(g_ctx, (int)nb, av, ov) != JRB_OK) JR_FATAL(jrb_last_error(g_ctx));
     pthread_mutex_unlock(&g_lock);
     for (size_t b = 0; b < nb; b++) { /* K[:, j] = (y1 - y0) / h over the finite radiances (obs2y order) */

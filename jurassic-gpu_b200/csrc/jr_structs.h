@@ -17,6 +17,7 @@
 #define NW 1     /* spectral windows   (:154) */
 #define LEN 5000 /* string length      (:157) */
 #define NLOS 400
+#define NSHAPE 2048 /* points of a shape file (:172) */
 #define TBLNP 40
 #define TBLNT 30
 #define TBLNU 304

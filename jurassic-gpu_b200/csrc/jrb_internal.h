@@ -51,6 +51,19 @@ struct EgaArgs {
   unsigned long long *work_counter; // dynamic work distribution (zeroed before launch)
 };
 
+struct FovArgs { // optional epilogue: field-of-view convolution (formod_fov, src/jurassic.c:214-258)
+  long long n_rays;
+  int nd, n_shape;
+  const double *dz, *w;        // [n_shape] FOV shape: altitude offsets [km] and weights
+  const int *ray_pkg;          // [n_rays]
+  const double *time, *vpz;    // [n_rays]
+  const double *rad_in, *tau_in; // [n_rays][nd] pencil-beam results
+  double *rad_out, *tau_out;
+  int *error;                  // bit 0: a ray with fewer than 2 rays of its own time in its +-NFOV window
+};
+cudaError_t launch_fov(const FovArgs &a, cudaStream_t stream);
+cudaError_t launch_nan_mask(double *rad, const long long *flat, long long n, cudaStream_t stream);
+
 // three launches: level slopes, ray stepping (thread per ray), LOS finalisation (thread per ray x segment)
 cudaError_t launch_raytrace(const TraceArgs &a, cudaStream_t stream, int *launches);
 cudaError_t launch_ega_generic(const EgaArgs &a, cudaStream_t stream);

@@ -97,6 +97,11 @@ struct jrb_context {
   TblDev td;
   int variant_req = -1;
 
+  // optional field-of-view epilogue (jrb_set_fov)
+  int fov_n = 0;
+  bool fov_applied = false; // of the last run: results are convolved and the NaN mask is already in them
+  DevBuf d_fov, d_fov_out, d_mask, d_flag;
+
   // staged batch
   bool staged = false, ran = false;
   int npk = 0;
@@ -184,6 +189,7 @@ void jrb_destroy(jrb_context *ctx) {
   ctx->d_chan.release(); ctx->d_window.release(); ctx->d_blob.release();
   ctx->d_in.release(); ctx->d_out.release(); ctx->d_los.release(); ctx->d_np.release(); ctx->d_tsurf.release();
   ctx->d_counter.release(); ctx->d_slope.release(); ctx->d_level0.release(); ctx->h_in.release(); ctx->h_out.release();
+  ctx->d_fov.release(); ctx->d_fov_out.release(); ctx->d_mask.release(); ctx->d_flag.release();
   cudaStreamDestroy(ctx->stream);
   if (ctx->s_trace) cudaStreamDestroy(ctx->s_trace);
   for (auto st : ctx->s_ega) if (st) cudaStreamDestroy(st);
@@ -328,6 +334,22 @@ int jrb_set_kernel_variant(jrb_context *ctx, int variant) {
   std::lock_guard<std::mutex> lk(ctx->mtx);
   ctx->variant_req = variant;
   ctx->staged = false;
+  return JRB_OK;
+}
+
+// FOV shape (what read_shape returns for ctl->fov, src/jurassic.c:222): n = 0 switches the epilogue off
+int jrb_set_fov(jrb_context *ctx, int n, const double *dz, const double *w) {
+  if (!ctx || n < 0 || (n > 0 && (!dz || !w))) return JRB_ERR_ARG;
+  std::lock_guard<std::mutex> lk(ctx->mtx);
+  if (n > 2048) return ctx->fail(JRB_ERR_LIMIT, "Too many data points!"); // NSHAPE (src/jurassic.h:172, src/jurassic.c:1143)
+  CU(cudaSetDevice(ctx->device));
+  if (n > 0) {
+    CU(ctx->d_fov.ensure((size_t)2 * n * 8));
+    CU(cudaMemcpyAsync(ctx->d_fov.p, dz, (size_t)n * 8, cudaMemcpyHostToDevice, ctx->stream));
+    CU(cudaMemcpyAsync((double *)ctx->d_fov.p + n, w, (size_t)n * 8, cudaMemcpyHostToDevice, ctx->stream));
+    CU(cudaStreamSynchronize(ctx->stream));
+  }
+  ctx->fov_n = n;
   return JRB_OK;
 }
 
@@ -581,8 +603,40 @@ int jrb_run_staged(jrb_context *ctx) {
     CU(cudaStreamWaitEvent(ctx->stream, EV(nchunks - 1, 3), 0));
     if (nchunks > 1) CU(cudaStreamWaitEvent(ctx->stream, EV(nchunks - 2, 3), 0));
   }
+  ctx->fov_applied = false;
+  if (ctx->fov_n > 0 && R > 0) { // formod(); formod_fov(); of the reference: mask first, then convolve
+    const size_t n_out = (size_t)R * nd;
+    CU(ctx->d_fov_out.ensure(2 * n_out * 8));
+    CU(ctx->d_flag.ensure(256));
+    CU(cudaMemsetAsync(ctx->d_flag.p, 0, 4, ctx->stream));
+    if (!ctx->nan_mask.empty()) {
+      std::vector<long long> flat(ctx->nan_mask.size());
+      for (size_t i = 0; i < flat.size(); i++) flat[i] = ctx->nan_mask[i].first * nd + ctx->nan_mask[i].second;
+      CU(ctx->d_mask.ensure(flat.size() * 8));
+      CU(cudaMemcpyAsync(ctx->d_mask.p, flat.data(), flat.size() * 8, cudaMemcpyHostToDevice, ctx->stream));
+      CU(cudaStreamSynchronize(ctx->stream)); // flat is a local
+      CU(launch_nan_mask(ctx->o_rad, (const long long *)ctx->d_mask.p, (long long)flat.size(), ctx->stream));
+      launches++;
+    }
+    FovArgs f;
+    f.n_rays = R; f.nd = nd; f.n_shape = ctx->fov_n;
+    f.dz = (const double *)ctx->d_fov.p; f.w = f.dz + ctx->fov_n;
+    f.ray_pkg = ctx->ray_pkg; f.time = ctx->geo + 6 * R; f.vpz = ctx->geo + 3 * R;
+    f.rad_in = ctx->o_rad; f.tau_in = ctx->o_tau;
+    f.rad_out = (double *)ctx->d_fov_out.p; f.tau_out = f.rad_out + n_out;
+    f.error = (int *)ctx->d_flag.p;
+    CU(launch_fov(f, ctx->stream));
+    launches++;
+    CU(cudaMemcpyAsync(ctx->o_rad, f.rad_out, 2 * n_out * 8, cudaMemcpyDeviceToDevice, ctx->stream)); // o_tau follows o_rad
+    ctx->fov_applied = true;
+  }
   CU(cudaEventRecord(ctx->events[1], ctx->stream));
   CU(cudaStreamSynchronize(ctx->stream));
+  if (ctx->fov_applied) {
+    int flag = 0;
+    CU(cudaMemcpy(&flag, ctx->d_flag.p, 4, cudaMemcpyDeviceToHost));
+    if (flag) return ctx->fail(JRB_ERR_ARG, "Cannot apply FOV convolution!"); // src/jurassic.c:236
+  }
   float ms_rt = 0, ms_ega = 0, ms_tot = 0, ms;
   for (long long c = 0; c < nchunks; c++) {
     CU(cudaEventElapsedTime(&ms, EV(c, 0), EV(c, 1))); ms_rt += ms;
@@ -615,7 +669,8 @@ int jrb_fetch_staged(jrb_context *ctx, int npk, const jrb_obs_view *obs) {
   const double t_d2h1 = now_ms();
   double *hrad = (double *)ctx->h_out.p, *htau = hrad + (size_t)R * nd, *htp = htau + (size_t)R * nd;
   const double nan = std::nan("");
-  for (auto &m : ctx->nan_mask) hrad[(size_t)m.first * nd + m.second] = nan; // apply_mask (src/jr_common.h:203-210)
+  if (!ctx->fov_applied) // (with the FOV epilogue the mask went in on the device, before the convolution)
+    for (auto &m : ctx->nan_mask) hrad[(size_t)m.first * nd + m.second] = nan; // apply_mask (src/jr_common.h:203-210)
 #pragma omp parallel for schedule(dynamic, 4) num_threads(host_threads())
   for (int k = 0; k < npk; k++) {
     const jrb_obs_view &o = obs[k];

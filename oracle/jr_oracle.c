@@ -454,6 +454,44 @@ int jro_traceray(const jrb_ctl_view *c, const jrb_atm_view *a, const jrb_obs_vie
   return np;
 }
 
+/* formod_fov (src/jurassic.c:214-258) for one package, applied to the results already in obs (i.e. what a caller gets
+ * from formod(); formod_fov();).  n, dz, w: the shape file as read_shape returns it.  -1: "Cannot apply FOV convolution!" */
+int jro_formod_fov(const jrb_obs_view *o, int nd, int n, const double *dz, const double *w) {
+  enum { NFOV = 5 }; /* src/jurassic.h:175 */
+  const int nr = o->nr;
+  double *rad0 = (double *)malloc(sizeof(double) * (size_t)(nr ? nr : 1) * nd * 2), *tau0 = rad0 + (size_t)nr * nd;
+  for (int ir = 0; ir < nr; ir++) /* copy_obs (:224) */
+    for (int id = 0; id < nd; id++) {
+      rad0[(size_t)ir * nd + id] = o->rad[(size_t)ir * o->row_stride + id];
+      tau0[(size_t)ir * nd + id] = o->tau[(size_t)ir * o->row_stride + id];
+    }
+  int rc = 0;
+  for (int ir = 0; ir < nr && rc == 0; ir++) {
+    double z[2 * NFOV + 1];
+    int src[2 * NFOV + 1], nz = 0;
+    for (int ir2 = (ir - NFOV > 0 ? ir - NFOV : 0); ir2 < (ir + 1 + NFOV < nr ? ir + 1 + NFOV : nr); ir2++) /* :227-235 */
+      if (o->time[ir2] == o->time[ir]) { z[nz] = o->vpz[ir2]; src[nz] = ir2; nz++; }
+    if (nz < 2) { rc = -1; break; } /* :236 */
+    double *rr = o->rad + (size_t)ir * o->row_stride, *tt = o->tau + (size_t)ir * o->row_stride;
+    double wsum = 0;
+    for (int id = 0; id < nd; id++) { rr[id] = 0; tt[id] = 0; }
+    for (int i = 0; i < n; i++) { /* :243-251 */
+      const double zfov = o->vpz[ir] + dz[i];
+      const int k = o_locate(z, nz, zfov);
+      for (int id = 0; id < nd; id++) {
+        const double r0 = rad0[(size_t)src[k] * nd + id], r1 = rad0[(size_t)src[k + 1] * nd + id];
+        const double t0 = tau0[(size_t)src[k] * nd + id], t1 = tau0[(size_t)src[k + 1] * nd + id];
+        rr[id] += w[i] * (r0 + (zfov - z[k]) * (r1 - r0) / (z[k + 1] - z[k])); /* LIN, src/jurassic.h:81 */
+        tt[id] += w[i] * (t0 + (zfov - z[k]) * (t1 - t0) / (z[k + 1] - z[k]));
+      }
+      wsum += w[i];
+    }
+    for (int id = 0; id < nd; id++) { rr[id] /= wsum; tt[id] /= wsum; } /* :253-256 */
+  }
+  free(rad0);
+  return rc;
+}
+
 int jro_max_threads(void) {
 #ifdef _OPENMP
   extern int omp_get_max_threads(void);

@@ -9,6 +9,8 @@ extern "C" {
 int jro_formod(const jrb_ctl_view *ctl, const jrb_tbl_view *tbl, const jrb_atm_view *atm, const jrb_obs_view *obs);
 /* ray tracer only; flattened LOS, see jr_oracle.c */
 int jro_traceray(const jrb_ctl_view *ctl, const jrb_atm_view *atm, const jrb_obs_view *obs, int ir, double *out, double *tsurf);
+/* formod_fov (src/jurassic.c:214-258) applied in place to the rad/tau already in obs; shape = (dz[n], w[n]) */
+int jro_formod_fov(const jrb_obs_view *obs, int nd, int n, const double *dz, const double *w);
 int jro_max_threads(void);
 #ifdef __cplusplus
 }

@@ -34,6 +34,8 @@ class Oracle:
                                      abi.c_double_p, abi.c_double_p]
         lib.jro_traceray.restype = C.c_int
         lib.jro_max_threads.restype = C.c_int
+        lib.jro_formod_fov.argtypes = [C.POINTER(abi.ObsView), C.c_int, C.c_int, abi.c_double_p, abi.c_double_p]
+        lib.jro_formod_fov.restype = C.c_int
         self.lib = lib
 
     def formod(self, ctl, tbl, pkg):
@@ -41,6 +43,12 @@ class Oracle:
         rc = self.lib.jro_formod(C.byref(cv), C.byref(tv), C.byref(av), C.byref(ov))
         if rc != 0:
             raise RuntimeError("jro_formod failed")
+
+    def formod_fov(self, pkg, dz, w):
+        """field-of-view convolution of the results held in pkg, in place; False if the reference would abort"""
+        ov = pkg.obs_view()
+        dz, w = np.ascontiguousarray(dz, dtype=np.float64), np.ascontiguousarray(w, dtype=np.float64)
+        return self.lib.jro_formod_fov(C.byref(ov), pkg.nd, len(dz), _dp(dz), _dp(w)) == 0
 
     def traceray(self, ctl, pkg, ir):
         """-> (los[np][6+nw+2ng] = z,lon,lat,p,t,ds,k..,q..,u.., tsurf); also updates pkg.tp*."""
@@ -91,6 +99,8 @@ class Reference:
         lib.jrref_kernel_dims.argtypes = [vp, vp, vp, C.POINTER(C.c_size_t)]
         lib.jrref_kernel_dims.restype = C.c_size_t
         lib.jrref_kernel.argtypes = [vp, vp, vp, abi.c_double_p, C.c_size_t, C.c_size_t]
+        lib.formod_fov.argtypes = [vp, vp]  # the reference's own public symbol (src/jurassic.c:214)
+        lib.formod_fov.restype = None
         self.lib = lib
 
     # ---- ABI facts ----
@@ -194,6 +204,10 @@ class Reference:
         ts = C.c_double()
         n = self.lib.jrref_traceray(C.addressof(c), C.addressof(a), C.addressof(o), ir, _dp(buf), C.byref(ts))
         return buf[: n * stride].reshape(n, stride).copy(), ts.value
+
+    def formod_fov(self, c, o):
+        """the reference's FOV convolution; NOTE it caches the shape file of the first call for the life of the process"""
+        self.lib.formod_fov(C.addressof(c), C.addressof(o))
 
     def kernel(self, c, a, o):
         """the reference's finite-difference Jacobian kernel() (tables via get_tbl, i.e. from ctl.tblbase files)"""

@@ -205,3 +205,50 @@ def test_batched_jacobian_matches_reference_kernel(jr, refdrv, tmp_path):
     assert np.all(np.abs(k - k_ref) <= 1e-5 * np.abs(k_ref) + 1e-7 * scale), float(np.max(np.abs(k - k_ref) / (scale + 1e-300)))
     assert np.count_nonzero(k_ref) > 300  # the Jacobian is sparse: a ray only sees levels above its tangent point
     lib.jr_b200_finalize()
+
+
+def test_formod_fov_batch_matches_reference(jr, refdrv, oracle):
+    """Row f3: jr_b200_formod_fov_batch == the reference's formod(); formod_fov(); per package (shape file ctl->fov);
+    formod_GPU itself keeps ignoring ctl->fov like the reference's formod()"""
+    from test_oracle_vs_reference import FOV_SHAPE, fov_cases
+    ND, NG = 2, 5
+    ctl = jr.synth.control_limb_example()
+    tbl = jr.synth.make_tables(ctl)
+    shape = jr.synth.read_tab(FOV_SHAPE)
+    pkgs = [p for _, p in fov_cases(jr, ctl)]
+    io = StructIO(jr, refdrv, ND, NG)
+    lib = _load_dropin(jr, ND, NG)
+    lib.jr_b200_formod_fov_batch.argtypes = [C.c_void_p, C.POINTER(C.c_void_p), C.POINTER(C.c_void_p), C.c_int]
+    c = io.r.make_ctl(ctl, useGPU=1)
+    c.fov = FOV_SHAPE.encode()
+    t, keep = _tbl_struct(io, tbl)
+    assert lib.jr_b200_init(C.addressof(c), C.addressof(t), 0) == 0
+    atms = [io.r.make_atm(p) for p in pkgs]
+    obss = [io.r.make_obs(p) for p in pkgs]
+    ap = (C.c_void_p * len(pkgs))(*[C.addressof(x) for x in atms])
+    op = (C.c_void_p * len(pkgs))(*[C.addressof(x) for x in obss])
+    lib.jr_b200_formod_fov_batch(C.addressof(c), ap, op, len(pkgs))
+    plain = run_oracle(oracle, ctl, tbl, pkgs)
+    want = copy.deepcopy(plain)
+    for i, p in enumerate(pkgs):
+        assert oracle.formod_fov(want[i], shape[:, 0], shape[:, 1])
+        mine = copy.deepcopy(p)
+        io.r.read_obs(obss[i], mine)
+        assert_parity(mine, want[i], f"fov batch {i}")
+        if refdrv.reference_available(ND, NG):   # and the reference itself, same structs
+            ref = refdrv.Reference(ND, NG)
+            c0, a0, o0 = ref.make_ctl(ctl), ref.make_atm(p), ref.make_obs(p)
+            c0.fov = FOV_SHAPE.encode()
+            tp = ref.make_tbl(tbl)
+            ref.formod_tbl(c0, a0, o0, tp)
+            ref.formod_fov(c0, o0)
+            r = copy.deepcopy(p)
+            ref.read_obs(o0, r)
+            ref.free_tbl(tp)
+            assert_parity(mine, r, f"fov batch {i} vs reference")
+        single = io.r.make_obs(p)                # plain entry point: no convolution although ctl->fov is set
+        lib.formod_GPU(C.addressof(c), C.addressof(atms[i]), C.addressof(single))
+        m0 = copy.deepcopy(p)
+        io.r.read_obs(single, m0)
+        assert_parity(m0, plain[i], f"formod_GPU ignores fov {i}")
+    lib.jr_b200_finalize()

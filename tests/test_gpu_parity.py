@@ -379,3 +379,51 @@ def test_sharding_over_contexts_is_bit_identical(jr, gpu_ctx_factory):
         got += part
     for a, b in zip(whole, got):
         assert np.array_equal(a.rad, b.rad) and np.array_equal(a.tau, b.tau) and np.array_equal(a.tplat, b.tplat)
+
+
+# ---- row f3: field-of-view convolution as a device epilogue ---------------------------------------------------------
+def _fov_shape(jr):
+    s = jr.synth.read_tab(os.path.join(ROOT, "tests", "golden", "fov_shape.tab"))
+    return s[:, 0].copy(), s[:, 1].copy()
+
+
+def test_fov_epilogue_matches_oracle(jr, oracle, gpu_ctx_factory):
+    """jrb_set_fov: results == formod(); formod_fov(); of the reference (pinned bit for bit by the CPU test
+    test_oracle_fov_matches_reference_formod_fov); ascending and descending scans, windows limited to the own package and
+    time, NaN mask applied before the convolution; several packages per batch"""
+    from test_oracle_vs_reference import fov_cases
+    ctl = jr.synth.control_limb_example()
+    tbl = jr.synth.make_tables(ctl)
+    dz, w = _fov_shape(jr)
+    pkgs = [p for _, p in fov_cases(jr, ctl)] + [jr.synth.limb_package(ctl, n_profiles=1, rays_per_profile=2, z0=20.0, seed=3)]
+    ref = run_oracle(oracle, ctl, tbl, pkgs)
+    plain = copy.deepcopy(ref)
+    for r in ref:
+        assert oracle.formod_fov(r, dz, w)
+    ctx = gpu_ctx_factory()
+    for variant in (1, 0):
+        ctx.set_control(ctl)
+        ctx.set_tables(tbl)
+        ctx.set_kernel_variant(variant)
+        ctx.set_fov(dz, w)
+        mine = [copy.deepcopy(p) for p in pkgs]
+        ctx.formod_batch(mine)
+        for m, r in zip(mine, ref):
+            assert_parity(m, r, f"fov variant {variant}")
+        assert np.isnan(mine[1].rad).sum() > 1  # the masked measurement spreads to its neighbours, as in the reference
+        ctx.set_fov(None)                       # and off again: pencil-beam results
+        mine = [copy.deepcopy(p) for p in pkgs]
+        ctx.formod_batch(mine)
+        for m, r in zip(mine, plain):
+            assert_parity(m, r, f"fov off variant {variant}")
+
+
+def test_fov_epilogue_fails_like_the_reference_on_single_ray_scans(jr, gpu_ctx_factory):
+    ctl = jr.synth.control_limb_example()
+    ctx = gpu_ctx_factory()
+    ctx.set_control(ctl)
+    ctx.set_tables(jr.synth.make_tables(ctl))
+    ctx.set_fov([0.0, 0.5], [1.0, 0.5])
+    with pytest.raises(jr.core.JrbError, match="Cannot apply FOV convolution"):
+        ctx.formod_batch([jr.synth.limb_package(ctl, n_profiles=2, rays_per_profile=1, seed=5)])
+    ctx.set_fov(None)

@@ -176,3 +176,51 @@ def test_oracle_traceray_equals_reference(jr, oracle, refdrv):
             los_o, ts_o = oracle.traceray(ctl, copy.deepcopy(pkg), ir)
             assert los_r.shape == los_o.shape and ts_r == ts_o
             assert np.array_equal(los_r, los_o)
+
+
+# ---- 3. field-of-view convolution -----------------------------------------------------------------
+FOV_SHAPE = os.path.join(ROOT, "tests", "golden", "fov_shape.tab")
+
+
+def fov_cases(jr, ctl):
+    """packages exercising formod_fov: the limb example (one scan, ascending), and three scans in one package run top-down
+    (descending view-point altitudes, windows that reach into the neighbouring scan) with one masked measurement"""
+    a = jr.synth.example_package("limb", ctl)
+    b = jr.synth.limb_package(ctl, n_profiles=3, rays_per_profile=9, z0=8.0, dz=1.5, seed=91)
+    for name in ("time", "obsz", "obslon", "obslat", "vpz", "vplon", "vplat"):
+        getattr(b, name)[:] = getattr(b, name)[::-1].copy()
+    b.rad[4, 1] = np.nan
+    return [("limb example", a), ("descending scans + mask", b)]
+
+
+def test_oracle_fov_matches_reference_formod_fov(jr, oracle, refdrv):
+    """jro_formod_fov == the reference's formod_fov (src/jurassic.c:214-258) applied after formod(), bit for bit"""
+    _need(refdrv, 2, 5)
+    ctl = jr.synth.control_limb_example()
+    tbl = jr.synth.make_tables(ctl)
+    shape = jr.synth.read_tab(FOV_SHAPE)
+    ref = refdrv.Reference(2, 5)
+    tp = ref.make_tbl(tbl)
+    for what, pkg in fov_cases(jr, ctl):
+        c, a, o = ref.make_ctl(ctl), ref.make_atm(pkg), ref.make_obs(pkg)
+        c.fov = FOV_SHAPE.encode()
+        ref.formod_tbl(c, a, o, tp)
+        plain = copy.deepcopy(pkg)
+        ref.read_obs(o, plain)
+        ref.formod_fov(c, o)
+        want = copy.deepcopy(pkg)
+        ref.read_obs(o, want)
+        mine = copy.deepcopy(pkg)
+        oracle.formod(ctl, tbl, mine)
+        assert oracle.formod_fov(mine, shape[:, 0], shape[:, 1])
+        _same(mine.rad, want.rad, f"{what}: rad")
+        _same(mine.tau, want.tau, f"{what}: tau")
+        ok = ~np.isnan(want.rad) & ~np.isnan(plain.rad)
+        assert np.any(np.abs(want.rad[ok] - plain.rad[ok]) > 1e-3 * np.abs(plain.rad[ok])), "the convolution must change something"
+    ref.free_tbl(tp)
+
+
+def test_oracle_fov_needs_two_rays_per_scan(jr, oracle):
+    ctl = jr.synth.control_limb_example()
+    pkg = jr.synth.limb_package(ctl, n_profiles=2, rays_per_profile=1, seed=5)
+    assert not oracle.formod_fov(pkg, [0.0], [1.0])
