@@ -133,6 +133,20 @@ int jrb_host_tables_view(const jrb_host_tables *t, jrb_tbl_view *view, int *n_mi
 void jrb_host_tables_free(jrb_host_tables *t);
 const char *jrb_ingest_last_error(void);
 
+/* The reference's binary table cache (src/jr_binary_tables_io.h:12-290; read/written by init_tbl when READ_BINARY /
+ * WRITE_BINARY are set, src/jurassic.c:312-320, 669-671): a 16 KiB text header naming the writer's compile-time extents,
+ * followed by its raw tbl_t.  Host only.  The reader maps the file instead of loading it (only the populated entries are
+ * ever touched, by the packer) and accepts files of ANY extents that contain the requested gases and channels at the
+ * same indices; the writer produces the file a reference build with the extents dim_g = NG, dim_p = TBLNP, dim_t = TBLNT,
+ * dim_u = TBLNU, dim_d = ND would write (sparse where empty).
+ * jrb_binary_tables_filename: the reference's naming convention "bin.jurassic-fp32-tables-g<NG>-p..-T..-u..-d<ND>". */
+int jrb_binary_tables_filename(char *out, size_t cap, int dim_g, int dim_p, int dim_t, int dim_u, int dim_d);
+size_t jrb_binary_tables_size(int dim_g, int dim_p, int dim_t, int dim_u, int dim_d); /* header + sizeof(tbl_t) */
+int jrb_tables_read_binary(const char *filename, int ng, const char *const *emitters, int nd, const double *nu,
+                           jrb_host_tables **out);
+int jrb_tables_write_binary(const char *filename, const jrb_tbl_view *tbl, int ng, const char *const *emitters, int nd,
+                            const double *nu, int dim_g, int dim_p, int dim_t, int dim_u, int dim_d);
+
 /* select kernel: -1 auto, 0 force generic, 1 force fast (fails if tables do not allow it) */
 int jrb_set_kernel_variant(jrb_context *ctx, int variant);
 

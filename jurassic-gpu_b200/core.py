@@ -55,6 +55,14 @@ def load_core():
     lib.jrb_host_tables_free.argtypes = [vp]
     lib.jrb_host_tables_free.restype = None
     lib.jrb_ingest_last_error.restype = C.c_char_p
+    lib.jrb_binary_tables_filename.argtypes = [C.c_char_p, C.c_size_t] + [C.c_int] * 5
+    lib.jrb_binary_tables_size.argtypes = [C.c_int] * 5
+    lib.jrb_binary_tables_size.restype = C.c_size_t
+    lib.jrb_tables_read_binary.argtypes = [C.c_char_p, C.c_int, C.POINTER(C.c_char_p), C.c_int, abi.c_double_p, C.POINTER(vp)]
+    lib.jrb_tables_read_binary.restype = C.c_int
+    lib.jrb_tables_write_binary.argtypes = [C.c_char_p, C.POINTER(abi.TblView), C.c_int, C.POINTER(C.c_char_p), C.c_int,
+                                            abi.c_double_p] + [C.c_int] * 5
+    lib.jrb_tables_write_binary.restype = C.c_int
     lib.jrb_tables_blob.argtypes = [vp, C.POINTER(vp), C.POINTER(C.c_size_t)]
     lib.jrb_tables_alloc_blob.argtypes = [vp, C.c_size_t, C.POINTER(vp)]
     lib.jrb_tables_adopt_blob.argtypes = [vp]
@@ -75,7 +83,8 @@ def load_core():
     return lib
 
 
-EXPORTED_SYMBOLS = ["jrb_tables_read_ascii", "jrb_host_tables_view", "jrb_host_tables_free", "jrb_ingest_last_error",
+EXPORTED_SYMBOLS = ["jrb_binary_tables_filename", "jrb_binary_tables_size", "jrb_tables_read_binary", "jrb_tables_write_binary",
+                    "jrb_tables_read_ascii", "jrb_host_tables_view", "jrb_host_tables_free", "jrb_ingest_last_error",
                     "jrb_tables_pack_host", "jrb_tables_upload_blob", "jrb_tables_pack_info", "jrb_version", "jrb_device_count", "jrb_create", "jrb_destroy", "jrb_last_error",
                     "jrb_set_control", "jrb_set_tables", "jrb_tables_blob", "jrb_tables_alloc_blob",
                     "jrb_tables_adopt_blob", "jrb_set_kernel_variant", "jrb_set_fov", "jrb_formod_batch", "jrb_stage",
@@ -116,6 +125,84 @@ def read_ascii_tables(ctl, tblbase):
     lib.jrb_host_tables_free(h)
     t.n_missing = miss.value
     return t
+
+
+class HostTables:
+    """Tables held by the core library (here: the mapped binary cache file).  Has .view() like Tables, so it can be
+    handed to Context.set_tables / tables_pack_host / tables_pack_info without copying the (up to 8.8 GB) arrays."""
+
+    def __init__(self, handle, lib):
+        self.h, self.lib = handle, lib
+
+    def view(self):
+        v = abi.TblView()
+        self.lib.jrb_host_tables_view(self.h, C.byref(v), None)
+        return v
+
+    @property
+    def extents(self):
+        v = self.view()
+        return dict(NG=v.dim_g, TBLNP=v.dim_p, TBLNT=v.dim_t, TBLNU=v.dim_u, ND=v.dim_d)
+
+    def compact(self, ng, nd):
+        """copy of the populated part as a Tables container"""
+        v = self.view()
+        G, P, T, U, D = v.dim_g, v.dim_p, v.dim_t, v.dim_u, v.dim_d
+        arr = lambda name, shape: np.ctypeslib.as_array(getattr(v, name), shape=shape)
+        n_p = arr("np", (G, D))[:ng, :nd]
+        mp = max(int(n_p.max(initial=0)), 1)
+        n_t = arr("nt", (G, P, D))[:ng, :mp, :nd]
+        mt = max(int(n_t.max(initial=0)), 1)
+        n_u = arr("nu", (G, P, T, D))[:ng, :mp, :mt, :nd]
+        mu = max(int(n_u.max(initial=0)), 1)
+        t = Tables(max(ng, 1), nd, mp, mt, mu)
+        t.np[:ng], t.nt[:ng], t.nu[:ng] = n_p, n_t, n_u
+        t.p[:ng] = arr("p", (G, P, D))[:ng, :mp, :nd]
+        t.t[:ng] = arr("t", (G, P, T, D))[:ng, :mp, :mt, :nd]
+        t.u[:ng] = arr("u", (G, P, T, U, D))[:ng, :mp, :mt, :mu, :nd]
+        t.eps[:ng] = arr("eps", (G, P, T, U, D))[:ng, :mp, :mt, :mu, :nd]
+        t.sr[...] = arr("sr", (abi.TBLNS, D))[:, :nd]
+        t.st[...] = arr("st", (abi.TBLNS,))
+        return t
+
+    def close(self):
+        if self.h:
+            self.lib.jrb_host_tables_free(self.h)
+            self.h = None
+
+    def __del__(self):
+        self.close()
+
+
+def binary_tables_filename(NG, ND, TBLNP=abi.TBLNP, TBLNT=abi.TBLNT, TBLNU=abi.TBLNU):
+    """the reference's name of the binary cache for a build with these extents (src/jr_binary_tables_io.h:12-16)"""
+    buf = C.create_string_buffer(256)
+    if load_core().jrb_binary_tables_filename(buf, 256, NG, TBLNP, TBLNT, TBLNU, ND) != 0:
+        raise JrbError("jrb_binary_tables_filename failed")
+    return buf.value.decode()
+
+
+def read_binary_tables(ctl, filename):
+    """Map the reference's binary table cache -> HostTables (host only).  Raises if the header does not hold ctl's gases
+    and channels at the same indices (rules of jr_binary_tables_check_header, src/jr_binary_tables_io.h:65-211)."""
+    lib = load_core()
+    names = (C.c_char_p * max(ctl.ng, 1))(*[e.encode() for e in ctl.emitters])
+    h = C.c_void_p()
+    rc = lib.jrb_tables_read_binary(os.fspath(filename).encode(), ctl.ng, names, ctl.nd, _dp(ctl.nu), C.byref(h))
+    if rc != 0:
+        raise JrbError(f"jrb_tables_read_binary failed ({rc}): {lib.jrb_ingest_last_error().decode()}")
+    return HostTables(h, lib)
+
+
+def write_binary_tables(filename, tbl, ctl, NG, ND, TBLNP=abi.TBLNP, TBLNT=abi.TBLNT, TBLNU=abi.TBLNU):
+    """Write `tbl` as the binary cache file of a reference build with the given compile-time extents (sparse file)."""
+    lib = load_core()
+    names = (C.c_char_p * max(ctl.ng, 1))(*[e.encode() for e in ctl.emitters])
+    v = tbl.view()
+    rc = lib.jrb_tables_write_binary(os.fspath(filename).encode(), C.byref(v), ctl.ng, names, ctl.nd, _dp(ctl.nu), NG, TBLNP, TBLNT,
+                                     TBLNU, ND)
+    if rc != 0:
+        raise JrbError(f"jrb_tables_write_binary failed ({rc}): {lib.jrb_ingest_last_error().decode()}")
 
 
 def tables_pack_host(tbl, ng, nd):

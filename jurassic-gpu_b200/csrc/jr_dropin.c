@@ -104,18 +104,38 @@ static void init_locked(ctl_t const *ctl, tbl_t const *tbl, int device) {
   g_have_tables = 1;
 }
 
-/* tables straight from the ASCII .tab/.filt files below ctl->tblbase, without the reference's init_tbl / 8.8 GB tbl_t */
+/* tables straight from the files init_tbl would use (src/jurassic.c:311-416, 612-672), without its 8.8 GB tbl_t: the binary
+ * cache "bin.jurassic-fp32-tables-g<NG>-..." in the working directory when ctl->read_binary is set (mapped, not loaded;
+ * fatal if it fails and READ_BINARY > 0), else the ASCII .tab/.filt files below ctl->tblbase, after which the cache is
+ * written when ctl->write_binary is set */
 int jr_b200_init_from_files(ctl_t const *ctl, int device) {
   if (!ctl) JR_FATAL("jr_b200_init_from_files: NULL argument");
   char const *names[NG > 0 ? NG : 1];
   for (int ig = 0; ig < ctl->ng; ig++) names[ig] = ctl->emitter[ig];
+  char binname[256];
+  jrb_binary_tables_filename(binname, sizeof(binname), NG, TBLNP, TBLNT, TBLNU, ND);
   jrb_host_tables *ht = NULL;
-  if (jrb_tables_read_ascii(ctl->tblbase, ctl->ng, names, ctl->nd, ctl->nu, TBLNP, TBLNT, TBLNU, &ht) != JRB_OK)
-    JR_FATAL(jrb_ingest_last_error());
   jrb_tbl_view tv;
   int missing = 0;
-  jrb_host_tables_view(ht, &tv, &missing);
-  if (missing > 0) printf("Warning! %d files were not found!\n", missing); /* like init_tbl (src/jurassic.c:424-427) */
+  if (ctl->read_binary) {
+    if (jrb_tables_read_binary(binname, ctl->ng, names, ctl->nd, ctl->nu, &ht) == JRB_OK) {
+      printf("matching binary tables file found\n");
+    } else {
+      printf("# %s\n", jrb_ingest_last_error());
+      if (ctl->read_binary > 0) JR_FATAL("Failed to read binary file while READ_BINARY > 0");
+    }
+  }
+  if (!ht) {
+    if (jrb_tables_read_ascii(ctl->tblbase, ctl->ng, names, ctl->nd, ctl->nu, TBLNP, TBLNT, TBLNU, &ht) != JRB_OK)
+      JR_FATAL(jrb_ingest_last_error());
+    jrb_host_tables_view(ht, &tv, &missing);
+    if (missing > 0) printf("Warning! %d files were not found!\n", missing); /* like init_tbl (src/jurassic.c:424-427) */
+    if (ctl->write_binary) {
+      int const status = jrb_tables_write_binary(binname, &tv, ctl->ng, names, ctl->nd, ctl->nu, NG, TBLNP, TBLNT, TBLNU, ND);
+      printf("# jr_write_binary_tables returns status %d\n", status);
+    }
+  }
+  jrb_host_tables_view(ht, &tv, NULL);
   pthread_mutex_lock(&g_lock);
   if (!g_ctx) {
     if (device < 0) device = ctl->MPIlocalrank;
