@@ -63,8 +63,9 @@ class Oracle:
         return self.lib.jro_max_threads()
 
 
-def ref_lib_path(ND, NG):
-    return os.path.join(_HERE, "_ref", f"libjurassic_ref_nd{ND}_ng{NG}.so")
+def ref_lib_path(ND, NG, gpu=False):
+    """gpu=True: the build that also holds the reference's own CUDA path (GPUdrivers.cu for sm_100a, `make refgpu`)"""
+    return os.path.join(_HERE, "_ref", f"libjurassic_ref{'gpu' if gpu else ''}_nd{ND}_ng{NG}.so")
 
 
 def reference_available(ND, NG):
@@ -74,8 +75,8 @@ def reference_available(ND, NG):
 class Reference:
     """The unmodified reference CPU path for one compile-time dimension set."""
 
-    def __init__(self, ND, NG, rtld_global=False):
-        path = ref_lib_path(ND, NG)
+    def __init__(self, ND, NG, rtld_global=False, gpu=False):
+        path = ref_lib_path(ND, NG, gpu)
         if not os.path.exists(path):
             raise RuntimeError(f"{path} missing: run `make -C oracle ref` where /root/reference exists")
         self.ND, self.NG = ND, NG
