@@ -53,10 +53,12 @@ __device__ __forceinline__ double continuum_beta_ds(const int mask, const double
 
 // Band-averaged Planck radiance at temperature t (src_planck_core, src/jr_common.h:220-224): the source axis is
 // st[it] = 100 + 0.25 it, so the index is (int)(4t) - 400 (locate_st, :82-84) and the divisor of the linear
-// interpolation is exactly 0.25.
+// interpolation is exactly 0.25.  The reference indexes without a bounds check (valid for 100 <= t < 400 K, outside it
+// reads whatever lies next to the array); here the index is clipped to the table, i.e. temperatures outside the source
+// table extrapolate its first / last interval -- identical inside the range, defined (and no stray access) outside.
 __device__ __forceinline__ double planck_source(const double *__restrict__ sr, const int nd, const int id,
                                                 const double t) {
-  const int it = (int)(4 * t) - 400;
+  const int it = min(max((int)(4 * t) - 400, 0), kTBLNS - 2);
   const double st = 100.0 + 0.25 * it;
   const double y0 = sr[(size_t)it * nd + id], y1 = sr[(size_t)(it + 1) * nd + id];
   return y0 + (t - st) * (y1 - y0) * 4.0;

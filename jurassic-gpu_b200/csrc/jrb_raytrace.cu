@@ -137,7 +137,9 @@ __global__ void __launch_bounds__(128) ray_step_kernel(TraceArgs a) {
     zmin = fmin(zmin, P.z[i]);
   }
 
-  const bool rejected = (obsz < zmin) || (vpz > zmax - 0.001);
+  // (a ray whose time selects fewer than two levels -- no profile matches -- is undefined behaviour in the reference,
+  //  src/jr_common.h:640; here it is rejected like a ray that misses the atmosphere: np = 0, rad = 0, tau = 1)
+  const bool rejected = (obsz < zmin) || (vpz > zmax - 0.001) || (P.n < 2);
   int z_low_idx = -1;
   if (!rejected) {
     double xobs[3], xvp[3], ex0[3], x[3];

@@ -427,3 +427,32 @@ def test_fov_epilogue_fails_like_the_reference_on_single_ray_scans(jr, gpu_ctx_f
     with pytest.raises(jr.core.JrbError, match="Cannot apply FOV convolution"):
         ctx.formod_batch([jr.synth.limb_package(ctl, n_profiles=2, rays_per_profile=1, seed=5)])
     ctx.set_fov(None)
+
+
+def test_inputs_outside_the_reference_domain_stay_defined(jr, oracle, gpu_ctx_factory):
+    """Two inputs that are undefined behaviour in the reference (out-of-bounds reads) must
+    neither disturb the device nor other rays: temperatures outside the 100..400 K source table (here: the Planck index is
+    clipped, the edge interval extrapolates) and rays whose time matches no profile (here: rejected, rad = 0, tau = 1)."""
+    ctl = jr.synth.control_limb_example()
+    tbl = jr.synth.make_tables(ctl)
+    good = jr.synth.limb_package(ctl, n_profiles=2, rays_per_profile=8, z0=10.0, dz=4.0, seed=11)
+    hot = copy.deepcopy(good)
+    hot.t[:] += 250.0                      # 450..550 K
+    cold = copy.deepcopy(good)
+    cold.t[:] = 60.0
+    lost = copy.deepcopy(good)
+    lost.time[3] = 17.0                    # later than every profile
+    lost.time[12] = -5.0                   # earlier than every profile
+    ctx = gpu_ctx_factory()
+    ref = run_oracle(oracle, ctl, tbl, [good])[0]
+    for variant in (1, 0):
+        out = run_cuda(ctx, ctl, tbl, [hot, good, cold, lost], variant)
+        assert_parity(out[1], ref, f"neighbour of out-of-domain packages, variant {variant}")
+        for o in (out[0], out[2]):
+            assert np.all(np.isfinite(o.rad)) and np.all(np.isfinite(o.tau)) and np.all((o.tau >= 0) & (o.tau <= 1))
+        assert np.all(out[3].rad[3] == 0.0) and np.all(out[3].tau[3] == 1.0)
+        keep = np.ones(good.n_rays, bool)
+        keep[[3, 12]] = False
+        if not np.all(out[3].rad[12] == 0.0):  # a time before the first profile selects it (locate_atm, src/jr_common.h:127-154)
+            keep[12] = True
+        assert np.allclose(out[3].rad[keep], ref.rad[keep], rtol=1e-6, atol=0)
