@@ -58,3 +58,20 @@ def test_reference_cli_linked_against_dropin(jr, tmp_path):
     assert np.all(np.abs(gpu[:, 8] - cpu[:, 8]) < 1e-6)  # tangent longitude: round-off level values of atan2
     same = open(os.path.join(str(tmp_path), "rad_cpu.tab")).read() == open(os.path.join(str(tmp_path), "rad_gpu.tab")).read()
     print("rad.tab byte-identical:", same)
+
+
+@pytest.mark.gpu
+def test_reference_cli_benchmark_mode_reports_no_deviations(jr, tmp_path):
+    """T6 in full: formod.c built with the reference's -DBENCHMARK_FORMOD and linked against the drop-in repeats the forward
+    model USEGPU^2 times and compares every rad/tau of the repeats with the first call bit for bit (src/formod.c:71-176)"""
+    exe = os.path.join(ROOT, "oracle", "_ref", "formod_b200bench_nd2_ng5")
+    if not os.path.exists(exe):
+        pytest.skip("oracle/_ref/formod_b200bench_nd2_ng5 not built (needs /root/reference at build time)")
+    _case(jr, str(tmp_path))
+    env = dict(os.environ, OMP_NUM_THREADS="2")
+    r = subprocess.run([exe, "limb.ctl", "obs.tab", "atm.tab", "rad_bench.tab", "USEGPU", "3"], cwd=str(tmp_path), env=env,
+                       capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
+    assert "for 66 rays times 2 channels shows no deviations" in r.stdout, r.stdout[-2000:]
+    assert "# ran 9 iterations for benchmark" in r.stdout
+    assert "formod took" in r.stdout and "on the GPU" in r.stdout
