@@ -101,7 +101,7 @@ int jrb_tables_read_ascii(const char *tblbase, int ng, const char *const *emitte
   if (max_u <= 0) max_u = 304;
   *out = nullptr;
   std::vector<PairTable> pairs((size_t)ng * nd);
-#pragma omp parallel for schedule(dynamic, 1)
+#pragma omp parallel for schedule(dynamic, 1) num_threads(host_threads())
   for (int k = 0; k < ng * nd; k++) {
     const int ig = k / nd, id = k % nd;
     char fn[6000];
@@ -146,7 +146,7 @@ int jrb_tables_read_ascii(const char *tblbase, int ng, const char *const *emitte
   T->st.resize(kTBLNS); T->sr.assign((size_t)kTBLNS * D, 0.0);
   for (int it = 0; it < kTBLNS; it++) T->st[it] = 100.0 + ((double)it - 0.0) * (400.0 - 100.0) / ((kTBLNS - 1.0) - 0.0);
   int bad = 0;
-#pragma omp parallel for schedule(dynamic, 1)
+#pragma omp parallel for schedule(dynamic, 1) num_threads(host_threads())
   for (int id = 0; id < nd; id++) {
     char fn[6000];
     std::snprintf(fn, sizeof(fn), "%s_%.4f.filt", tblbase, nu[id]);

@@ -54,24 +54,6 @@ inline double now_ms() {
   return std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now().time_since_epoch()).count();
 }
 
-// host threads for packing / scattering packages.  Launchers such as torchrun export OMP_NUM_THREADS=1, which would
-// serialise the host side of the end-to-end path, so the count is taken from JRB_HOST_THREADS or the hardware.
-inline int host_threads() {
-  static int n = 0;
-  if (n == 0) {
-    n = 8;
-    if (const char *s = getenv("JRB_HOST_THREADS")) { int v = atoi(s); if (v > 0) n = v; }
-    else {
-      int hw = (int)std::thread::hardware_concurrency();
-      // one process per GPU: share the cores with the other ranks of this node (torchrun exports LOCAL_WORLD_SIZE)
-      if (const char *w = getenv("LOCAL_WORLD_SIZE")) { int lw = atoi(w); if (lw > 1 && hw > 0) hw = hw / lw; }
-      if (hw > 0 && hw < n) n = hw;
-      if (n < 1) n = 1;
-    }
-  }
-  return n;
-}
-
 } // namespace
 
 struct jrb_context {

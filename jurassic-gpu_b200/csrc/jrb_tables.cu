@@ -153,7 +153,7 @@ int pack_tables(const jrb_tbl_view &v, int ng, int nd, std::vector<unsigned char
 
   // --- brackets: read tbl_t with the channel innermost (its contiguous direction), write per-column runs ---
   int monotone = 1;
-#pragma omp parallel for collapse(2) schedule(dynamic, 4) reduction(&& : monotone)
+#pragma omp parallel for collapse(2) schedule(dynamic, 4) reduction(&& : monotone) num_threads(host_threads())
   for (int g = 0; g < ng; g++)
     for (int ip = 0; ip < npmax; ip++)
       for (int it = 0; it < ntmax; it++) {
