@@ -456,3 +456,30 @@ def test_inputs_outside_the_reference_domain_stay_defined(jr, oracle, gpu_ctx_fa
         if not np.all(out[3].rad[12] == 0.0):  # a time before the first profile selects it (locate_atm, src/jr_common.h:127-154)
             keep[12] = True
         assert np.allclose(out[3].rad[keep], ref.rad[keep], rtol=1e-6, atol=0)
+
+
+def test_full_baseline_size_in_one_call(jr, gpu_ctx_factory):
+    """BASELINE.json's full Config-D size in ONE call: 920 packages = 1 000 960 rays x 32 channels (the LOS scratch
+    limit forces several chunks).  Size-independent properties: the 8 copies of each of 115 distinct packages, scattered
+    over the batch, come back bit-identical (checksum of checksums), tau in [0,1], rad finite and >= 0, every ray traced."""
+    ctl = jr.synth.control_config_d()
+    tbl = jr.synth.make_tables(ctl)
+    base = [jr.synth.limb_package(ctl, seed=20240517 + i) for i in range(115)]
+    order = np.random.default_rng(7).permutation(920)
+    pkgs = [copy.deepcopy(base[j % 115]) for j in order]
+    ctx = gpu_ctx_factory()
+    ctx.set_control(ctl)
+    ctx.set_tables(tbl)
+    ctx.formod_batch(pkgs)
+    st = ctx.stats()
+    assert st["n_rays"] == 1000960 and st["n_ray_channels"] == 1000960 * 32 and st["ega_kernel_variant"] == 1
+    assert st["n_chunks"] >= 2
+    assert st["n_los_points"] > 250 * 1000960           # mean LOS length of the recipe is 257 (SURVEY.md 8d)
+    sums = {}
+    for j, p in zip(order, pkgs):
+        key = (p.rad.tobytes(), p.tau.tobytes(), p.tpz.tobytes())
+        sums.setdefault(j % 115, set()).add(hash(key))
+    assert len(sums) == 115 and all(len(s) == 1 for s in sums.values())
+    assert len({next(iter(s)) for s in sums.values()}) == 115   # and distinct packages give distinct results
+    for p in pkgs[::37]:
+        assert np.all(np.isfinite(p.rad)) and np.all(p.rad >= 0) and np.all((p.tau >= 0) & (p.tau <= 1))
