@@ -80,26 +80,28 @@ __device__ __forceinline__ float hi_of(const float4 b) { return ON_EPS ? b.w : b
 // tangent point add several grid steps at once) jump by the distance estimated from the local grid ratio -- the u axes
 // of JURASSIC tables are geometric -- and whatever is still not bracketed goes to the out-of-line bisection.
 template <bool ON_EPS>
-__device__ __forceinline__ void relocate(const float4 *__restrict__ col, const int nu, const float xd, int &k, float4 &b) {
+__device__ __forceinline__ void relocate(const float4 *__restrict__ brk, const unsigned first, const int nu, const float xd, int &k,
+                                         float4 &b) {
+  // brackets are addressed as brk[first + k] with a 32-bit index: one IMAD.WIDE per load instead of a 64-bit pointer chain
   if (lo_of<ON_EPS>(b) > xd) { // x < val[k]
     if (k > 0) {
-      --k; b = col[k];
-      if (k > 0 && lo_of<ON_EPS>(b) > xd) { k = search_range(col, 0, k, xd, ON_EPS); b = col[k]; }
+      --k; b = brk[first + (unsigned)k];
+      if (k > 0 && lo_of<ON_EPS>(b) > xd) { k = search_range(brk + first, 0, k, xd, ON_EPS); b = brk[first + (unsigned)k]; }
     }
   } else if (hi_of<ON_EPS>(b) <= xd) { // x >= val[k+1]
     if (k < nu - 2) {
-      ++k; b = col[k];
+      ++k; b = brk[first + (unsigned)k];
       if (k < nu - 2 && hi_of<ON_EPS>(b) <= xd) {
         if (!ON_EPS) {
           const float l0 = __log2f(b.x), r = __log2f(b.z) - l0;
           const float d = (r > 0.f) ? fminf((__log2f(xd) - l0) * __frcp_rn(r), 65535.f) : 1.f;
           const int k0 = k;
           k = min(k0 + max((int)d, 1), nu - 2);
-          b = col[k];
-          if (b.x > xd) { k = search_range(col, k0, k, xd, 0); b = col[k]; }
-          else if (k < nu - 2 && b.z <= xd) { k = search_range(col, k, nu - 1, xd, 0); b = col[k]; }
+          b = brk[first + (unsigned)k];
+          if (b.x > xd) { k = search_range(brk + first, k0, k, xd, 0); b = brk[first + (unsigned)k]; }
+          else if (k < nu - 2 && b.z <= xd) { k = search_range(brk + first, k, nu - 1, xd, 0); b = brk[first + (unsigned)k]; }
         } else {
-          k = search_range(col, k, nu - 1, xd, 1); b = col[k];
+          k = search_range(brk + first, k, nu - 1, xd, 1); b = brk[first + (unsigned)k];
         }
       }
     }
@@ -108,15 +110,15 @@ __device__ __forceinline__ void relocate(const float4 *__restrict__ col, const i
 
 // One table column of the EGA step, starting from the prefetched bracket (k, b):
 // u* = u(eps) (get_u, may extrapolate), then eps(u* + u_seg) clamped to [0,1] (get_eps + c01, src/jr_common.h:249-257).
-__device__ __forceinline__ double column_finish(const float4 *__restrict__ col, const int nu, const double eps, const float epsd,
-                                                const double useg, int &k, float4 b) {
-  relocate<true>(col, nu, epsd, k, b);
+__device__ __forceinline__ double column_finish(const float4 *__restrict__ brk, const unsigned first, const int nu, const double eps,
+                                                const float epsd, const double useg, int &k, float4 b) {
+  relocate<true>(brk, first, nu, epsd, k, b);
   // the bracket is widened to double once; the second stage reuses it unless the column-density lookup moves on
   double u0 = (double)b.x, e0 = (double)b.y, u1 = (double)b.z, e1 = (double)b.w;
   const double x = lerp_fast(e0, u0, e1, u1, eps) + useg;
   const float xd = round_down(x);
   if (b.x > xd || b.z <= xd) {
-    relocate<false>(col, nu, xd, k, b);
+    relocate<false>(brk, first, nu, xd, k, b);
     u0 = (double)b.x; e0 = (double)b.y; u1 = (double)b.z; e1 = (double)b.w;
   }
   return clamp01(lerp_fast(u0, e0, u1, e1, x));
@@ -332,8 +334,7 @@ __global__ void __launch_bounds__(kEgaBlock, JRB_EGA_MINBLOCKS) ega_fast_kernel(
           if (h != ~0ull && cell != kCellInvalid && n00u >= 2 && n01u >= 2 && n10u >= 2 && n11u >= 2) {
             const unsigned ocell = (unsigned)(h >> 40);
             if (ocell != cell) h = fast::remap_hints(h, ocell, cell); // uniform per ray: the cell belongs to the ray
-            const float4 *__restrict__ p00 = T.brk + c00.x, *__restrict__ p01 = T.brk + c01.x,
-                                       *__restrict__ p10 = T.brk + c10.x, *__restrict__ p11 = T.brk + c11.x;
+            const float4 *__restrict__ brk = T.brk;
             int k00 = min((int)(h & 0x3ffu), (int)n00u - 2), k01 = min((int)((h >> 10) & 0x3ffu), (int)n01u - 2),
                 k10 = min((int)((h >> 20) & 0x3ffu), (int)n10u - 2), k11 = min((int)((h >> 30) & 0x3ffu), (int)n11u - 2);
             const double *__restrict__ cw = R + L.c0 + L.cstride * ig;
@@ -341,17 +342,18 @@ __global__ void __launch_bounds__(kEgaBlock, JRB_EGA_MINBLOCKS) ega_fast_kernel(
             double e00, e01, e10, e11;
             if (!ROBUST || !unsorted) {
               // the four hinted brackets are requested back to back: their latencies overlap
-              const float4 b00 = p00[k00], b01 = p01[k01], b10 = p10[k10], b11 = p11[k11];
+              const float4 b00 = brk[c00.x + (unsigned)k00], b01 = brk[c01.x + (unsigned)k01], b10 = brk[c10.x + (unsigned)k10],
+                           b11 = brk[c11.x + (unsigned)k11];
               const float epsd = fast::round_down(eps);
-              e00 = fast::column_finish(p00, (int)n00u, eps, epsd, useg, k00, b00);
-              e01 = fast::column_finish(p01, (int)n01u, eps, epsd, useg, k01, b01);
-              e10 = fast::column_finish(p10, (int)n10u, eps, epsd, useg, k10, b10);
-              e11 = fast::column_finish(p11, (int)n11u, eps, epsd, useg, k11, b11);
+              e00 = fast::column_finish(brk, c00.x, (int)n00u, eps, epsd, useg, k00, b00);
+              e01 = fast::column_finish(brk, c01.x, (int)n01u, eps, epsd, useg, k01, b01);
+              e10 = fast::column_finish(brk, c10.x, (int)n10u, eps, epsd, useg, k10, b10);
+              e11 = fast::column_finish(brk, c11.x, (int)n11u, eps, epsd, useg, k11, b11);
             } else {
-              e00 = fast::column_finish_bisect(p00, (int)n00u, eps, useg); // (hints keep their old values)
-              e01 = fast::column_finish_bisect(p01, (int)n01u, eps, useg); // (hints keep their old values)
-              e10 = fast::column_finish_bisect(p10, (int)n10u, eps, useg); // (hints keep their old values)
-              e11 = fast::column_finish_bisect(p11, (int)n11u, eps, useg); // (hints keep their old values)
+              e00 = fast::column_finish_bisect(brk + c00.x, (int)n00u, eps, useg); // (hints keep their old values)
+              e01 = fast::column_finish_bisect(brk + c01.x, (int)n01u, eps, useg);
+              e10 = fast::column_finish_bisect(brk + c10.x, (int)n10u, eps, useg);
+              e11 = fast::column_finish_bisect(brk + c11.x, (int)n11u, eps, useg);
             }
             hint_s[ig * sstride] = (unsigned long long)k00 | ((unsigned long long)k01 << 10) | ((unsigned long long)k10 << 20) |
                                    ((unsigned long long)k11 << 30) | ((unsigned long long)cell << 40);
