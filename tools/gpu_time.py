@@ -7,7 +7,12 @@ jr = importlib.import_module("jurassic-gpu_b200")
 synth = jr.synth
 
 def timing(name, ctl, tbl, pkgs, reps=3):
-    ctx = jr.Context(0); ctx.set_control(ctl); ctx.set_tables(tbl); ctx.set_kernel_variant(1); ctx.stage(pkgs)
+    ctx = jr.Context(0); ctx.set_control(ctl); ctx.set_tables(tbl); ctx.set_kernel_variant(1)
+    if os.environ.get("FOV", "0") == "1":  # field-of-view epilogue with the 13-point test shape
+        import numpy as np
+        shape = np.loadtxt(os.path.join(ROOT, "tests", "golden", "fov_shape.tab"))
+        ctx.set_fov(shape[:, 0], shape[:, 1])
+    ctx.stage(pkgs)
     best = None
     for _ in range(reps):
         ctx.run_staged(); st = ctx.stats()
