@@ -172,14 +172,43 @@ __device__ __forceinline__ unsigned long long remap_hints(const unsigned long lo
   return out;
 }
 
+// Work distribution.  Items (rays, or ray x channel group) are handed out in CHUNKS of consecutive items per CTA: the
+// warps of a CTA draw single items from the CTA's current chunk (shared-memory word: chunk base << 8 | items taken) and
+// whoever finds it exhausted fetches the next chunk from the global counter.  Consecutive items are neighbouring rays of
+// one scan / swath: they cross the same (p,T) cells with nearly the same column amounts, so the warps that run side by
+// side on an SM gather the same or neighbouring brackets and share them through L1.  Still dynamic at chunk granularity,
+// so rays of different length balance themselves.
+constexpr unsigned long long kChunkEmpty = 0xffull;  // "items taken" = 255: no chunk yet / exhausted
+constexpr unsigned long long kChunkLocked = 0xfeull; // a warp is fetching the next chunk
+__device__ __forceinline__ unsigned long long next_item(unsigned long long *state, unsigned long long *global_counter, const unsigned chunk) {
+  for (;;) {
+    const unsigned long long old = *reinterpret_cast<volatile unsigned long long *>(state);
+    const unsigned taken = (unsigned)(old & 0xffull);
+    if (taken == (unsigned)kChunkLocked) continue;                      // another warp is refilling
+    if (taken < chunk) {
+      if (atomicCAS(state, old, old + 1ull) == old) return (old >> 8) + taken;
+      continue;
+    }
+    if (atomicCAS(state, old, kChunkLocked) != old) continue;           // somebody else was faster
+    const unsigned long long base = atomicAdd(global_counter, (unsigned long long)chunk);
+    atomicExch(state, (base << 8) | 1ull);
+    return base;
+  }
+}
+
 } // namespace fast
 
+// 24 warps per SM at 80 registers is the measured optimum (profiles/README.md).  Large batches run them as ONE 768-thread
+// CTA per SM, so that all 24 warps draw neighbouring rays from the same work chunk (L1 sharing, see next_item); small
+// batches, and gas counts whose per-thread state does not fit one CTA's shared memory, use 256-thread CTAs (3 per SM),
+// which spread a single package over all SMs.
 #ifndef JRB_EGA_BLOCK
-#define JRB_EGA_BLOCK 256
+#define JRB_EGA_BLOCK 768
 #endif
-constexpr int kEgaBlock = JRB_EGA_BLOCK;
+constexpr int kEgaBlock = JRB_EGA_BLOCK; // launch bound (register budget); the launched block is kEgaBlock or kEgaSmallBlock
+constexpr int kEgaSmallBlock = 256;
 #ifndef JRB_EGA_MINBLOCKS
-#define JRB_EGA_MINBLOCKS 3 // CTAs per SM the register allocation must allow (3 x 8 warps; measured best, see profiles/)
+#define JRB_EGA_MINBLOCKS 1
 #endif
 
 // rays per warp: 1 for nd > 16; for fewer channels a warp takes floor(32/nd) whole rays (lane = ray_in_warp * nd + channel)
@@ -187,7 +216,8 @@ __host__ __device__ inline int ega_rays_per_warp(int nd) { return nd > 16 ? 1 : 
 
 __host__ __device__ inline size_t ega_fast_smem_bytes(int ng, int rec, int threads, int rpw) {
   const int nwarps = threads / 32;
-  return (size_t)nwarps * 2 * 8                  // mbarriers
+  return 16                                      // work-chunk state of the CTA
+         + (size_t)nwarps * 2 * 8                // mbarriers
          + (size_t)nwarps * 2 * rpw * rec * 8    // LOS record double buffers (one record per ray of the warp)
          + (size_t)ng * threads * 16;            // tau_path + hints
 }
@@ -209,13 +239,15 @@ __global__ void __launch_bounds__(kEgaBlock, JRB_EGA_MINBLOCKS) ega_fast_kernel(
 
   const int rpw = MULTI ? 32 / nd : 1;          // rays per warp
   const int bufstride = rpw * L.head;           // doubles per record buffer of a warp
-  unsigned long long *bars = reinterpret_cast<unsigned long long *>(smem_raw) + warp * 2;
-  double *recbuf = reinterpret_cast<double *>(smem_raw + (size_t)nwarps * 16) + (size_t)warp * 2 * bufstride;
-  double *tau_s = reinterpret_cast<double *>(smem_raw + (size_t)nwarps * 16 + (size_t)nwarps * 2 * bufstride * 8) + tid;
+  unsigned long long *chunk_state = reinterpret_cast<unsigned long long *>(smem_raw);
+  unsigned long long *bars = reinterpret_cast<unsigned long long *>(smem_raw + 16) + warp * 2;
+  double *recbuf = reinterpret_cast<double *>(smem_raw + 16 + (size_t)nwarps * 16) + (size_t)warp * 2 * bufstride;
+  double *tau_s = reinterpret_cast<double *>(smem_raw + 16 + (size_t)nwarps * 16 + (size_t)nwarps * 2 * bufstride * 8) + tid;
   unsigned long long *hint_s = reinterpret_cast<unsigned long long *>(tau_s - tid + (size_t)ng * blockDim.x) + tid;
   const int sstride = blockDim.x;
 
   if (lane == 0) { fast::mbar_init(&bars[0], 1); fast::mbar_init(&bars[1], 1); }
+  if (tid == 0) *chunk_state = fast::kChunkEmpty;
   asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   __syncthreads();
   unsigned parity0 = 0, parity1 = 0;
@@ -226,7 +258,7 @@ __global__ void __launch_bounds__(kEgaBlock, JRB_EGA_MINBLOCKS) ega_fast_kernel(
 
   for (;;) {
     unsigned long long item = 0;
-    if (lane == 0) item = atomicAdd(a.work_counter, 1ull);
+    if (lane == 0) item = fast::next_item(chunk_state, a.work_counter, (unsigned)a.work_chunk);
     item = __shfl_sync(0xffffffffu, item, 0);
     if (item >= n_items) break;
     long long ir;
@@ -384,21 +416,33 @@ __global__ void __launch_bounds__(kEgaBlock, JRB_EGA_MINBLOCKS) ega_fast_kernel(
 template <int MASK, bool MULTI, bool ROBUST>
 cudaError_t launch_ega_fast_tm(const EgaArgs &a, cudaStream_t stream, int sm_count) {
   const int rpw = MULTI ? ega_rays_per_warp(a.nd) : 1;
-  const size_t smem = ega_fast_smem_bytes(a.ng, a.los.head, kEgaBlock, rpw);
+  const int ngroups = (a.nd + 31) >> 5;
+  const long long n_items = MULTI ? (a.n_rays + rpw - 1) / rpw : a.n_rays * ngroups;
+  // block size: one big CTA per SM when there is work for many rounds of 24 warps on every SM (with few rounds the coarser
+  // chunks cost more in the tail than the L1 sharing gains: measured cross-over between 35 k and 125 k items) and its state fits
+  int block = kEgaBlock;
+  int dev = 0, smem_max = 0;
+  cudaGetDevice(&dev);
+  cudaDeviceGetAttribute(&smem_max, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev);
+  if (const char *s = getenv("JRB_EGA_THREADS")) { const int v = atoi(s); if (v >= 32 && v <= kEgaBlock && v % 32 == 0) block = v; } // experiments
+  else if (n_items < 16ll * sm_count * (kEgaBlock / 32) || ega_fast_smem_bytes(a.ng, a.los.head, kEgaBlock, rpw) > (size_t)smem_max)
+    block = kEgaSmallBlock;
+  const size_t smem = ega_fast_smem_bytes(a.ng, a.los.head, block, rpw);
   cudaError_t e = cudaFuncSetAttribute(ega_fast_kernel<MASK, MULTI, ROBUST>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   if (e != cudaSuccess) return e;
   int blocks_per_sm = 0;
-  e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&blocks_per_sm, ega_fast_kernel<MASK, MULTI, ROBUST>, kEgaBlock, smem);
+  e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&blocks_per_sm, ega_fast_kernel<MASK, MULTI, ROBUST>, block, smem);
   if (e != cudaSuccess) return e;
   if (blocks_per_sm < 1) return cudaErrorInvalidConfiguration;
   if (const char *s = getenv("JRB_EGA_CTAS_PER_SM")) { const int v = atoi(s); if (v >= 1 && v < blocks_per_sm) blocks_per_sm = v; } // occupancy experiments
-  const int ngroups = (a.nd + 31) >> 5;
-  const long long n_items = MULTI ? (a.n_rays + rpw - 1) / rpw : a.n_rays * ngroups;
+  EgaArgs args = a;
+  if (args.work_chunk <= 0) args.work_chunk = block / 32; // one item per warp of the CTA: the warps of a CTA stay on neighbouring rays
   long long grid = (long long)sm_count * blocks_per_sm; // persistent: a whole number of CTAs per SM
-  const long long need = (n_items + (kEgaBlock / 32) - 1) / (kEgaBlock / 32);
+  const long long per_cta = args.work_chunk > block / 32 ? args.work_chunk : block / 32;
+  const long long need = (n_items + per_cta - 1) / per_cta;
   if (grid > need) grid = need;
   if (grid < 1) grid = 1;
-  ega_fast_kernel<MASK, MULTI, ROBUST><<<(unsigned)grid, kEgaBlock, smem, stream>>>(a);
+  ega_fast_kernel<MASK, MULTI, ROBUST><<<(unsigned)grid, block, smem, stream>>>(args);
   return cudaGetLastError();
 }
 

@@ -49,6 +49,7 @@ struct EgaArgs {
   TblDev tbl;
   double *rad, *tau;    // [n_rays][nd]
   unsigned long long *work_counter; // dynamic work distribution (zeroed before launch)
+  int work_chunk;                   // consecutive items a CTA draws at a time (1..200); 0 = one per warp of the CTA
 };
 
 struct FovArgs { // optional epilogue: field-of-view convolution (formod_fov, src/jurassic.c:214-258)

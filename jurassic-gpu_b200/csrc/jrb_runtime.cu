@@ -574,6 +574,8 @@ int jrb_run_staged(jrb_context *ctx) {
     e.tbl = ctx->td;
     e.rad = ctx->o_rad + (size_t)r0 * nd; e.tau = ctx->o_tau + (size_t)r0 * nd;
     e.work_counter = (unsigned long long *)ctx->d_counter.p + c;
+    e.work_chunk = 0; // 0: the launcher picks one item per warp of the CTA
+    if (const char *s = getenv("JRB_EGA_CHUNK")) { const int v = atoi(s); if (v >= 1 && v <= 200) e.work_chunk = v; } // experiments
     if (pipe) CU(cudaStreamWaitEvent(st_e, EV(c, 1), 0));
     CU(cudaEventRecord(EV(c, 2), st_e));
     if (ctx->use_fast) CU(launch_ega_fast(e, st_e, &ngb));

@@ -26,7 +26,7 @@ ctl = synth.control_config_d(); tbl = synth.make_tables(ctl)
 timing("D", ctl, tbl, [synth.limb_package(ctl, seed=20240517 + i) for i in range(int(os.environ.get("NPK", "32")))])
 if os.environ.get("WITH_E", "1") == "1":
     ctl = synth.control_config_e(); tbl = synth.make_tables(ctl)
-    timing("E", ctl, tbl, [synth.nadir_package(ctl, seed=20240518 + i) for i in range(8)])
+    timing("E", ctl, tbl, [synth.nadir_package(ctl, seed=20240518 + i) for i in range(int(os.environ.get("NPK_E", "8")))])
 if os.environ.get("WITH_A", "0") == "1":
     ctl = synth.control_limb_example(); tbl = synth.make_tables(ctl)
     timing("A-like nd=2", ctl, tbl, [synth.limb_package(ctl, seed=20240517 + i) for i in range(32)])
