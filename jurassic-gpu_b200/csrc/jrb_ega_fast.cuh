@@ -251,6 +251,9 @@ __global__ void __launch_bounds__(kEgaBlock, JRB_EGA_MINBLOCKS) ega_fast_kernel(
   asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   __syncthreads();
   unsigned parity0 = 0, parity1 = 0;
+  // balance[0] = idle segment slots, balance[1] = all segment slots if every chunk of blockDim/32 consecutive items ran in
+  // lock step (chunk_balance_kernel): lock step is chosen when less than 1/32 of the slots would idle
+  const bool phase_lock = a.phase_lock_mode == 1 || (a.phase_lock_mode < 0 && a.balance != nullptr && a.balance[0] * 32ull < a.balance[1]);
 
   const int ngroups = (nd + 31) >> 5;
   const unsigned long long n_items = MULTI ? (unsigned long long)((a.n_rays + rpw - 1) / rpw) : (unsigned long long)a.n_rays * ngroups;
@@ -258,9 +261,22 @@ __global__ void __launch_bounds__(kEgaBlock, JRB_EGA_MINBLOCKS) ega_fast_kernel(
 
   for (;;) {
     unsigned long long item = 0;
-    if (lane == 0) item = fast::next_item(chunk_state, a.work_counter, (unsigned)a.work_chunk);
-    item = __shfl_sync(0xffffffffu, item, 0);
-    if (item >= n_items) break;
+    if (phase_lock) {
+      // all warps of the CTA start their rays together and therefore stay in phase (same segment index = same altitude
+      // range = same table cells): what one warp gathers, its neighbours find in L1.  Costs the idle time of the
+      // shorter rays at the end of each chunk, hence only used when the rays of a chunk are of (nearly) equal length.
+      __syncthreads();
+      if (tid == 0) *chunk_state = atomicAdd(a.work_counter, (unsigned long long)nwarps);
+      __syncthreads();
+      const unsigned long long base = *chunk_state;
+      if (base >= n_items) break;
+      item = base + warp;
+      if (item >= n_items) continue;
+    } else {
+      if (lane == 0) item = fast::next_item(chunk_state, a.work_counter, (unsigned)a.work_chunk);
+      item = __shfl_sync(0xffffffffu, item, 0);
+      if (item >= n_items) break;
+    }
     long long ir;
     int id;
     bool lane_on;
@@ -413,6 +429,32 @@ __global__ void __launch_bounds__(kEgaBlock, JRB_EGA_MINBLOCKS) ega_fast_kernel(
   }
 }
 
+// Load balance of lock-step execution: for every chunk of `chunk` consecutive items (an item = `rpw` consecutive rays
+// handled by one warp, its length the longest of them) the segment slots that would idle while the chunk's longest
+// item finishes, and the total.  One thread per chunk; rays are short rows of ints, the kernel is negligible.
+static __global__ void chunk_balance_kernel(const int *__restrict__ ray_np, const long long n_rays, const int rpw, const int chunk,
+                                            unsigned long long *__restrict__ balance) {
+  const long long c = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  const long long n_items = (n_rays + rpw - 1) / rpw;
+  unsigned long long idle = 0, total = 0;
+  if (c * chunk < n_items) {
+    int lmax = 0, cnt = 0;
+    long long sum = 0;
+    for (int j = 0; j < chunk; j++) {
+      const long long item = c * chunk + j;
+      if (item >= n_items) break;
+      int len = 0;
+      for (int r = 0; r < rpw; r++) { const long long ir = item * rpw + r; if (ir < n_rays) len = max(len, ray_np[ir]); }
+      lmax = max(lmax, len); sum += len; cnt++;
+    }
+    total = (unsigned long long)lmax * (unsigned long long)cnt;
+    idle = total - (unsigned long long)sum;
+  }
+  // warp-level reduction, one atomic pair per warp
+  for (int o = 16; o > 0; o >>= 1) { idle += __shfl_down_sync(0xffffffffu, idle, o); total += __shfl_down_sync(0xffffffffu, total, o); }
+  if ((threadIdx.x & 31) == 0 && total) { atomicAdd(&balance[0], idle); atomicAdd(&balance[1], total); }
+}
+
 template <int MASK, bool MULTI, bool ROBUST>
 cudaError_t launch_ega_fast_tm(const EgaArgs &a, cudaStream_t stream, int sm_count) {
   const int rpw = MULTI ? ega_rays_per_warp(a.nd) : 1;
@@ -437,6 +479,10 @@ cudaError_t launch_ega_fast_tm(const EgaArgs &a, cudaStream_t stream, int sm_cou
   if (const char *s = getenv("JRB_EGA_CTAS_PER_SM")) { const int v = atoi(s); if (v >= 1 && v < blocks_per_sm) blocks_per_sm = v; } // occupancy experiments
   EgaArgs args = a;
   if (args.work_chunk <= 0) args.work_chunk = block / 32; // one item per warp of the CTA: the warps of a CTA stay on neighbouring rays
+  if (args.phase_lock_mode < 0 && args.balance != nullptr && a.n_rays > 0) { // let the device decide: equal-length chunks -> lock step
+    const long long n_chunks = (n_items + block / 32 - 1) / (block / 32);
+    chunk_balance_kernel<<<(unsigned)((n_chunks + 127) / 128), 128, 0, stream>>>(a.ray_np, a.n_rays, rpw, block / 32, args.balance);
+  }
   long long grid = (long long)sm_count * blocks_per_sm; // persistent: a whole number of CTAs per SM
   const long long per_cta = args.work_chunk > block / 32 ? args.work_chunk : block / 32;
   const long long need = (n_items + per_cta - 1) / per_cta;

@@ -503,7 +503,7 @@ int jrb_stage(jrb_context *ctx, int npk, const jrb_atm_view *atm, const jrb_obs_
   CU(ctx->d_los.ensure((size_t)(chunk ? chunk : 1) * per_ray * ctx->nbuf));
   {
     const long long nch = R > 0 ? (R + chunk - 1) / chunk : 1;
-    CU(ctx->d_counter.ensure((size_t)nch * 8 + 256));
+    CU(ctx->d_counter.ensure((size_t)nch * 32 + 256)); // per LOS chunk: work counter, lock-step balance (idle, total), pad
   }
 
   CU(cudaStreamSynchronize(ctx->stream));
@@ -534,7 +534,7 @@ int jrb_run_staged(jrb_context *ctx) {
   cudaStream_t st_tr = pipe ? ctx->s_trace : ctx->stream;
   CU(cudaEventRecord(ctx->events[0], ctx->stream));
   if (pipe) CU(cudaStreamWaitEvent(st_tr, ctx->events[0], 0));
-  if (ctx->use_fast && nchunks > 0) CU(cudaMemsetAsync(ctx->d_counter.p, 0, (size_t)nchunks * 8, st_tr));
+  if (ctx->use_fast && nchunks > 0) CU(cudaMemsetAsync(ctx->d_counter.p, 0, (size_t)nchunks * 32, st_tr));
   for (long long c = 0; c < nchunks; c++) {
     const long long r0 = c * ctx->chunk_rays, r1 = std::min(R, r0 + ctx->chunk_rays);
     double *los_buf = (double *)ctx->d_los.p + (size_t)(c % ctx->nbuf) * (size_t)ctx->chunk_rays * per_ray;
@@ -573,14 +573,17 @@ int jrb_run_staged(jrb_context *ctx) {
     e.chan = (const double *)ctx->d_chan.p; e.window = (const int *)ctx->d_window.p;
     e.tbl = ctx->td;
     e.rad = ctx->o_rad + (size_t)r0 * nd; e.tau = ctx->o_tau + (size_t)r0 * nd;
-    e.work_counter = (unsigned long long *)ctx->d_counter.p + c;
+    e.work_counter = (unsigned long long *)ctx->d_counter.p + 4 * c;
+    e.balance = e.work_counter + 1;
+    e.phase_lock_mode = -1;
+    if (const char *s = getenv("JRB_EGA_LOCKSTEP")) { const int v = atoi(s); if (v == 0 || v == 1) e.phase_lock_mode = v; } // experiments
     e.work_chunk = 0; // 0: the launcher picks one item per warp of the CTA
     if (const char *s = getenv("JRB_EGA_CHUNK")) { const int v = atoi(s); if (v >= 1 && v <= 200) e.work_chunk = v; } // experiments
     if (pipe) CU(cudaStreamWaitEvent(st_e, EV(c, 1), 0));
     CU(cudaEventRecord(EV(c, 2), st_e));
     if (ctx->use_fast) CU(launch_ega_fast(e, st_e, &ngb));
     else CU(launch_ega_generic(e, st_e));
-    launches++;
+    launches += (ctx->use_fast && e.phase_lock_mode < 0 && e.n_rays > 0) ? 2 : 1; // + chunk_balance_kernel
     CU(cudaEventRecord(EV(c, 3), st_e));
   }
   if (pipe) {
@@ -748,6 +751,15 @@ int jrb_get_stats(const jrb_context *cctx, jrb_stats *out) {
     long long s = 0;
     for (int v : np) s += v;
     ctx->stats.n_los_points = s;
+    // lock-step decision of the specialised kernel (made on the device from the balance words of LOS chunk 0)
+    ctx->stats.ega_phase_lock = 0;
+    if (ctx->use_fast && ctx->n_rays > 0) {
+      unsigned long long w[4] = {0, 0, 0, 0};
+      CU(cudaMemcpy(w, ctx->d_counter.p, sizeof(w), cudaMemcpyDeviceToHost));
+      int mode = -1;
+      if (const char *e = getenv("JRB_EGA_LOCKSTEP")) { const int v = atoi(e); if (v == 0 || v == 1) mode = v; }
+      ctx->stats.ega_phase_lock = mode >= 0 ? mode : (w[1] * 32ull < w[2] ? 1 : 0);
+    }
     ctx->np_fetched = true;
   }
   *out = ctx->stats;

@@ -483,3 +483,26 @@ def test_full_baseline_size_in_one_call(jr, gpu_ctx_factory):
     assert len({next(iter(s)) for s in sums.values()}) == 115   # and distinct packages give distinct results
     for p in pkgs[::37]:
         assert np.all(np.isfinite(p.rad)) and np.all(p.rad >= 0) and np.all((p.tau >= 0) & (p.tau <= 1))
+
+
+def test_lock_step_mode_is_chosen_for_equal_length_rays_and_changes_nothing(jr, oracle, gpu_ctx_factory, monkeypatch):
+    """The specialised kernel starts the rays of a CTA together (lock step -> neighbouring warps share table brackets in L1)
+    when the rays of a work chunk are of nearly equal length: nadir swaths yes, limb scans (130..393 segments) no.  The
+    decision is made on the device; results are bit-identical either way."""
+    ctx = gpu_ctx_factory()
+    for name, ctl, pkgs, expect in (
+            ("nadir", jr.synth.control_config_e(nd=32), [jr.synth.nadir_package(jr.synth.control_config_e(nd=32), n_profiles=2, rays_per_profile=68, seed=3 + i) for i in range(3)], 1),
+            ("limb", jr.synth.control_config_d(nd=32), [jr.synth.limb_package(jr.synth.control_config_d(nd=32), n_profiles=2, rays_per_profile=64, seed=5 + i) for i in range(3)], 0)):
+        tbl = jr.synth.make_tables(ctl)
+        monkeypatch.delenv("JRB_EGA_LOCKSTEP", raising=False)
+        auto = run_cuda(ctx, ctl, tbl, pkgs, 1)
+        assert ctx.stats()["ega_phase_lock"] == expect, name
+        ref = run_oracle(oracle, ctl, tbl, pkgs[:1])[0]
+        assert_parity(auto[0], ref, f"lock step auto {name}")
+        for forced in ("0", "1"):
+            monkeypatch.setenv("JRB_EGA_LOCKSTEP", forced)
+            out = run_cuda(ctx, ctl, tbl, pkgs, 1)
+            assert ctx.stats()["ega_phase_lock"] == int(forced)
+            for a, b in zip(auto, out):
+                assert np.array_equal(a.rad, b.rad) and np.array_equal(a.tau, b.tau)
+        monkeypatch.delenv("JRB_EGA_LOCKSTEP", raising=False)
