@@ -460,12 +460,16 @@ cudaError_t launch_ega_fast_tm(const EgaArgs &a, cudaStream_t stream, int sm_cou
   const int rpw = MULTI ? ega_rays_per_warp(a.nd) : 1;
   const int ngroups = (a.nd + 31) >> 5;
   const long long n_items = MULTI ? (a.n_rays + rpw - 1) / rpw : a.n_rays * ngroups;
-  // block size: one big CTA per SM when there is work for many rounds of 24 warps on every SM (with few rounds the coarser
-  // chunks cost more in the tail than the L1 sharing gains: measured cross-over between 35 k and 125 k items) and its state fits
-  int block = kEgaBlock;
+  // Block size.  Large batches: ONE 768-thread CTA per SM, so that all 24 warps share one work chunk.  Small batches (fewer
+  // than 16 rounds of work per SM: the coarser chunks would cost more in the tail than the L1 sharing gains, measured
+  // cross-over between 35 k and 125 k items) and gas counts whose per-thread state (16 B per gas and thread) does not
+  // fit one such CTA use 256-thread CTAs, as many per SM as fit (3 up to 16 gases).  For the 30-gas refspec shape that
+  // is 8 warps per SM; a 448-thread CTA (14 warps) was measured SLOWER there (226 vs 145 ms): its 960 (gas, channel)
+  // table pairs exceed the L2 and more rays in flight only widen the working set.
   int dev = 0, smem_max = 0;
   cudaGetDevice(&dev);
   cudaDeviceGetAttribute(&smem_max, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev);
+  int block = kEgaBlock;
   if (const char *s = getenv("JRB_EGA_THREADS")) { const int v = atoi(s); if (v >= 32 && v <= kEgaBlock && v % 32 == 0) block = v; } // experiments
   else if (n_items < 16ll * sm_count * (kEgaBlock / 32) || ega_fast_smem_bytes(a.ng, a.los.head, kEgaBlock, rpw) > (size_t)smem_max)
     block = kEgaSmallBlock;

@@ -27,6 +27,12 @@ timing("D", ctl, tbl, [synth.limb_package(ctl, seed=20240517 + i) for i in range
 if os.environ.get("WITH_E", "1") == "1":
     ctl = synth.control_config_e(); tbl = synth.make_tables(ctl)
     timing("E", ctl, tbl, [synth.nadir_package(ctl, seed=20240518 + i) for i in range(int(os.environ.get("NPK_E", "8")))])
+if os.environ.get("WITH_C", "0") == "1":  # refspec shape: 30 gases (channels cut to 32 to keep the tables small)
+    gases = ["CO2", "H2O", "O3", "N2O", "CH4", "CO", "HNO3", "SO2", "F11", "CCl4"] + [f"X{i}" for i in range(20)]
+    ctl = jr.Control(gases, 2150.0 + synth.np.arange(32)); tbl = synth.make_tables(ctl)
+    pk = [synth.limb_package(ctl, seed=20240517 + i) for i in range(int(os.environ.get("NPK_C", "8")))]
+    for p in pk: p.q[10:, :] = 1e-9
+    timing("C-like ng=30", ctl, tbl, pk)
 if os.environ.get("WITH_A", "0") == "1":
     ctl = synth.control_limb_example(); tbl = synth.make_tables(ctl)
     timing("A-like nd=2", ctl, tbl, [synth.limb_package(ctl, seed=20240517 + i) for i in range(32)])
