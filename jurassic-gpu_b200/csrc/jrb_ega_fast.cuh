@@ -211,8 +211,6 @@ constexpr int kEgaSmallBlock = 256;
 #define JRB_EGA_MINBLOCKS 1
 #endif
 
-// rays per warp: 1 for nd > 16; for fewer channels a warp takes floor(32/nd) whole rays (lane = ray_in_warp * nd + channel)
-__host__ __device__ inline int ega_rays_per_warp(int nd) { return nd > 16 ? 1 : 32 / nd; }
 
 __host__ __device__ inline size_t ega_fast_smem_bytes(int ng, int rec, int threads, int rpw) {
   const int nwarps = threads / 32;
@@ -222,9 +220,12 @@ __host__ __device__ inline size_t ega_fast_smem_bytes(int ng, int rec, int threa
          + (size_t)ng * threads * 16;            // tau_path + hints
 }
 
-// MULTI = false: one ray per warp, lane = channel of a 32-channel group (nd > 16).
-// MULTI = true : nd <= 16, floor(32/nd) rays per warp so that few-channel instruments (the reference's own examples have
-//                2 and 3 channels) do not leave 90 % of the lanes idle; every ray of the warp gets its own staged record.
+// MULTI = false: one ray per warp, lane = channel of a 32-channel group.
+// MULTI = true : a warp handles cpw < 32 channels of floor(32/cpw) consecutive rays (lane = ray_in_warp * cpw + channel); every
+//                ray of the warp gets its own staged record.  Used (a) for few-channel instruments, cpw = nd <= 16 -- the
+//                reference's own examples have 2 and 3 channels, which would leave 90 % of the lanes idle -- and (b) to
+//                narrow the channel group when (32 channels x ng gases) of tables do not fit the L2: work is channel-group
+//                major, so the hot table set is cpw channels x ng gases (EgaArgs::cpw, chosen by the runtime).
 // ROBUST = true: the table set contains columns that are not sorted in u or eps (flagged kColNonMonotone at pack time);
 //                cells touching such a column are evaluated with the reference's plain bisection.  The ROBUST = false
 //                instantiation is used for fully sorted table sets and carries no trace of this.
@@ -237,7 +238,8 @@ __global__ void __launch_bounds__(kEgaBlock, JRB_EGA_MINBLOCKS) ega_fast_kernel(
   const int nd = a.nd, ng = a.ng;
   const unsigned rec_bytes = (unsigned)L.head * 8u; // only the head of a record is staged
 
-  const int rpw = MULTI ? 32 / nd : 1;          // rays per warp
+  const int cpw = MULTI ? a.cpw : 32;           // channels of a ray handled by one warp
+  const int rpw = MULTI ? 32 / cpw : 1;         // rays per warp
   const int bufstride = rpw * L.head;           // doubles per record buffer of a warp
   unsigned long long *chunk_state = reinterpret_cast<unsigned long long *>(smem_raw);
   unsigned long long *bars = reinterpret_cast<unsigned long long *>(smem_raw + 16) + warp * 2;
@@ -255,9 +257,10 @@ __global__ void __launch_bounds__(kEgaBlock, JRB_EGA_MINBLOCKS) ega_fast_kernel(
   // lock step (chunk_balance_kernel): lock step is chosen when less than 1/32 of the slots would idle
   const bool phase_lock = a.phase_lock_mode == 1 || (a.phase_lock_mode < 0 && a.balance != nullptr && a.balance[0] * 32ull < a.balance[1]);
 
-  const int ngroups = (nd + 31) >> 5;
-  const unsigned long long n_items = MULTI ? (unsigned long long)((a.n_rays + rpw - 1) / rpw) : (unsigned long long)a.n_rays * ngroups;
-  const int sub = MULTI ? lane / nd : 0;        // ray of this lane within the warp
+  const int ngroups = (nd + cpw - 1) / cpw;
+  const unsigned long long n_blocks = MULTI ? (unsigned long long)((a.n_rays + rpw - 1) / rpw) : (unsigned long long)a.n_rays;
+  const unsigned long long n_items = n_blocks * ngroups; // channel-group major: item = group * n_blocks + ray block
+  const int sub = MULTI ? lane / cpw : 0;       // ray of this lane within the warp
 
   for (;;) {
     unsigned long long item = 0;
@@ -280,11 +283,15 @@ __global__ void __launch_bounds__(kEgaBlock, JRB_EGA_MINBLOCKS) ega_fast_kernel(
     long long ir;
     int id;
     bool lane_on;
+    bool ray_on = true; // this lane's ray exists (MULTI: the lane may still be off if its channel is beyond nd)
     if (MULTI) {
-      ir = (long long)item * rpw + sub;
-      lane_on = sub < rpw && ir < a.n_rays;
-      if (!lane_on) ir = a.n_rays - 1; // idle lanes shadow a valid ray and never store
-      id = lane_on ? lane - sub * nd : 0;
+      const int grp = (int)(item / n_blocks);
+      ir = (long long)(item - (unsigned long long)grp * n_blocks) * rpw + sub;
+      ray_on = sub < rpw && ir < a.n_rays;
+      const int id_raw = grp * cpw + (lane - sub * cpw);
+      lane_on = ray_on && id_raw < nd;
+      if (!ray_on) ir = a.n_rays - 1; // idle lanes shadow a valid ray and never store
+      id = lane_on ? id_raw : 0;
     } else {
       // channel-group major: all warps in flight work on the same 32 channels, so the part of the tables that is hot
       // at any time is (32 channels x ng gases), which is what has to fit into L2
@@ -296,9 +303,9 @@ __global__ void __launch_bounds__(kEgaBlock, JRB_EGA_MINBLOCKS) ega_fast_kernel(
     }
 
     const double *__restrict__ rec_g = a.los_data + (size_t)ir * kNLOS * L.rec;
-    const int np = lane_on || !MULTI ? a.ray_np[ir] : 0;       // segments of this lane's ray
+    const int np = ray_on ? a.ray_np[ir] : 0;                  // segments of this lane's ray
     const int np_max = MULTI ? __reduce_max_sync(0xffffffffu, np) : np;
-    const bool head_lane = MULTI ? (lane_on && id == 0) : (lane == 0); // issues the record copies of its ray
+    const bool head_lane = MULTI ? (ray_on && lane == sub * cpw) : (lane == 0); // issues the record copies of its ray
     const int win = a.window[id];
 
     for (int ig = 0; ig < ng; ig++) {
@@ -457,9 +464,9 @@ static __global__ void chunk_balance_kernel(const int *__restrict__ ray_np, cons
 
 template <int MASK, bool MULTI, bool ROBUST>
 cudaError_t launch_ega_fast_tm(const EgaArgs &a, cudaStream_t stream, int sm_count) {
-  const int rpw = MULTI ? ega_rays_per_warp(a.nd) : 1;
-  const int ngroups = (a.nd + 31) >> 5;
-  const long long n_items = MULTI ? (a.n_rays + rpw - 1) / rpw : a.n_rays * ngroups;
+  const int cpw = MULTI ? a.cpw : 32, rpw = 32 / cpw;
+  const int ngroups = (a.nd + cpw - 1) / cpw;
+  const long long n_items = ((a.n_rays + rpw - 1) / rpw) * ngroups;
   // Block size.  Large batches: ONE 768-thread CTA per SM, so that all 24 warps share one work chunk.  Small batches (fewer
   // than 16 rounds of work per SM: the coarser chunks would cost more in the tail than the L1 sharing gains, measured
   // cross-over between 35 k and 125 k items) and gas counts whose per-thread state (16 B per gas and thread) does not
@@ -498,9 +505,10 @@ cudaError_t launch_ega_fast_tm(const EgaArgs &a, cudaStream_t stream, int sm_cou
 
 template <int MASK>
 cudaError_t launch_ega_fast_t(const EgaArgs &a, cudaStream_t stream, int sm_count) {
+  const bool multi = a.cpw < 32; // several rays per warp
   if (a.unsorted_columns)
-    return a.nd <= 16 ? launch_ega_fast_tm<MASK, true, true>(a, stream, sm_count) : launch_ega_fast_tm<MASK, false, true>(a, stream, sm_count);
-  return a.nd <= 16 ? launch_ega_fast_tm<MASK, true, false>(a, stream, sm_count) : launch_ega_fast_tm<MASK, false, false>(a, stream, sm_count);
+    return multi ? launch_ega_fast_tm<MASK, true, true>(a, stream, sm_count) : launch_ega_fast_tm<MASK, false, true>(a, stream, sm_count);
+  return multi ? launch_ega_fast_tm<MASK, true, false>(a, stream, sm_count) : launch_ega_fast_tm<MASK, false, false>(a, stream, sm_count);
 }
 
 // one translation unit per MASK

@@ -52,6 +52,7 @@ struct EgaArgs {
   int work_chunk;                   // consecutive items a CTA draws at a time (1..200); 0 = one per warp of the CTA
   unsigned long long *balance;      // [2] scratch (zeroed before launch): idle / total segment slots of lock-step execution
   int phase_lock_mode;              // -1 decide on the device from `balance`, 0 never, 1 always
+  int cpw;                          // channels of a ray per warp: 32, or less (= several rays per warp, see jrb_ega_fast.cuh)
 };
 
 struct FovArgs { // optional epilogue: field-of-view convolution (formod_fov, src/jurassic.c:214-258)

@@ -577,6 +577,19 @@ int jrb_run_staged(jrb_context *ctx) {
     e.balance = e.work_counter + 1;
     e.phase_lock_mode = -1;
     if (const char *s = getenv("JRB_EGA_LOCKSTEP")) { const int v = atoi(s); if (v == 0 || v == 1) e.phase_lock_mode = v; } // experiments
+    // channels per warp: all of them for few-channel instruments; otherwise 32 unless the tables of (32 channels x ng
+    // gases) cannot stay in L2 -- then narrower channel groups with several rays per warp (channel-group-major order keeps
+    // the hot set at cpw x ng pairs).  Hot bytes per (gas, channel) pair: ~30 % of its brackets (measured on the synthetic
+    // sets: a package touches 357 KB of a 1.26 MB pair); budget 0.7 x L2, which reproduces the measured optima (Config D,
+    // 57 MB at 32 channels: 32 = 16 > 8; Config E, 94 MB: 16 best, -4 %; 30 gases, 343 MB: 8 best, -14 %).
+    e.cpw = nd <= 16 ? nd : 32;
+    if (nd > 16 && ng > 0) {
+      const double pair_hot = 0.3 * 16.0 * (double)ctx->th.n_entries / ((double)ng * nd);
+      int l2 = 0;
+      cudaDeviceGetAttribute(&l2, cudaDevAttrL2CacheSize, ctx->device);
+      while (e.cpw > 4 && pair_hot * e.cpw * ng > 0.7 * (double)l2) e.cpw >>= 1;
+    }
+    if (const char *s = getenv("JRB_EGA_CPW")) { const int v = atoi(s); if (v >= 1 && v <= 32 && (v == nd || (32 % v == 0 && v <= nd))) e.cpw = v; } // experiments
     e.work_chunk = 0; // 0: the launcher picks one item per warp of the CTA
     if (const char *s = getenv("JRB_EGA_CHUNK")) { const int v = atoi(s); if (v >= 1 && v <= 200) e.work_chunk = v; } // experiments
     if (pipe) CU(cudaStreamWaitEvent(st_e, EV(c, 1), 0));

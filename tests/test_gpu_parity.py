@@ -506,3 +506,24 @@ def test_lock_step_mode_is_chosen_for_equal_length_rays_and_changes_nothing(jr, 
             for a, b in zip(auto, out):
                 assert np.array_equal(a.rad, b.rad) and np.array_equal(a.tau, b.tau)
         monkeypatch.delenv("JRB_EGA_LOCKSTEP", raising=False)
+
+
+def test_narrow_channel_groups_give_identical_results(jr, oracle, gpu_ctx_factory, monkeypatch):
+    """The specialised kernel can give a warp fewer than 32 channels of several consecutive rays (chosen by the runtime when
+    the tables of 32 channels x ng gases exceed the L2, here forced): any split gives bit-identical results, including a
+    channel count that is not a multiple of the group width and a ray count that is not a multiple of the rays per warp."""
+    ctl = jr.Control(jr.synth.LIMB_GASES, 785.0 + np.arange(37))
+    tbl = jr.synth.make_tables(ctl)
+    pkgs = [jr.synth.limb_package(ctl, n_profiles=1, rays_per_profile=13, z0=5.0, dz=4.0, seed=21 + i) for i in range(2)]
+    ctx = gpu_ctx_factory()
+    monkeypatch.delenv("JRB_EGA_CPW", raising=False)
+    base = run_cuda(ctx, ctl, tbl, pkgs, 1)
+    ref = run_oracle(oracle, ctl, tbl, pkgs)
+    for b, r in zip(base, ref):
+        assert_parity(b, r, "cpw default")
+    for cpw in ("16", "8", "4"):
+        monkeypatch.setenv("JRB_EGA_CPW", cpw)
+        out = run_cuda(ctx, ctl, tbl, pkgs, 1)
+        for a, b in zip(base, out):
+            assert np.array_equal(a.rad, b.rad) and np.array_equal(a.tau, b.tau), cpw
+    monkeypatch.delenv("JRB_EGA_CPW", raising=False)
