@@ -1,8 +1,11 @@
 // jrb_ega_fast.cuh -- specialised EGA kernels, template <continuum MASK> (the 16 variants the reference stamps out
 // with src/jr_multiversion4gases.h are template instantiations here).
 //
-// Mapping: one warp = one ray x 32 consecutive channels (lane = channel); warps fetch rays from a global work
-// counter so that rays of different length (130..393 segments) balance themselves.
+// Mapping: one warp = one ray x 32 consecutive channels (lane = channel), or fewer channels of several consecutive rays
+// (MULTI).  Persistent CTAs draw work in chunks of consecutive rays, one ray per warp, from a global counter -- rays of
+// different length (130..393 segments) balance themselves, and the warps of an SM work on neighbouring rays, whose table
+// brackets they share through L1; CTAs run in lock step when the rays of a chunk are equally long (next_item and the
+// work loop of the kernel).
 //
 // Data movement per segment:
 //   * the head of the ray's LOS record (p, T, ds, extinction, per-gas u, table cell + interpolation weights; 112 B for
