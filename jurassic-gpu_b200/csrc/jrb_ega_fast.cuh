@@ -486,6 +486,10 @@ cudaError_t launch_ega_fast_tm(const EgaArgs &a, cudaStream_t stream, int sm_cou
   const size_t smem = ega_fast_smem_bytes(a.ng, a.los.head, block, rpw);
   cudaError_t e = cudaFuncSetAttribute(ega_fast_kernel<MASK, MULTI, ROBUST>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   if (e != cudaSuccess) return e;
+  if (const char *s = getenv("JRB_EGA_CARVEOUT")) { // experiments: shared-memory carve-out in percent (the rest of the 256 KB is L1)
+    const int v = atoi(s);
+    if (v >= 0 && v <= 100) cudaFuncSetAttribute(ega_fast_kernel<MASK, MULTI, ROBUST>, cudaFuncAttributePreferredSharedMemoryCarveout, v);
+  }
   int blocks_per_sm = 0;
   e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&blocks_per_sm, ega_fast_kernel<MASK, MULTI, ROBUST>, block, smem);
   if (e != cudaSuccess) return e;
