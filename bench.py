@@ -385,7 +385,8 @@ def main():
             traffic = json.load(open(tp)).get("dram_bytes_per_launch")
         except Exception:
             traffic = None
-    roofline = {"bound": "hbm", "kernel": f"ega_fast_kernel<mask={st['ega_ctm_mask']}> ({st['ega_ngb']} gases)" if st["ega_kernel_variant"] else "ega_generic_kernel",
+    roofline = {"bound": "hbm", "kernel": (f"ega_fast_kernel<mask={st['ega_ctm_mask']}> ({st['ega_ngb']} gases, {st['ega_channels_per_warp']} channels per warp, "
+                           f"{'lock-step' if st['ega_phase_lock'] else 'free-running'} CTAs)") if st["ega_kernel_variant"] else "ega_generic_kernel",
                 "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": traffic,
                 "peak_source": peak_src, "algorithmic_bytes_per_ray_channel": bytes_rc, "mean_los_points": sbar,
                 "kernel_ms": ega, "raytrace_ms": float(np.mean(rt_ms)), "kernel_share_of_step": ega / ms_per_step}

@@ -98,6 +98,7 @@ typedef struct {
   float host_ms_pack, host_ms_h2d, host_ms_d2h, host_ms_scatter; /* wall-clock phases of the last stage / fetch */
   int n_chunks, pipelined; /* LOS chunks of the last run; 1 if the tracer of chunk c+1 ran beside the EGA kernel of chunk c */
   int ega_phase_lock;      /* 1 if the specialised kernel ran its CTAs in lock step (rays of equal length) */
+  int ega_channels_per_warp; /* channels of a ray handled by one warp of the specialised kernel (32, or fewer = several rays per warp) */
 } jrb_stats;
 
 typedef struct jrb_context jrb_context;

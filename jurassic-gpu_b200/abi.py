@@ -90,4 +90,4 @@ class Stats(C.Structure):
                 ("d2h_bytes", C.c_longlong), ("ega_kernel_variant", C.c_int), ("ega_ngb", C.c_int),
                 ("ega_ctm_mask", C.c_int), ("table_blob_bytes", C.c_longlong), ("host_ms_pack", C.c_float),
                 ("host_ms_h2d", C.c_float), ("host_ms_d2h", C.c_float), ("host_ms_scatter", C.c_float),
-                ("n_chunks", C.c_int), ("pipelined", C.c_int), ("ega_phase_lock", C.c_int)]
+                ("n_chunks", C.c_int), ("pipelined", C.c_int), ("ega_phase_lock", C.c_int), ("ega_channels_per_warp", C.c_int)]

@@ -590,6 +590,7 @@ int jrb_run_staged(jrb_context *ctx) {
       while (e.cpw > 4 && pair_hot * e.cpw * ng > 0.7 * (double)l2) e.cpw >>= 1;
     }
     if (const char *s = getenv("JRB_EGA_CPW")) { const int v = atoi(s); if (v >= 1 && v <= 32 && (v == nd || (32 % v == 0 && v <= nd))) e.cpw = v; } // experiments
+    ctx->stats.ega_channels_per_warp = ctx->use_fast ? e.cpw : 0;
     e.work_chunk = 0; // 0: the launcher picks one item per warp of the CTA
     if (const char *s = getenv("JRB_EGA_CHUNK")) { const int v = atoi(s); if (v >= 1 && v <= 200) e.work_chunk = v; } // experiments
     if (pipe) CU(cudaStreamWaitEvent(st_e, EV(c, 1), 0));

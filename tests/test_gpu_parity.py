@@ -518,12 +518,14 @@ def test_narrow_channel_groups_give_identical_results(jr, oracle, gpu_ctx_factor
     ctx = gpu_ctx_factory()
     monkeypatch.delenv("JRB_EGA_CPW", raising=False)
     base = run_cuda(ctx, ctl, tbl, pkgs, 1)
+    assert ctx.stats()["ega_channels_per_warp"] == 32   # 37 channels x 5 gases of tables fit the L2 budget
     ref = run_oracle(oracle, ctl, tbl, pkgs)
     for b, r in zip(base, ref):
         assert_parity(b, r, "cpw default")
     for cpw in ("16", "8", "4"):
         monkeypatch.setenv("JRB_EGA_CPW", cpw)
         out = run_cuda(ctx, ctl, tbl, pkgs, 1)
+        assert ctx.stats()["ega_channels_per_warp"] == int(cpw)
         for a, b in zip(base, out):
             assert np.array_equal(a.rad, b.rad) and np.array_equal(a.tau, b.tau), cpw
     monkeypatch.delenv("JRB_EGA_CPW", raising=False)
