@@ -33,6 +33,14 @@ if os.environ.get("WITH_C", "0") == "1":  # refspec shape: 30 gases (channels cu
     pk = [synth.limb_package(ctl, seed=20240517 + i) for i in range(int(os.environ.get("NPK_C", "8")))]
     for p in pk: p.q[10:, :] = 1e-9
     timing("C-like ng=30", ctl, tbl, pk)
+if os.environ.get("WITH_J", "0") == "1":  # Jacobian-like batch: one package, NJ atmospheres with a single perturbed temperature each
+    import copy
+    ctl = synth.control_config_d(); tbl = synth.make_tables(ctl)
+    base = synth.limb_package(ctl, seed=20240517)
+    pk = []
+    for j in range(int(os.environ.get("NJ", "115"))):
+        p = copy.deepcopy(base); p.t[(7 * j) % p.n_atm] += 1.0; pk.append(p)
+    timing("J-like (perturbed copies of one package)", ctl, tbl, pk)
 if os.environ.get("WITH_A", "0") == "1":
     ctl = synth.control_limb_example(); tbl = synth.make_tables(ctl)
     timing("A-like nd=2", ctl, tbl, [synth.limb_package(ctl, seed=20240517 + i) for i in range(32)])
