@@ -405,18 +405,39 @@ def main():
             if tstruct is None:
                 tstruct, keep = fill_tbl_struct(ref.tbl_t, tbl)
             kind, cores = "reference", ref.threads()
-            run1 = lambda p: ref.formod_tbl(cc, ref.make_atm(p), ref.make_obs(p), C.addressof(tstruct))
+
+            def run1(p):
+                o = ref.make_obs(p)
+                ref.formod_tbl(cc, ref.make_atm(p), o, C.addressof(tstruct))
+                return (np.ctypeslib.as_array(o.rad)[: p.n_rays, : ctl.nd].copy(), np.ctypeslib.as_array(o.tau)[: p.n_rays, : ctl.nd].copy())
         else:
             orc = refdrv.Oracle()
             kind, cores = "port", orc.threads()
-            run1 = lambda p: orc.formod(ctl, tbl, copy.deepcopy(p))
+
+            def run1(p):
+                q = copy.deepcopy(p)
+                orc.formod(ctl, tbl, q)
+                return q.rad, q.tau
         run1(sample_pk[0])  # warm-up
-        done, t0 = 0, time.perf_counter()
+        done, t0, cpu_out = 0, time.perf_counter(), []
         while done < len(sample_pk) and (time.perf_counter() - t0) < budget:
-            run1(sample_pk[done]); done += 1
+            cpu_out.append(run1(sample_pk[done])); done += 1
         el = time.perf_counter() - t0
         cpu = {"value": done * 1088 * ctl.nd / el, "unit": "ray-channels/s", "cores": cores, "kind": kind,
                "sample": f"{done} packages ({done*1088*ctl.nd} ray-channels) in {el:.1f} s, formod_CPU call sequence, serial ray tracing as in the reference"}
+        # parity of the measured run: the same packages as computed by the device path in the timed region (the CPU side is
+        # the checker here, SURVEY.md 8c tolerance: |d| <= 1e-6 |ref| + floor)
+        ctx.fetch_staged(pkgs)
+        n_cmp = min(done, len(pkgs))
+        e_rad = e_tau = 0.0
+        for i in range(n_cmp):
+            r_ref, t_ref = cpu_out[i]
+            e_rad = max(e_rad, float(np.max(np.abs(pkgs[i].rad - r_ref) / (np.abs(r_ref) + 1e-12 * np.max(np.abs(r_ref))))))
+            e_tau = max(e_tau, float(np.max(np.abs(pkgs[i].tau - t_ref) / (np.abs(t_ref) + 1e-12))))
+        cpu["parity"] = {"packages": n_cmp, "ray_channels": int(n_cmp * 1088 * ctl.nd), "max_rel_err_rad": e_rad, "max_rel_err_tau": e_tau,
+                         "tolerance": 1e-6, "ok": bool(e_rad <= 1e-6 and e_tau <= 1e-6)}
+        if not cpu["parity"]["ok"]:
+            raise SystemExit(f"bench: device results differ from the CPU {kind}: rad {e_rad:.3e}, tau {e_tau:.3e}")
 
     if rank == 0:
         out = {"metric": METRIC, "value": value, "unit": "ray-channels/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
