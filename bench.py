@@ -187,7 +187,8 @@ def reference_arm(args, jr):
         "impl": "reference", "metric": METRIC, "value": value, "unit": "ray-channels/s", "n_gpus": args.gpus, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": dt * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": "f64", "data": "synthetic",
-        "config": {"workload": WORKLOADS[args.config]["name"] + " (bounded CPU sample)", "packages_per_step": npk},
+        "config": {"workload": WORKLOADS[args.config]["name"], "packages_per_step": npk, "channels": ctl.nd, "gases": ctl.ng,
+                   "sample": "bounded CPU sample of the same workload: %d package(s) of 1088 rays per step" % npk},
         "cpu_baseline": {"value": value, "unit": "ray-channels/s", "cores": cores, "kind": kind, "sample": sample},
         "e2e": {"value": value, "unit": "ray-channels/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     })
