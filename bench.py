@@ -2,18 +2,24 @@
 """bench.py -- ray*channel radiances per second of the EGA forward model on N B200 GPUs (BASELINE.json metric).
 
   python bench.py --gpus 1 --steps K --warmup W             our CUDA path (default)
-  python -m torch.distributed.run --nproc-per-node N ... bench.py --gpus N ...   one rank per GPU, weak scaling
+  python -m torch.distributed.run --nproc-per-node N ... bench.py --gpus N ...   one rank per GPU, strong scaling
   python bench.py --impl reference ...                      the reference's own CPU path (oracle/_ref) on the host cores
 
-Workload ("config D" of BASELINE.json / SURVEY.md 8d): synthetic limb sounder, packages of 17 profiles x 64 rays
-(1088 rays, the capacity of one obs_t), 32 channels (785..816 cm^-1), 5 gases, CO2+H2O continua; 115 packages per GPU
-(8 GPUs x 115 = 920 packages = 1 000 960 rays, the "1M rays on 8xB200" case).  A step = one pass of the hot path
-(ray tracing -> column densities -> EGA/continua/Planck/accumulation) over the rank's packages.
+Workload = "config D" of BASELINE.json / SURVEY.md 8d, the configuration the metric is quoted on: synthetic limb sounder,
+920 packages of 17 profiles x 64 rays (1088 rays, the capacity of one obs_t) = 1 000 960 rays, 32 channels
+(785..816 cm^-1), 5 gases, CO2+H2O continua.  It fits one GPU, so N = 1 runs all of it and N ranks share it (contiguous
+package slices, "scaling": "strong").  A step = one pass of the hot path (ray tracing -> column densities ->
+EGA/continua/Planck/accumulation) over all packages.
 
-value : device path, inputs resident in HBM (jrb_run_staged), wall clock over K steps between synchronisations,
-        max over ranks.
-e2e   : the same through the reference-facing call jr_b200_formod_batch(ctl_t*, atm_t*[], obs_t*[]) with HOST structs:
-        packing + H2D + kernels + D2H + scatter inside the timed region (+ the NCCL gather of radiances for N > 1).
+e2e   : through the reference-facing C entry jr_b200_formod_batch(ctl_t*, atm_t*[], obs_t*[]) with the reference's HOST
+        structs, page-locked once (jr_b200_pin_packages): per step the device gathers the inputs from the structs over PCIe
+        and stores every ray's results into obs_t while the kernels run.  With N ranks the library itself holds the NCCL
+        communicator (jr_b200_dist_init: tables broadcast from rank 0), every rank owns a contiguous obs slice, and the obs_t
+        array lives in node-shared page-locked memory, so rank 0 has all radiances when the step ends.
+value : device path, inputs resident in HBM (jrb_run_staged on the same context), wall clock over K steps between
+        synchronisations, max over ranks.
+After the headline line is computed a short pass over "config E" (nadir, 128 channels, 8 gases, 4 continua) is measured the
+same way and embedded as extra.config_e.
 """
 import argparse
 import copy
@@ -32,14 +38,13 @@ import numpy as np
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 METRIC = "ray-channel radiances/sec"
-ND_D, NG_D = 32, 5
 
-# workloads of BASELINE.json; "d" is the one the metric is quoted on (the bench line), "e" is kept for profiling
+# workloads of BASELINE.json; "d" is the one the metric is quoted on (the bench line), "e" is embedded as extra.config_e
 WORKLOADS = {
-    "d": dict(name="config D: synthetic limb sounder, 17 profiles x 64 rays per package, 32 channels, 5 gases, CO2+H2O continua",
-              dims=(32, 5), packages=115),
-    "e": dict(name="config E: synthetic AIRS-like nadir, 16 profiles x 68 footprints per package, 128 channels, 8 gases, 4 continua",
-              dims=(128, 8), packages=58),
+    "d": dict(name="config D: synthetic limb sounder, 920 packages x (17 profiles x 64 rays) = 1 000 960 rays, 32 channels, 5 gases, CO2+H2O continua",
+              dims=(32, 5), packages=920),
+    "e": dict(name="config E: synthetic AIRS-like nadir, 460 packages x (16 profiles x 68 footprints) = 500 480 footprints, 128 channels, 8 gases, 4 continua",
+              dims=(128, 8), packages=460),
 }
 
 
@@ -58,6 +63,16 @@ def hbm_peak():
     return 6650.0, "fallback (B200_PROFILING.md)"
 
 
+def config_dict(args, workload, world):
+    """identical for our arm and the reference arm (the driver compares them)"""
+    W = WORKLOADS[workload]
+    total = args.packages if (workload == args.config and args.packages > 0) else W["packages"]
+    return {"workload": W["name"] if total == W["packages"] else W["name"] + f" -- REDUCED to {total} packages",
+            "packages_total": total, "rays_total": total * 1088, "channels": W["dims"][0], "gases": W["dims"][1],
+            "l2_policy": "inputs larger than L2 (line-of-sight records rewritten every step, 64 KB per ray; tables 0.2-1.3 GB)",
+            "parallelism": f"contiguous package slices over {world} GPU(s), one process per GPU, tables broadcast once by NCCL inside the library"}
+
+
 _REAL_STDOUT = None
 
 
@@ -66,6 +81,10 @@ def emit(obj):
     sys.stdout.flush()
     line = (json.dumps(obj) + "\n").encode()
     os.write(_REAL_STDOUT if _REAL_STDOUT is not None else 1, line)
+
+
+def log(*a):
+    print("[bench]", *a, file=sys.stderr, flush=True)
 
 
 class ClockSampler:
@@ -109,13 +128,6 @@ class ClockSampler:
                 "reasons": sorted(reasons), "samples": len(sm)}
 
 
-class CudaAlias:
-    """zero-copy torch view of device memory owned by the library (__cuda_array_interface__)"""
-
-    def __init__(self, ptr, nbytes):
-        self.__cuda_array_interface__ = {"shape": (nbytes,), "typestr": "|u1", "data": (ptr, False), "version": 2}
-
-
 def make_packages(jr, ctl, first, count, workload="d"):
     if workload == "e":
         return [jr.synth.nadir_package(ctl, seed=20240518 + first + i) for i in range(count)]
@@ -141,6 +153,43 @@ def fill_tbl_struct(tbl_t, tbl):
     return t, buf
 
 
+class _StructFiller:
+    """host structs of the reference (ctypes mirrors) from the flat containers"""
+
+    def __init__(self, ctl_t, atm_t, obs_t):
+        self.ctl_t, self.atm_t, self.obs_t = ctl_t, atm_t, obs_t
+
+    def ctl(self, ctl):
+        c = self.ctl_t()
+        c.ng, c.nd, c.nw = ctl.ng, ctl.nd, ctl.nw
+        for i, e in enumerate(ctl.emitters):
+            c.emitter[i].value = e.encode()
+        for i in range(ctl.nd):
+            c.nu[i] = ctl.nu[i]; c.window[i] = int(ctl.window[i])
+        c.hydz, c.ctm_co2, c.ctm_h2o, c.ctm_n2, c.ctm_o2 = ctl.hydz, ctl.ctm_co2, ctl.ctm_h2o, ctl.ctm_n2, ctl.ctm_o2
+        c.ip, c.refrac, c.rayds, c.raydz, c.write_bbt, c.formod, c.useGPU = ctl.ip, ctl.refrac, ctl.rayds, ctl.raydz, ctl.write_bbt, ctl.formod, 1
+        c.fov.value = b"-"
+        return c
+
+    def atm(self, pkg, a=None):
+        a = a if a is not None else self.atm_t()
+        n = pkg.n_atm
+        a.np = n
+        for name, src in (("time", pkg.atm_time), ("z", pkg.z), ("lon", pkg.lon), ("lat", pkg.lat), ("p", pkg.p), ("t", pkg.t)):
+            np.ctypeslib.as_array(getattr(a, name))[:n] = src
+        np.ctypeslib.as_array(a.q)[: pkg.ng, :n] = pkg.q[: pkg.ng]
+        np.ctypeslib.as_array(a.k)[: pkg.nw, :n] = pkg.k[: pkg.nw]
+        return a
+
+    def obs(self, pkg, o=None):
+        o = o if o is not None else self.obs_t()
+        n = pkg.n_rays
+        o.nr = n
+        for name in ("time", "obsz", "obslon", "obslat", "vpz", "vplon", "vplat"):
+            np.ctypeslib.as_array(getattr(o, name))[:n] = getattr(pkg, name)
+        return o
+
+
 def reference_arm(args, jr):
     """--impl reference: the reference's own CPU implementation (oracle/_ref, unmodified CPUdrivers.c path, OpenMP over
     all host cores) on a bounded sample of the same workload per step.  Falls back to the C restatement if oracle/_ref
@@ -150,12 +199,13 @@ def reference_arm(args, jr):
         return 0
     sys.path.insert(0, os.path.join(ROOT, "oracle"))
     import refdrv
+    ND, NG = WORKLOADS[args.config]["dims"]
     ctl = make_control(jr, args.config)
     tbl = jr.synth.make_tables(ctl)
     npk = args.ref_packages
     pkgs = make_packages(jr, ctl, 0, npk, args.config)
-    if refdrv.reference_available(ND_D, NG_D):
-        ref = refdrv.Reference(ND_D, NG_D)
+    if refdrv.reference_available(ND, NG):
+        ref = refdrv.Reference(ND, NG)
         ref.lib.jrref_set_threads(len(os.sched_getaffinity(0)))  # all host cores (torchrun exports OMP_NUM_THREADS=1)
         kind, cores = "reference", ref.threads()
         c = ref.make_ctl(ctl)
@@ -182,17 +232,322 @@ def reference_arm(args, jr):
     dt = (time.perf_counter() - t0) / args.steps
     rc = sum(p.n_rays for p in pkgs) * ctl.nd
     value = rc / dt
-    sample = f"{npk} package(s) = {rc} ray-channels per step"
+    sample = (f"the first {npk} of the workload's packages ({rc} ray-channels) per step, formod_CPU call sequence per package, "
+              f"{cores} OpenMP threads; the rate is per ray-channel and independent of the number of packages")
     emit({
         "impl": "reference", "metric": METRIC, "value": value, "unit": "ray-channels/s", "n_gpus": args.gpus, "steps": args.steps,
-        "warmup": args.warmup, "ms_per_step": dt * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-        "dtype": "f64", "data": "synthetic",
-        "config": {"workload": WORKLOADS[args.config]["name"], "packages_per_step": npk, "channels": ctl.nd, "gases": ctl.ng,
-                   "sample": "bounded CPU sample of the same workload: %d package(s) of 1088 rays per step" % npk},
+        "warmup": args.warmup, "ms_per_step": dt * 1e3, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
+        "dtype": "f64", "data": "synthetic", "config": config_dict(args, args.config, max(args.gpus, 1)),
         "cpu_baseline": {"value": value, "unit": "ray-channels/s", "cores": cores, "kind": kind, "sample": sample},
         "e2e": {"value": value, "unit": "ray-channels/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     })
     return 0
+
+
+class Dist:
+    """torch.distributed is the launcher plumbing only: barrier, max/sum over ranks, broadcast of the NCCL unique id"""
+
+    def __init__(self, torch, dist, rank, world, local):
+        self.torch, self.dist, self.rank, self.world, self.local = torch, dist, rank, world, local
+
+    def barrier(self):
+        self.torch.cuda.synchronize()
+        if self.dist:
+            self.dist.barrier()
+        self.torch.cuda.synchronize()
+
+    def reduce(self, x, op):
+        if not self.dist:
+            return x
+        t = self.torch.tensor([x], dtype=self.torch.float64, device="cuda")
+        self.dist.all_reduce(t, op=getattr(self.dist.ReduceOp, op))
+        return float(t.item())
+
+    def allmax(self, x):
+        return self.reduce(x, "MAX")
+
+    def allsum(self, x):
+        return self.reduce(x, "SUM")
+
+    def bcast_bytes(self, b, n):
+        if not self.dist:
+            return b
+        t = self.torch.zeros(n, dtype=self.torch.uint8, device="cuda")
+        if self.rank == 0:
+            t.copy_(self.torch.frombuffer(bytearray(b), dtype=self.torch.uint8))
+        self.dist.broadcast(t, 0)
+        return bytes(t.cpu().numpy().tobytes())
+
+
+def load_traffic(workload, packages_per_launch, kernel):
+    """DRAM traffic and the secondary pipe numbers of the dominant kernel come from one committed ncu --set full capture; they
+    are attached only when that capture is of this very launch (same workload, packages per launch and kernel), else null"""
+    p = os.path.join(ROOT, "profiles", "ega_traffic.json")
+    if not os.path.exists(p):
+        return None, None, None
+    try:
+        for e in json.load(open(p)).get("captures", []):
+            if e.get("workload") == workload and e.get("packages_per_launch") == packages_per_launch and e.get("kernel_contains", "") in kernel:
+                return e.get("dram_bytes_per_launch"), e.get("capture"), e.get("secondary")
+    except Exception:
+        pass
+    return None, None, None
+
+
+def run_workload(args, jr, D, workload, steps, warmup, cpu_seconds, with_gather_check):
+    """measures one workload: e2e through the drop-in C entry (host structs) and the device path on the same context"""
+    rank, world, local = D.rank, D.world, D.local
+    ND, NG = WORKLOADS[workload]["dims"]
+    cfg = config_dict(args, workload, world)
+    total_pk = cfg["packages_total"]
+    ctl = make_control(jr, workload)
+    ctl_t, atm_t, obs_t, tbl_t = jr.abi.structs(ND, NG)
+    io = _StructFiller(ctl_t, atm_t, obs_t)
+    core = jr.load_core()
+    lib = C.CDLL(os.path.join(ROOT, "jurassic-gpu_b200", "lib", f"libjurassic_b200_dropin_nd{ND}_ng{NG}.so"))
+    lib.jr_b200_init.argtypes = [C.c_void_p, C.c_void_p, C.c_int]
+    lib.jr_b200_dist_init.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_char_p, C.c_int, C.c_int]
+    lib.jr_b200_dist_unique_id.argtypes = [C.c_char_p]
+    lib.jr_b200_dist_gather.argtypes = [C.POINTER(C.c_void_p), C.POINTER(C.c_int), C.c_int, C.c_int]
+    lib.jr_b200_dist_gather.restype = None
+    lib.jr_b200_formod_batch.argtypes = [C.c_void_p, C.POINTER(C.c_void_p), C.POINTER(C.c_void_p), C.c_int]
+    lib.jr_b200_formod_batch.restype = None
+    lib.jr_b200_pin_packages.argtypes = [C.POINTER(C.c_void_p), C.POINTER(C.c_void_p), C.c_int]
+    lib.jr_b200_core_context.restype = C.c_void_p
+    lib.jr_b200_core_group.restype = C.c_void_p
+    lib.jr_b200_shared_alloc.argtypes = [C.c_char_p, C.c_size_t, C.c_int]
+    lib.jr_b200_shared_alloc.restype = C.c_void_p
+    lib.jr_b200_shared_free.argtypes = [C.c_char_p, C.c_void_p, C.c_size_t, C.c_int]
+    lib.jr_b200_shared_free.restype = None
+
+    # ---- tables: built on rank 0, packed once, broadcast by the library's own NCCL communicator ----
+    t_tab0 = time.perf_counter()
+    tbl = tstruct = keep = None
+    c = io.ctl(ctl)
+    c.MPIlocalrank = local
+    if rank == 0:
+        tbl = jr.synth.make_tables(ctl)
+        tstruct, keep = fill_tbl_struct(tbl_t, tbl)
+    if world == 1:
+        lib.jr_b200_init(C.addressof(c), C.addressof(tstruct), local)
+    else:
+        uid = C.create_string_buffer(128)
+        if rank == 0:
+            assert lib.jr_b200_dist_unique_id(uid) == 0, "NCCL unique id"
+        uid = C.create_string_buffer(D.bcast_bytes(uid.raw, 128), 128)
+        lib.jr_b200_dist_init(C.addressof(c), C.addressof(tstruct) if rank == 0 else None, rank, world, uid, local, 0)
+    t_tables = time.perf_counter() - t_tab0
+    gst = jr.abi.GroupStats()
+    core.jrb_group_get_stats(C.c_void_p(lib.jr_b200_core_group()), C.byref(gst))
+    ctx = jr.Context(handle=lib.jr_b200_core_context())  # the drop-in's own context (device 0 of its group, lane 0)
+
+    # ---- this rank's contiguous slice of packages; obs_t of ALL packages in node-shared page-locked memory when N > 1 ----
+    first, count = jr.shard.shard_range(total_pk, rank, world)
+    counts = [jr.shard.shard_range(total_pk, r, world)[1] for r in range(world)]
+    firsts = [jr.shard.shard_range(total_pk, r, world)[0] for r in range(world)]
+    pkgs = make_packages(jr, ctl, first, count, workload)
+    atms = [io.atm(p) for p in pkgs]
+    shm_name, shm_ptr, shm_bytes = None, None, 0
+    if world > 1:
+        shm_name = f"/jrb_bench_{os.environ.get('MASTER_PORT', '0')}_{workload}".encode()
+        shm_bytes = C.sizeof(obs_t) * total_pk
+        if rank == 0:
+            shm_ptr = lib.jr_b200_shared_alloc(shm_name, shm_bytes, 1)
+        D.barrier()
+        if rank != 0:
+            shm_ptr = lib.jr_b200_shared_alloc(shm_name, shm_bytes, 0)
+        assert shm_ptr, "node-shared page-locked memory could not be set up"
+        all_obs = [obs_t.from_address(shm_ptr + k * C.sizeof(obs_t)) for k in range(total_pk)]
+        obss = all_obs[first:first + count]
+        for p, o in zip(pkgs, obss):
+            io.obs(p, o)
+    else:
+        obss = [io.obs(p) for p in pkgs]
+        all_obs = obss
+    ap_ = (C.c_void_p * count)(*[C.addressof(x) for x in atms])
+    op_ = (C.c_void_p * count)(*[C.addressof(x) for x in obss])
+    assert lib.jr_b200_pin_packages(ap_, op_ if world == 1 else None, count) == 0, "page-locking the host structs failed"
+    D.barrier()
+
+    # ---- end to end through the drop-in call, host structs in and out ----
+    def e2e_step():
+        lib.jr_b200_formod_batch(C.addressof(c), ap_, op_, count)
+        if D.dist:  # rank 0 may read the node-shared obs_t array once every rank is through
+            D.dist.barrier()
+
+    for _ in range(max(warmup, 1)):
+        e2e_step()
+    sampler = ClockSampler(local)
+    gc.collect()
+    gc.disable()  # no collector pauses inside the timed regions
+    D.barrier()
+    sampler.start()
+    t0 = time.perf_counter()
+    per_step = []
+    for _ in range(steps):
+        ts = time.perf_counter()
+        e2e_step()
+        per_step.append((time.perf_counter() - ts) * 1e3)
+    D.barrier()
+    dt_e = D.allmax(time.perf_counter() - t0)
+    st = ctx.stats()
+    assert st["io_direct"] == 1, "the e2e path did not run in direct (page-locked) mode"
+    my_rc, my_rays, my_los = st["n_ray_channels"], st["n_rays"], st["n_los_points"]
+    tot_rc, tot_rays, tot_los = D.allsum(my_rc), D.allsum(my_rays), D.allsum(my_los)
+    e2e = {"value": tot_rc / (dt_e / steps), "unit": "ray-channels/s", "ms_per_step": dt_e / steps * 1e3,
+           "h2d_bytes_per_step": int(D.allsum(st["h2d_bytes"])), "d2h_bytes_per_step": int(D.allsum(st["d2h_bytes"])),
+           "ms_per_step_min": float(min(per_step)), "ms_per_step_max": float(max(per_step)),
+           "host_ms": {"stage": st["host_ms_stage"], "mask_scan": st["host_ms_pack"], "device": st["ms_total_device"], "scatter": st["host_ms_scatter"]},
+           "io": "direct: inputs gathered by the device from the page-locked atm_t/obs_t, results stored by the kernels into obs_t rows (no copy phase)",
+           "api": f"jr_b200_formod_batch(ctl_t*, atm_t*[], obs_t*[], n) with host structs (ND={ND}, NG={NG})" +
+                  ("; obs_t[] of all ranks in node-shared page-locked memory (jr_b200_shared_alloc), NCCL communicator of the library: %d ranks" % gst.nccl_nranks if world > 1 else "")}
+    first_rad = np.ctypeslib.as_array(obss[0].rad)[: pkgs[0].n_rays, : ctl.nd].copy()
+
+    # ---- device path on the same context: inputs resident in HBM ----
+    av = (jr.abi.AtmView * count)(*[jr.abi.atm_view_of(a, ND, NG) for a in atms])
+    ov = (jr.abi.ObsView * count)(*[jr.abi.obs_view_of(o, ND) for o in obss])
+    ctx.stage_views(count, av, ov)
+    for _ in range(max(warmup, 1)):
+        ctx.run_staged()
+    ctx.stage_views(count, av, ov)  # resets the accumulated kernel times
+    D.barrier()
+    t0 = time.perf_counter()
+    for _ in range(steps):
+        ctx.run_staged()  # synchronous: returns after the step's kernels have finished
+    D.barrier()
+    dt = D.allmax(time.perf_counter() - t0)
+    clocks = sampler.stop()
+    gc.enable()
+    st = ctx.stats()
+    launches = int(D.allsum(st["cum_launches"]))
+    ms_per_step = dt / steps * 1e3
+    value = tot_rc / (ms_per_step / 1e3)
+    if not np.array_equal(np.ctypeslib.as_array(obss[0].rad)[: pkgs[0].n_rays, : ctl.nd], first_rad, equal_nan=True):
+        raise SystemExit("bench: device-path results differ from the drop-in call's")
+
+    # ---- roofline of the dominant kernel (EGA), measured live with CUDA events on its stream ----
+    sbar = tot_los / max(tot_rays, 1)
+    bytes_rc = algorithmic_bytes_per_ray_channel(sbar, ctl.ng)
+    peak, peak_src = hbm_peak()
+    n_launch = max(int(st["cum_ega_launches"]), 1)
+    ega = st["cum_ms_ega"] / n_launch                       # average duration of one launch
+    rc_per_launch = my_rc * st["cum_runs"] / n_launch       # ray-channels one launch processes
+    achieved = rc_per_launch * bytes_rc / (ega / 1e3) / 1e9
+    kernel = (f"ega_fast_kernel<mask={st['ega_ctm_mask']}> ({st['ega_ngb']} gases, {st['ega_channels_per_warp']} channels per warp, "
+              f"{'lock-step' if st['ega_phase_lock'] else 'free-running'} CTAs)") if st["ega_kernel_variant"] else "ega_generic_kernel"
+    traffic, traffic_src, secondary = load_traffic(workload, count // max(st["n_chunks"], 1), kernel)
+    roofline = {"bound": "hbm", "kernel": kernel, "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                "traffic": traffic, "traffic_source": traffic_src, "secondary": secondary,
+                "peak_source": peak_src, "algorithmic_bytes_per_ray_channel": bytes_rc, "mean_los_points": sbar,
+                "ray_channels_per_launch": rc_per_launch, "launches_per_step": st["n_chunks"],
+                "kernel_ms": ega, "raytrace_ms_per_step": st["cum_ms_raytrace"] / max(st["cum_runs"], 1),
+                "kernel_share_of_step": st["cum_ms_ega"] / max(st["cum_runs"], 1) / ms_per_step}
+
+    # ---- parity of the measured data + CPU baseline: the reference's own CPU path on the host cores (rank 0) ----
+    cpu, parity = None, None
+    if rank == 0 and cpu_seconds > 0:
+        sys.path.insert(0, os.path.join(ROOT, "oracle"))
+        import refdrv
+        if refdrv.reference_available(ND, NG):
+            ref = refdrv.Reference(ND, NG)
+            ref.lib.jrref_set_threads(len(os.sched_getaffinity(0)))
+            cc = ref.make_ctl(ctl)
+            kind, cores = "reference", ref.threads()
+
+            def run1(p):
+                o = ref.make_obs(p)
+                ref.formod_tbl(cc, ref.make_atm(p), o, C.addressof(tstruct))
+                return (np.ctypeslib.as_array(o.rad)[: p.n_rays, : ctl.nd].copy(), np.ctypeslib.as_array(o.tau)[: p.n_rays, : ctl.nd].copy())
+        else:
+            orc = refdrv.Oracle()
+            kind, cores = "port", orc.threads()
+
+            def run1(p):
+                q = copy.deepcopy(p)
+                orc.formod(ctl, tbl, q)
+                return q.rad, q.tau
+        e_rad = e_tau = 0.0
+        n_cmp = 0
+
+        def compare(k_global, pkg, r_ref, t_ref):
+            nonlocal e_rad, e_tau, n_cmp
+            o = all_obs[k_global]
+            rad = np.ctypeslib.as_array(o.rad)[: pkg.n_rays, : ctl.nd]
+            tau = np.ctypeslib.as_array(o.tau)[: pkg.n_rays, : ctl.nd]
+            e_rad = max(e_rad, float(np.max(np.abs(rad - r_ref) / (np.abs(r_ref) + 1e-12 * np.max(np.abs(r_ref))))))
+            e_tau = max(e_tau, float(np.max(np.abs(tau - t_ref) / (np.abs(t_ref) + 1e-12))))
+            n_cmp += 1
+
+        if world == 1:
+            run1(pkgs[0])  # warm-up
+            done, el = 0, 0.0
+            while done < min(len(pkgs), 64) and el < cpu_seconds:
+                t0 = time.perf_counter()
+                r_ref, t_ref = run1(pkgs[done])
+                el += time.perf_counter() - t0  # (the comparison below is not part of the CPU timing)
+                compare(done, pkgs[done], r_ref, t_ref)
+                done += 1
+            cpu = {"value": done * 1088 * ctl.nd / el, "unit": "ray-channels/s", "cores": cores, "kind": kind,
+                   "sample": f"the first {done} packages of the workload ({done*1088*ctl.nd} ray-channels) in {el:.1f} s, formod_CPU call sequence per package, serial ray tracing as in the reference"}
+            where = f"the first {done} packages"
+        else:  # SURVEY.md section 7, T8 on the measured multi-rank data: package 0 of EVERY rank's slice against the reference
+            for r in range(world):
+                p = make_packages(jr, ctl, firsts[r], 1, workload)[0]
+                r_ref, t_ref = run1(p)
+                compare(firsts[r], p, r_ref, t_ref)
+            where = f"package 0 of each of the {world} ranks' slices, read on rank 0 from the node-shared obs_t array"
+        parity = {"packages": n_cmp, "ray_channels": int(n_cmp * 1088 * ctl.nd), "which": where, "against": kind, "max_rel_err_rad": e_rad,
+                  "max_rel_err_tau": e_tau, "tolerance": 1e-6, "ok": bool(e_rad <= 1e-6 and e_tau <= 1e-6)}
+
+    # ---- N > 1: the library's NCCL gather (ncclSend/ncclRecv of the compact device results to rank 0, then D2H + scatter into a
+    # private obs_t array on rank 0) must deliver the very bits the node-shared array holds; its cost is reported beside e2e ----
+    gather = None
+    if world > 1 and with_gather_check:
+        cnt = (C.c_int * world)(*counts)
+        priv, pp = None, None
+        if rank == 0:
+            priv = [obs_t() for _ in range(total_pk)]
+            for k in range(total_pk):
+                priv[k].nr = all_obs[k].nr
+            pp = (C.c_void_p * total_pk)(*[C.addressof(x) for x in priv])
+        lib.jr_b200_formod_batch(C.addressof(c), ap_, op_, count)
+        tg = []
+        for _ in range(2):
+            D.barrier()
+            t0 = time.perf_counter()
+            lib.jr_b200_dist_gather(pp, cnt, world, 0)
+            D.barrier()
+            tg.append(D.allmax(time.perf_counter() - t0) * 1e3)
+        core.jrb_group_get_stats(C.c_void_p(lib.jr_b200_core_group()), C.byref(gst))
+        if rank == 0:
+            same = True
+            for r in range(1, world):
+                for k in range(firsts[r], firsts[r] + counts[r]):
+                    same = same and np.array_equal(np.ctypeslib.as_array(priv[k].rad), np.ctypeslib.as_array(all_obs[k].rad), equal_nan=True) \
+                        and np.array_equal(np.ctypeslib.as_array(priv[k].tau), np.ctypeslib.as_array(all_obs[k].tau)) \
+                        and np.array_equal(np.ctypeslib.as_array(priv[k].tpz), np.ctypeslib.as_array(all_obs[k].tpz))
+            gather = {"ms": float(min(tg)), "bytes": int(gst.gather_bytes), "ms_scatter_on_root": float(gst.ms_gather_scatter),
+                      "bit_identical_to_shared_array": bool(same),
+                      "what": "jr_b200_dist_gather: grouped ncclSend/ncclRecv of rad/tau/tangent points to rank 0, page-locked D2H, scatter into obs_t[]"}
+            if parity is not None:
+                parity["nccl_gather_bit_identical"] = bool(same)
+                parity["ok"] = bool(parity["ok"] and same)
+            del priv
+
+    out = {"value": value, "ms_per_step": ms_per_step, "e2e": e2e, "roofline": roofline, "cpu_baseline": cpu, "parity": parity,
+           "gpu_launches": launches, "clocks": clocks, "config": cfg, "gather": gather,
+           "tables": {"seconds_incl_generation": t_tables, "blob_bytes": int(st["table_blob_bytes"]), "nccl_nranks": int(gst.nccl_nranks)},
+           "rays_per_gpu": int(my_rays), "los_chunks_per_step": int(st["n_chunks"])}
+    if parity is not None and not parity["ok"]:
+        emit({"error": "parity failed", "workload": workload, "parity": parity})
+        raise SystemExit(f"bench: device results differ from the CPU reference: {parity}")
+
+    lib.jr_b200_finalize()
+    core.jrb_host_unregister_all()
+    if shm_ptr:
+        D.barrier()
+        lib.jr_b200_shared_free(shm_name, shm_ptr, shm_bytes, 1 if rank == 0 else 0)
+    return out
 
 
 def main():
@@ -201,19 +556,16 @@ def main():
     ap.add_argument("--steps", type=int, default=5)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--config", default="d", choices=["d", "e"], help="workload: d = the bench line, e = nadir case (profiling)")
-    ap.add_argument("--packages", type=int, default=0, help="packages (of 1088 rays) per GPU (default: 115 for d, 58 for e)")
+    ap.add_argument("--config", default="d", choices=["d", "e"], help="workload of the bench line (d = the one the metric is quoted on)")
+    ap.add_argument("--packages", type=int, default=0, help="total packages of 1088 rays (default: the full workload, 920 for d); profiling only")
     ap.add_argument("--ref-packages", type=int, default=2, help="packages per step of the CPU reference arm")
     ap.add_argument("--cpu-baseline-seconds", type=float, default=15.0)
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-config-e", action="store_true", help="skip the embedded config E pass")
+    ap.add_argument("--e-packages", type=int, default=0, help="total packages of the embedded config E pass (default: all 460)")
+    ap.add_argument("--no-gather-check", action="store_true")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 0)
-    W = WORKLOADS[args.config]
-    if args.packages <= 0:
-        args.packages = W["packages"]
-    global ND_D, NG_D
-    ND_D, NG_D = W["dims"]
 
     # libraries (NCCL, the reference's printf's) write to stdout; keep fd 1 clean for the single JSON line
     sys.stdout.flush()
@@ -236,260 +588,32 @@ def main():
     if world > 1:
         import torch.distributed as dist
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    D = Dist(torch, dist, rank, world, local)
 
-    def barrier():
-        torch.cuda.synchronize()
-        if dist:
-            dist.barrier()
-        torch.cuda.synchronize()
-
-    ctl = make_control(jr, args.config)
-    ctx = jr.Context(local)  # raises without the CUDA library / a GPU: there is no fallback
-    ctx.set_control(ctl)
-
-    # ---- tables: packed once on rank 0, broadcast as one blob over NCCL/NVLink ----
-    tbl = None
-    t_tab0 = time.perf_counter()
+    cpu_s = 0.0 if args.no_cpu_baseline else args.cpu_baseline_seconds
+    res = run_workload(args, jr, D, args.config, args.steps, args.warmup, cpu_s, not args.no_gather_check)
+    extra = {}
+    if args.config == "d" and not args.no_config_e:
+        a2 = copy.copy(args)
+        a2.packages = args.e_packages
+        a2.config = "e"
+        e = run_workload(a2, jr, D, "e", 3, 1, min(cpu_s, 6.0), False)
+        extra["config_e"] = {"metric": METRIC, "value": e["value"], "ms_per_step": e["ms_per_step"], "e2e": e["e2e"], "roofline": e["roofline"],
+                             "parity": e["parity"], "cpu_baseline": e["cpu_baseline"], "clocks": e["clocks"], "config": e["config"],
+                             "steps": 3, "warmup": 1, "gpu_launches": e["gpu_launches"]}
     if rank == 0:
-        tbl = jr.synth.make_tables(ctl)
-        ctx.set_tables(tbl)
-    if dist:
-        n = torch.zeros(1, dtype=torch.int64, device="cuda")
-        if rank == 0:
-            ptr, nbytes = ctx.tables_blob()
-            n[0] = nbytes
-        dist.broadcast(n, 0)
-        nbytes = int(n.item())
-        if rank != 0:
-            ptr = ctx.tables_alloc_blob(nbytes)
-        blob = torch.as_tensor(CudaAlias(ptr, nbytes), device=torch.device("cuda", local))
-        dist.broadcast(blob, 0)
-        torch.cuda.synchronize()
-        if rank != 0:
-            ctx.tables_adopt_blob()
-    t_tables = time.perf_counter() - t_tab0
-
-    # ---- this rank's contiguous slice of packages (weak scaling: fixed work per GPU) ----
-    first, count = jr.shard.shard_range(world * args.packages, rank, world)
-    pkgs = make_packages(jr, ctl, first, count, args.config)
-    ctx.stage(pkgs)
-    for _ in range(max(args.warmup, 1) if args.warmup else 0):
-        ctx.run_staged()
-    sampler = ClockSampler(local)
-    gc.collect()
-    gc.disable()  # no collector pauses inside the timed regions
-    barrier()
-    sampler.start()
-    ega_ms, rt_ms, launches = [], [], 0
-    t0 = time.perf_counter()
-    for _ in range(args.steps):
-        ctx.run_staged()  # synchronous: returns after the step's kernels have finished
-        st = ctx.stats()
-        ega_ms.append(st["ms_ega"]); rt_ms.append(st["ms_raytrace"]); launches += st["n_kernel_launches"]
-    barrier()
-    dt = time.perf_counter() - t0
-    clocks = sampler.stop()
-    st = ctx.stats()
-    my_rc, my_rays, my_los = st["n_ray_channels"], st["n_rays"], st["n_los_points"]
-
-    def allmax(x):
-        if not dist:
-            return x
-        t = torch.tensor([x], dtype=torch.float64, device="cuda"); dist.all_reduce(t, op=dist.ReduceOp.MAX); return float(t.item())
-
-    def allsum(x):
-        if not dist:
-            return x
-        t = torch.tensor([x], dtype=torch.float64, device="cuda"); dist.all_reduce(t, op=dist.ReduceOp.SUM); return float(t.item())
-
-    dt = allmax(dt)
-    tot_rc, tot_rays, tot_los = allsum(my_rc), allsum(my_rays), allsum(my_los)
-    ms_per_step = dt / args.steps * 1e3
-    value = tot_rc / (ms_per_step / 1e3)
-
-    # ---- end-to-end through the reference-facing drop-in call, host structs in and out ----
-    e2e = None
-    tstruct = None
-    if not args.no_e2e:
-        lib = C.CDLL(os.path.join(ROOT, "jurassic-gpu_b200", "lib", f"libjurassic_b200_dropin_nd{ND_D}_ng{NG_D}.so"))
-        lib.jr_b200_init.argtypes = [C.c_void_p, C.c_void_p, C.c_int]
-        lib.jr_b200_formod_batch.argtypes = [C.c_void_p, C.POINTER(C.c_void_p), C.POINTER(C.c_void_p), C.c_int]
-        lib.jr_b200_core_context.restype = C.c_void_p
-        sys.path.insert(0, os.path.join(ROOT, "oracle"))
-        ctl_t, atm_t, obs_t, tbl_t = jr.abi.structs(ND_D, NG_D)
-        io = _StructFiller(jr, ctl_t, atm_t, obs_t)
-        c = io.ctl(ctl)
-        c.MPIlocalrank = local
-        if tbl is None:
-            tbl = jr.synth.make_tables(ctl)
-        tstruct, keep = fill_tbl_struct(tbl_t, tbl)
-        lib.jr_b200_init(C.addressof(c), C.addressof(tstruct), local)
-        atms = [io.atm(p) for p in pkgs]
-        obss = [io.obs(p) for p in pkgs]
-        ap_ = (C.c_void_p * len(pkgs))(*[C.addressof(x) for x in atms])
-        op_ = (C.c_void_p * len(pkgs))(*[C.addressof(x) for x in obss])
-        core = C.c_void_p(lib.jr_b200_core_context())
-        gather_buf = None
-
-        def e2e_step():
-            nonlocal gather_buf
-            lib.jr_b200_formod_batch(C.addressof(c), ap_, op_, len(pkgs))
-            if dist:  # radiances/transmittances of all ranks are gathered on rank 0 over NCCL
-                r, t, nr, nd = C.c_void_p(), C.c_void_p(), C.c_longlong(), C.c_int()
-                jr.load_core().jrb_staged_results(core, C.byref(r), C.byref(t), C.byref(nr), C.byref(nd))
-                nb = 2 * nr.value * nd.value * 8  # rad and tau are contiguous in the result buffer
-                mine = torch.as_tensor(CudaAlias(r.value, nb), device=torch.device("cuda", local))
-                if rank == 0 and gather_buf is None:
-                    gather_buf = [torch.empty(nb, dtype=torch.uint8, device="cuda") for _ in range(world)]
-                dist.gather(mine, gather_buf if rank == 0 else None, dst=0)
-                torch.cuda.synchronize()
-
-        for _ in range(min(args.warmup, 2)):
-            e2e_step()
-        barrier()
-        t0 = time.perf_counter()
-        per_step = []
-        for _ in range(args.steps):
-            ts = time.perf_counter()
-            e2e_step()
-            per_step.append((time.perf_counter() - ts) * 1e3)
-        t_loop = time.perf_counter() - t0
-        barrier()
-        dt_e = allmax(time.perf_counter() - t0)
-        if os.environ.get("JRB_DEBUG_TIMING"):
-            print(f"[bench] e2e steps {['%.1f' % x for x in per_step]} ms, loop {t_loop*1e3:.1f} ms, with barrier {dt_e*1e3:.1f} ms", file=sys.stderr)
-        cst = jr.abi.Stats()
-        jr.load_core().jrb_get_stats(core, C.byref(cst))
-        e2e = {"value": tot_rc / (dt_e / args.steps), "unit": "ray-channels/s", "ms_per_step": dt_e / args.steps * 1e3,
-               "h2d_bytes_per_step": int(cst.h2d_bytes), "d2h_bytes_per_step": int(cst.d2h_bytes),
-               "ms_per_step_min": float(min(per_step)), "ms_per_step_max": float(max(per_step)),
-               "host_ms": {"pack": cst.host_ms_pack, "h2d": cst.host_ms_h2d, "device": cst.ms_total_device, "d2h": cst.host_ms_d2h,
-                           "scatter": cst.host_ms_scatter},
-               "api": f"jr_b200_formod_batch(ctl_t*, atm_t*[], obs_t*[], n) with host structs (ND={ND_D}, NG={NG_D})"}
-        # spot check: the drop-in's host results equal the device-path results of the first package
-        ctx.fetch_staged(pkgs)
-        got = np.ctypeslib.as_array(obss[0].rad)[: pkgs[0].n_rays, : ctl.nd]
-        if not np.array_equal(got, pkgs[0].rad):
-            raise SystemExit("bench: drop-in results differ from the device path")
-        lib.jr_b200_finalize()
-
-    # ---- roofline of the dominant kernel (EGA) ----
-    sbar = tot_los / max(tot_rays, 1)
-    bytes_rc = algorithmic_bytes_per_ray_channel(sbar, ctl.ng)
-    peak, peak_src = hbm_peak()
-    ega = float(np.mean(ega_ms))
-    achieved = my_rc * bytes_rc / (ega / 1e3) / 1e9
-    traffic = None
-    tp = os.path.join(ROOT, "profiles", "ega_traffic.json")  # from one ncu --set full capture of this workload's launch
-    if os.path.exists(tp) and args.config == "d" and args.packages == WORKLOADS["d"]["packages"]:
-        try:
-            traffic = json.load(open(tp)).get("dram_bytes_per_launch")
-        except Exception:
-            traffic = None
-    roofline = {"bound": "hbm", "kernel": (f"ega_fast_kernel<mask={st['ega_ctm_mask']}> ({st['ega_ngb']} gases, {st['ega_channels_per_warp']} channels per warp, "
-                           f"{'lock-step' if st['ega_phase_lock'] else 'free-running'} CTAs)") if st["ega_kernel_variant"] else "ega_generic_kernel",
-                "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": traffic,
-                "peak_source": peak_src, "algorithmic_bytes_per_ray_channel": bytes_rc, "mean_los_points": sbar,
-                "kernel_ms": ega, "raytrace_ms": float(np.mean(rt_ms)), "kernel_share_of_step": ega / ms_per_step}
-
-    # ---- CPU baseline: the reference's own CPU path on the host cores (rank 0, N = 1 only) ----
-    cpu = None
-    if rank == 0 and world == 1 and not args.no_cpu_baseline:
-        sys.path.insert(0, os.path.join(ROOT, "oracle"))
-        import refdrv
-        budget = args.cpu_baseline_seconds
-        sample_pk = make_packages(jr, ctl, 0, 64, args.config)
-        if refdrv.reference_available(ND_D, NG_D):
-            ref = refdrv.Reference(ND_D, NG_D)
-            ref.lib.jrref_set_threads(len(os.sched_getaffinity(0)))
-            cc = ref.make_ctl(ctl)
-            if tstruct is None:
-                tstruct, keep = fill_tbl_struct(ref.tbl_t, tbl)
-            kind, cores = "reference", ref.threads()
-
-            def run1(p):
-                o = ref.make_obs(p)
-                ref.formod_tbl(cc, ref.make_atm(p), o, C.addressof(tstruct))
-                return (np.ctypeslib.as_array(o.rad)[: p.n_rays, : ctl.nd].copy(), np.ctypeslib.as_array(o.tau)[: p.n_rays, : ctl.nd].copy())
-        else:
-            orc = refdrv.Oracle()
-            kind, cores = "port", orc.threads()
-
-            def run1(p):
-                q = copy.deepcopy(p)
-                orc.formod(ctl, tbl, q)
-                return q.rad, q.tau
-        run1(sample_pk[0])  # warm-up
-        done, t0, cpu_out = 0, time.perf_counter(), []
-        while done < len(sample_pk) and (time.perf_counter() - t0) < budget:
-            cpu_out.append(run1(sample_pk[done])); done += 1
-        el = time.perf_counter() - t0
-        cpu = {"value": done * 1088 * ctl.nd / el, "unit": "ray-channels/s", "cores": cores, "kind": kind,
-               "sample": f"{done} packages ({done*1088*ctl.nd} ray-channels) in {el:.1f} s, formod_CPU call sequence, serial ray tracing as in the reference"}
-        # parity of the measured run: the same packages as computed by the device path in the timed region (the CPU side is
-        # the checker here, SURVEY.md 8c tolerance: |d| <= 1e-6 |ref| + floor)
-        ctx.fetch_staged(pkgs)
-        n_cmp = min(done, len(pkgs))
-        e_rad = e_tau = 0.0
-        for i in range(n_cmp):
-            r_ref, t_ref = cpu_out[i]
-            e_rad = max(e_rad, float(np.max(np.abs(pkgs[i].rad - r_ref) / (np.abs(r_ref) + 1e-12 * np.max(np.abs(r_ref))))))
-            e_tau = max(e_tau, float(np.max(np.abs(pkgs[i].tau - t_ref) / (np.abs(t_ref) + 1e-12))))
-        cpu["parity"] = {"packages": n_cmp, "ray_channels": int(n_cmp * 1088 * ctl.nd), "max_rel_err_rad": e_rad, "max_rel_err_tau": e_tau,
-                         "tolerance": 1e-6, "ok": bool(e_rad <= 1e-6 and e_tau <= 1e-6)}
-        if not cpu["parity"]["ok"]:
-            raise SystemExit(f"bench: device results differ from the CPU {kind}: rad {e_rad:.3e}, tau {e_tau:.3e}")
-
-    if rank == 0:
-        out = {"metric": METRIC, "value": value, "unit": "ray-channels/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
-               "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64",
-               "data": "synthetic",
-               "config": {"workload": W["name"],
-                          "packages_per_gpu": args.packages, "rays_per_gpu": int(my_rays), "rays_total": int(tot_rays), "channels": ctl.nd,
-                          "gases": ctl.ng, "l2_policy": "inputs larger than L2 (LOS records rewritten every step: %.1f GB)" % (my_los * 8 * (10 + 5 * ctl.ng) / 1e9),
-                          "parallelism": f"rays sharded over {world} GPU(s), tables broadcast once ({t_tables:.2f} s incl. generation)"},
-               "clocks": clocks, "e2e": e2e, "gpu_launches": int(launches), "roofline": roofline, "cpu_baseline": cpu}
+        out = {"metric": METRIC, "value": res["value"], "unit": "ray-channels/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+               "ms_per_step": res["ms_per_step"], "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f64",
+               "data": "synthetic", "config": res["config"], "clocks": res["clocks"], "e2e": res["e2e"], "gpu_launches": res["gpu_launches"],
+               "roofline": res["roofline"], "cpu_baseline": res["cpu_baseline"], "parity": res["parity"],
+               "extra": dict(extra, gather=res["gather"], tables=res["tables"], rays_per_gpu=res["rays_per_gpu"],
+                             los_chunks_per_step=res["los_chunks_per_step"])}
+        if out["cpu_baseline"] is not None and res["parity"] is not None:
+            out["cpu_baseline"]["parity"] = res["parity"]
         emit(out)
-    ctx.close()
     if dist:
         dist.destroy_process_group()
     return 0
-
-
-class _StructFiller:
-    """host structs of the reference (ctypes mirrors) from the flat containers"""
-
-    def __init__(self, jr, ctl_t, atm_t, obs_t):
-        self.ctl_t, self.atm_t, self.obs_t = ctl_t, atm_t, obs_t
-
-    def ctl(self, ctl):
-        c = self.ctl_t()
-        c.ng, c.nd, c.nw = ctl.ng, ctl.nd, ctl.nw
-        for i, e in enumerate(ctl.emitters):
-            c.emitter[i].value = e.encode()
-        for i in range(ctl.nd):
-            c.nu[i] = ctl.nu[i]; c.window[i] = int(ctl.window[i])
-        c.hydz, c.ctm_co2, c.ctm_h2o, c.ctm_n2, c.ctm_o2 = ctl.hydz, ctl.ctm_co2, ctl.ctm_h2o, ctl.ctm_n2, ctl.ctm_o2
-        c.ip, c.refrac, c.rayds, c.raydz, c.write_bbt, c.formod, c.useGPU = ctl.ip, ctl.refrac, ctl.rayds, ctl.raydz, ctl.write_bbt, ctl.formod, 1
-        return c
-
-    def atm(self, pkg):
-        a = self.atm_t()
-        n = pkg.n_atm
-        a.np = n
-        for name, src in (("time", pkg.atm_time), ("z", pkg.z), ("lon", pkg.lon), ("lat", pkg.lat), ("p", pkg.p), ("t", pkg.t)):
-            np.ctypeslib.as_array(getattr(a, name))[:n] = src
-        np.ctypeslib.as_array(a.q)[: pkg.ng, :n] = pkg.q[: pkg.ng]
-        np.ctypeslib.as_array(a.k)[: pkg.nw, :n] = pkg.k[: pkg.nw]
-        return a
-
-    def obs(self, pkg):
-        o = self.obs_t()
-        n = pkg.n_rays
-        o.nr = n
-        for name in ("time", "obsz", "obslon", "obslat", "vpz", "vplon", "vplat"):
-            np.ctypeslib.as_array(getattr(o, name))[:n] = getattr(pkg, name)
-        return o
 
 
 if __name__ == "__main__":

@@ -99,6 +99,11 @@ typedef struct {
   int n_chunks, pipelined; /* LOS chunks of the last run; 1 if the tracer of chunk c+1 ran beside the EGA kernel of chunk c */
   int ega_phase_lock;      /* 1 if the specialised kernel ran its CTAs in lock step (rays of equal length) */
   int ega_channels_per_warp; /* channels of a ray handled by one warp of the specialised kernel (32, or fewer = several rays per warp) */
+  int io_direct;           /* 1: inputs were gathered from / results stored into the caller's page-locked structs (jrb_host_register) */
+  float host_ms_stage;     /* wall clock of the whole staging phase (tables of addresses, packing or input gather, allocation) */
+  /* accumulated over all runs since the batch was staged (CUDA-event times; one EGA launch per run and LOS chunk) */
+  long long cum_runs, cum_launches, cum_ega_launches;
+  double cum_ms_ega, cum_ms_raytrace, cum_ms_device;
 } jrb_stats;
 
 typedef struct jrb_context jrb_context;
@@ -107,6 +112,8 @@ int jrb_device_count(void);
 int jrb_create(jrb_context **out, int device);
 void jrb_destroy(jrb_context *ctx);
 const char *jrb_last_error(const jrb_context *ctx); /* ctx may be NULL: last error of jrb_create */
+
+int jrb_context_device(const jrb_context *ctx);
 
 int jrb_set_control(jrb_context *ctx, const jrb_ctl_view *ctl);
 /* pack tbl_t into per-(gas,channel) slabs and upload (requires jrb_set_control first) */
@@ -124,6 +131,22 @@ int jrb_tables_upload_blob(jrb_context *ctx, const void *host_blob, size_t nbyte
 int jrb_tables_blob(jrb_context *ctx, void **dev_ptr, size_t *nbytes);
 int jrb_tables_alloc_blob(jrb_context *ctx, size_t nbytes, void **dev_ptr); /* receiver side */
 int jrb_tables_adopt_blob(jrb_context *ctx);                                 /* after the blob has been filled */
+
+/* lanes: ctx (same device as `from`, control already set) uses the packed tables of `from` -- no copy, shared ownership */
+int jrb_tables_share(jrb_context *ctx, jrb_context *from);
+/* upper limit of this context's line-of-sight scratch in GB (0: JRB_LOS_GB or the default of 72); larger batches are chunked */
+int jrb_set_los_limit_gb(jrb_context *ctx, double gb);
+
+/* Page-locking of caller memory (process-wide registry; replaces nothing in the reference, which copies whole structs
+ * from pageable memory, src/GPUdrivers.cu:222-223,244).  A batch whose atm/obs arrays ALL lie in registered memory runs in
+ * "direct" mode: a staging kernel gathers the inputs straight from the caller's structs over PCIe and the compute kernels
+ * store every ray's rad/tau row and tangent point straight into the caller's obs rows while they run -- no host-side
+ * packing, no copy phase, no scatter.  Anything else runs "staged" (pinned staging buffers, same results).  The caller
+ * must keep registered memory mapped until jrb_host_unregister_all(); blocks may overlap or share pages. */
+int jrb_host_register(void *ptr, size_t bytes);
+int jrb_host_unregister(void *ptr, size_t bytes); /* the registered ranges lying completely inside the block */
+int jrb_host_unregister_all(void);
+int jrb_host_is_registered(const void *ptr, size_t bytes);
 
 /* Native ingest of the reference's ASCII inputs "<tblbase>_<nu %.4f>_<GAS>.tab" / "<tblbase>_<nu %.4f>.filt" with the
  * acceptance rules of init_tbl (src/jurassic.c:311-416, 612-667), into compact host arrays (no 8.8 GB tbl_t).  Host only.
@@ -173,8 +196,59 @@ int jrb_staged_results(jrb_context *ctx, double **rad_dev, double **tau_dev, lon
 int jrb_debug_los(jrb_context *ctx, long long ray, double *out, int max_doubles, int *np_out, int *rec_doubles,
                   double *tsurf_out);
 
+/* the compact device results of the last run as one block: rad[R][nd], tau[R][nd], tpz[R], tplon[R], tplat[R] */
+int jrb_staged_results_blob(jrb_context *ctx, void **dev, size_t *bytes, long long *n_rays, int *nd);
+
 int jrb_get_stats(const jrb_context *ctx, jrb_stats *out);
 const char *jrb_version(void);
+
+/* ---- devices and lanes behind one handle (jrb_group.cu) -----------------------------------------------------------------
+ * Replaces the lane hand-out and the per-device loop of the reference (src/GPUdrivers.cu:275-358; device = ctl->MPIlocalrank
+ * :288, `omp parallel for num_threads(numDevices)` :351-357).  A group owns ndev devices x nlanes contexts:
+ *   - concurrent callers (host threads calling with one package each) get a lane each, their kernels overlap on the device;
+ *   - a large batch is cut into contiguous package slices, one per device, processed by one host thread per device; every
+ *     device stores its results straight into the caller's obs rows;
+ *   - the packed tables are broadcast once with NCCL (ncclCommInitAll + ncclBroadcast; NCCL is loaded at run time and only
+ *     needed when ndev > 1 or in rank style). */
+typedef struct jrb_group jrb_group;
+typedef struct {
+  int ndev, nlanes, n_slices; /* n_slices: devices the last batch was cut over */
+  int nccl_nranks;            /* ranks of the NCCL communicator the tables were broadcast over (0: one device, no NCCL) */
+  int dist_rank, dist_nranks; /* rank style (jrb_group_dist_init), else -1 / 0 */
+  long long table_bytes, gather_bytes;
+  float ms_tables, ms_last_call, ms_gather, ms_gather_scatter;
+} jrb_group_stats;
+
+/* ndev <= 0: all visible devices; devices == NULL: ordinals 0..ndev-1; nlanes in 1..8 */
+int jrb_group_create(jrb_group **out, int ndev, const int *devices, int nlanes);
+void jrb_group_destroy(jrb_group *g);
+const char *jrb_group_last_error(const jrb_group *g);
+int jrb_group_size(const jrb_group *g, int *ndev, int *nlanes);
+jrb_context *jrb_group_context(jrb_group *g, int dev, int lane); /* for tests / introspection */
+int jrb_group_set_control(jrb_group *g, const jrb_ctl_view *ctl);
+int jrb_group_set_fov(jrb_group *g, int n, const double *dz, const double *w); /* shape used by calls with use_fov != 0 */
+/* pack once, upload to the first device, ncclBroadcast to the others, share among the lanes (ctl may be NULL: keep) */
+int jrb_group_set_tables(jrb_group *g, const jrb_ctl_view *ctl, const jrb_tbl_view *tbl);
+/* jrb_formod_batch over the group; ctl == NULL: the control set last; thread safe */
+int jrb_group_formod_batch(jrb_group *g, const jrb_ctl_view *ctl, int npk, const jrb_atm_view *atm, const jrb_obs_view *obs,
+                           int use_fov);
+int jrb_group_get_stats(jrb_group *g, jrb_group_stats *out);
+
+/* Rank style: one process per GPU (MPI / torchrun launchers).  The launcher distributes the 128-byte id made by
+ * jrb_dist_unique_id on one rank; each process has a group of ONE device.
+ *   jrb_group_dist_set_tables : the root passes the tables, everybody receives the packed blob by ncclBroadcast;
+ *   jrb_group_dist_gather     : every rank sends the compact device results of its last batch to the root, which lands
+ *                               them in the obs views of all packages (counts[r] = packages of rank r, rank order). */
+int jrb_dist_unique_id(void *id, size_t capacity /* >= 128 */);
+int jrb_group_dist_init(jrb_group *g, int rank, int nranks, const void *id, size_t id_bytes);
+int jrb_group_dist_set_tables(jrb_group *g, const jrb_ctl_view *ctl, const jrb_tbl_view *tbl /* root only */, int root);
+int jrb_group_dist_gather(jrb_group *g, int root, const int *counts, int npk_all, const jrb_obs_view *obs_all /* root only */);
+
+/* Node-shared page-locked memory (POSIX shm + jrb_host_register): obs_t blocks placed here by all ranks of a node are
+ * written by every rank's GPU over its own PCIe link while its kernels run, so the root sees all results without any
+ * gather step.  create != 0 makes the segment, else it is attached. */
+int jrb_shared_alloc(const char *name, size_t bytes, int create, void **out);
+int jrb_shared_free(const char *name, void *ptr, size_t bytes, int unlink_it);
 
 #ifdef __cplusplus
 }

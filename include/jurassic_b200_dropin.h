@@ -53,6 +53,38 @@ size_t jr_b200_kernel_dims(ctl_t const *ctl, atm_t *atm, obs_t const *obs, size_
  * convolution running on the device on the resident results.  formod_GPU itself ignores ctl->fov, like formod(). */
 void jr_b200_formod_fov_batch(ctl_t const *ctl, atm_t *const atm[], obs_t *const obs[], int npackages);
 
+/* ---- more than one GPU ---------------------------------------------------------------------------------------------------
+ * The reference only pretends (device = ctl->MPIlocalrank, never set, src/GPUdrivers.cu:288; per-device loop over pointers of
+ * one device, :344-358).  Two real forms here (SURVEY.md 8b "needed extension", 8e):
+ *
+ * (1) one process, all GPUs: jr_b200_init_multi() makes one context set and one host thread per device, packs the tables
+ *     once and broadcasts them with NCCL (ncclCommInitAll + ncclBroadcast); jr_b200_formod_batch() then cuts every batch
+ *     into contiguous package slices, one per device, and each device stores its results straight into the caller's obs_t
+ *     rows.  ndevices <= 0: all visible devices.  Returns the number of devices in use.
+ *
+ * (2) one process per GPU (MPI or torchrun launchers): the launcher distributes the 128-byte id from
+ *     jr_b200_dist_unique_id() of one rank; jr_b200_dist_init() joins the NCCL communicator and receives the packed tables
+ *     from `root` (the only rank that passes tbl) by ncclBroadcast; every rank then calls jr_b200_formod_batch() on its own
+ *     contiguous slice of packages; jr_b200_dist_gather() finally lands all radiances, transmittances and tangent points in
+ *     the root's obs_t array (obs_all: root only, all packages in rank order; counts[r] = packages of rank r). */
+int jr_b200_init_multi(ctl_t const *ctl, tbl_t const *tbl, int ndevices);
+int jr_b200_dist_unique_id(char id[128]);
+int jr_b200_dist_init(ctl_t const *ctl, tbl_t const *tbl, int rank, int nranks, char const id[128], int device, int root);
+void jr_b200_dist_gather(obs_t *const obs_all[], int const counts[], int nranks, int root);
+
+/* ---- page-locked caller structs -------------------------------------------------------------------------------------------
+ * The reference copies whole atm_t / obs_t structs from pageable memory on every call (src/GPUdrivers.cu:222-223,244).
+ * Callers that keep their packages alive across calls (retrieval iterations, orbit loops) can page-lock them once: batches
+ * whose packages are ALL pinned run in "direct" mode -- the device gathers the populated prefixes of the inputs straight
+ * from the structs and stores every ray's results straight into obs->rad / obs->tau / obs->tp* while the kernels run, with
+ * no host-side packing, copy phase or scatter.  The structs must stay allocated until jr_b200_unpin_all().
+ * jr_b200_shared_alloc(): the same for memory shared by the processes of a node (POSIX shm): obs_t arrays placed there are
+ * filled by every rank's GPU over its own PCIe link, so the root rank sees all results without a gather step. */
+int jr_b200_pin_packages(atm_t *const atm[], obs_t *const obs[], int npackages);
+void jr_b200_unpin_all(void);
+void *jr_b200_shared_alloc(char const *name, size_t bytes, int create);
+void jr_b200_shared_free(char const *name, void *ptr, size_t bytes, int unlink_it);
+
 void jr_b200_finalize(void);
 
 /* introspection for tests: dimension macros this layer was compiled with: {ND, NG, NP, NR, NW, NLOS, TBLNP, TBLNT,
@@ -60,6 +92,8 @@ void jr_b200_finalize(void);
 void jr_b200_dims(int dims[11], long long sizes[4]);
 /* the core context behind the drop-in (struct jrb_context*, see jurassic_b200.h), NULL before initialisation */
 void *jr_b200_core_context(void);
+/* the device/lane group behind the drop-in (struct jrb_group*), NULL before initialisation */
+void *jr_b200_core_group(void);
 
 #ifdef __cplusplus
 }

@@ -5,6 +5,6 @@ thin host-side mirror used by tests and bench.py (ctypes bindings, synthetic wor
 The directory name contains a hyphen, so import it with importlib.import_module("jurassic-gpu_b200").
 """
 from . import abi, core, shard, synth  # noqa: F401
-from .core import Context, Control, JrbError, Package, Tables, load_core  # noqa: F401
+from .core import Context, Control, Group, JrbError, Package, Tables, load_core  # noqa: F401
 
-__all__ = ["abi", "core", "synth", "Context", "Control", "Package", "Tables", "JrbError", "load_core"]
+__all__ = ["abi", "core", "synth", "Context", "Control", "Group", "Package", "Tables", "JrbError", "load_core"]

@@ -90,4 +90,38 @@ class Stats(C.Structure):
                 ("d2h_bytes", C.c_longlong), ("ega_kernel_variant", C.c_int), ("ega_ngb", C.c_int),
                 ("ega_ctm_mask", C.c_int), ("table_blob_bytes", C.c_longlong), ("host_ms_pack", C.c_float),
                 ("host_ms_h2d", C.c_float), ("host_ms_d2h", C.c_float), ("host_ms_scatter", C.c_float),
-                ("n_chunks", C.c_int), ("pipelined", C.c_int), ("ega_phase_lock", C.c_int), ("ega_channels_per_warp", C.c_int)]
+                ("n_chunks", C.c_int), ("pipelined", C.c_int), ("ega_phase_lock", C.c_int), ("ega_channels_per_warp", C.c_int),
+                ("io_direct", C.c_int), ("host_ms_stage", C.c_float), ("cum_runs", C.c_longlong), ("cum_launches", C.c_longlong),
+                ("cum_ega_launches", C.c_longlong), ("cum_ms_ega", C.c_double), ("cum_ms_raytrace", C.c_double),
+                ("cum_ms_device", C.c_double)]
+
+
+class GroupStats(C.Structure):
+    _fields_ = [("ndev", C.c_int), ("nlanes", C.c_int), ("n_slices", C.c_int), ("nccl_nranks", C.c_int), ("dist_rank", C.c_int),
+                ("dist_nranks", C.c_int), ("table_bytes", C.c_longlong), ("gather_bytes", C.c_longlong), ("ms_tables", C.c_float),
+                ("ms_last_call", C.c_float), ("ms_gather", C.c_float), ("ms_gather_scatter", C.c_float)]
+
+
+def atm_view_of(a, ND, NG):
+    """AtmView onto a ctypes atm_t (no copy)"""
+    cls = type(a)
+    base = C.addressof(a)
+    v = AtmView()
+    v.np = a.np
+    for name in ("time", "z", "lon", "lat", "p", "t"):
+        setattr(v, name, C.cast(base + getattr(cls, name).offset, c_double_p))
+    v.q = C.cast(base + cls.q.offset, c_double_p); v.q_stride = NP
+    v.k = C.cast(base + cls.k.offset, c_double_p); v.k_stride = NP
+    return v
+
+
+def obs_view_of(o, ND):
+    """ObsView onto a ctypes obs_t (no copy)"""
+    cls = type(o)
+    base = C.addressof(o)
+    v = ObsView()
+    v.nr = o.nr
+    for name in ("time", "obsz", "obslon", "obslat", "vpz", "vplon", "vplat", "tpz", "tplon", "tplat", "rad", "tau"):
+        setattr(v, name, C.cast(base + getattr(cls, name).offset, c_double_p))
+    v.row_stride, v.nd_reset = ND, ND
+    return v

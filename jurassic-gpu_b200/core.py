@@ -75,6 +75,40 @@ def load_core():
     lib.jrb_staged_results.argtypes = [vp, C.POINTER(vp), C.POINTER(vp), C.POINTER(C.c_longlong), C.POINTER(C.c_int)]
     lib.jrb_debug_los.argtypes = [vp, C.c_longlong, abi.c_double_p, C.c_int, abi.c_int_p, abi.c_int_p, abi.c_double_p]
     lib.jrb_get_stats.argtypes = [vp, C.POINTER(abi.Stats)]
+    # lanes, page-locked caller memory, device groups, rank-style NCCL (include/jurassic_b200.h, second half)
+    lib.jrb_context_device.argtypes = [vp]
+    lib.jrb_tables_share.argtypes = [vp, vp]
+    lib.jrb_set_los_limit_gb.argtypes = [vp, C.c_double]
+    lib.jrb_host_register.argtypes = [C.c_void_p, C.c_size_t]
+    lib.jrb_host_unregister.argtypes = [C.c_void_p, C.c_size_t]
+    lib.jrb_host_unregister_all.argtypes = []
+    lib.jrb_host_is_registered.argtypes = [C.c_void_p, C.c_size_t]
+    lib.jrb_staged_results_blob.argtypes = [vp, C.POINTER(vp), C.POINTER(C.c_size_t), C.POINTER(C.c_longlong), abi.c_int_p]
+    lib.jrb_group_create.argtypes = [C.POINTER(vp), C.c_int, abi.c_int_p, C.c_int]
+    lib.jrb_group_destroy.argtypes = [vp]
+    lib.jrb_group_destroy.restype = None
+    lib.jrb_group_last_error.argtypes = [vp]
+    lib.jrb_group_last_error.restype = C.c_char_p
+    lib.jrb_group_size.argtypes = [vp, abi.c_int_p, abi.c_int_p]
+    lib.jrb_group_context.argtypes = [vp, C.c_int, C.c_int]
+    lib.jrb_group_context.restype = vp
+    lib.jrb_group_set_control.argtypes = [vp, C.POINTER(abi.CtlView)]
+    lib.jrb_group_set_fov.argtypes = [vp, C.c_int, abi.c_double_p, abi.c_double_p]
+    lib.jrb_group_set_tables.argtypes = [vp, C.POINTER(abi.CtlView), C.POINTER(abi.TblView)]
+    lib.jrb_group_formod_batch.argtypes = [vp, C.POINTER(abi.CtlView), C.c_int, C.POINTER(abi.AtmView), C.POINTER(abi.ObsView), C.c_int]
+    lib.jrb_group_get_stats.argtypes = [vp, C.POINTER(abi.GroupStats)]
+    lib.jrb_dist_unique_id.argtypes = [C.c_void_p, C.c_size_t]
+    lib.jrb_group_dist_init.argtypes = [vp, C.c_int, C.c_int, C.c_void_p, C.c_size_t]
+    lib.jrb_group_dist_set_tables.argtypes = [vp, C.POINTER(abi.CtlView), C.POINTER(abi.TblView), C.c_int]
+    lib.jrb_group_dist_gather.argtypes = [vp, C.c_int, abi.c_int_p, C.c_int, C.POINTER(abi.ObsView)]
+    lib.jrb_shared_alloc.argtypes = [C.c_char_p, C.c_size_t, C.c_int, C.POINTER(vp)]
+    lib.jrb_shared_free.argtypes = [C.c_char_p, C.c_void_p, C.c_size_t, C.c_int]
+    for f in ("jrb_context_device", "jrb_tables_share", "jrb_set_los_limit_gb", "jrb_host_register", "jrb_host_unregister",
+              "jrb_host_unregister_all", "jrb_host_is_registered", "jrb_staged_results_blob", "jrb_group_create", "jrb_group_size",
+              "jrb_group_set_control", "jrb_group_set_fov", "jrb_group_set_tables", "jrb_group_formod_batch", "jrb_group_get_stats",
+              "jrb_dist_unique_id", "jrb_group_dist_init", "jrb_group_dist_set_tables", "jrb_group_dist_gather", "jrb_shared_alloc",
+              "jrb_shared_free"):
+        getattr(lib, f).restype = C.c_int
     for f in ("jrb_create", "jrb_set_control", "jrb_set_tables", "jrb_tables_blob", "jrb_tables_alloc_blob",
               "jrb_tables_adopt_blob", "jrb_set_kernel_variant", "jrb_set_fov", "jrb_formod_batch", "jrb_stage", "jrb_run_staged",
               "jrb_fetch_staged", "jrb_staged_results", "jrb_debug_los", "jrb_get_stats"):
@@ -88,7 +122,13 @@ EXPORTED_SYMBOLS = ["jrb_binary_tables_filename", "jrb_binary_tables_size", "jrb
                     "jrb_tables_pack_host", "jrb_tables_upload_blob", "jrb_tables_pack_info", "jrb_version", "jrb_device_count", "jrb_create", "jrb_destroy", "jrb_last_error",
                     "jrb_set_control", "jrb_set_tables", "jrb_tables_blob", "jrb_tables_alloc_blob",
                     "jrb_tables_adopt_blob", "jrb_set_kernel_variant", "jrb_set_fov", "jrb_formod_batch", "jrb_stage",
-                    "jrb_run_staged", "jrb_fetch_staged", "jrb_staged_results", "jrb_debug_los", "jrb_get_stats"]
+                    "jrb_run_staged", "jrb_fetch_staged", "jrb_staged_results", "jrb_debug_los", "jrb_get_stats",
+                    "jrb_context_device", "jrb_tables_share", "jrb_set_los_limit_gb", "jrb_host_register", "jrb_host_unregister",
+                    "jrb_host_unregister_all", "jrb_host_is_registered", "jrb_staged_results_blob", "jrb_group_create",
+                    "jrb_group_destroy", "jrb_group_last_error", "jrb_group_size", "jrb_group_context", "jrb_group_set_control",
+                    "jrb_group_set_fov", "jrb_group_set_tables", "jrb_group_formod_batch", "jrb_group_get_stats",
+                    "jrb_dist_unique_id", "jrb_group_dist_init", "jrb_group_dist_set_tables", "jrb_group_dist_gather",
+                    "jrb_shared_alloc", "jrb_shared_free"]
 
 
 def _dp(a):
@@ -347,28 +387,36 @@ class Package:
 class Context:
     """One GPU context of the core library."""
 
-    def __init__(self, device=0):
+    def __init__(self, device=0, handle=None):
         self.lib = load_core()
+        self._keep = []
+        self.owned = handle is None
+        if handle is not None:  # a context owned by somebody else (a lane of a group, the drop-in layer's context)
+            self.h = C.c_void_p(handle)
+            return
         self.h = C.c_void_p()
         rc = self.lib.jrb_create(C.byref(self.h), device)
         if rc != 0:
             raise JrbError(f"jrb_create failed ({rc}): {self.lib.jrb_last_error(None).decode()}")
-        self._keep = []
 
     def _check(self, rc, what):
         if rc != 0:
             raise JrbError(f"{what} failed ({rc}): {self.lib.jrb_last_error(self.h).decode()}")
 
     def close(self):
-        if self.h:
+        if self.h and self.owned:
             self.lib.jrb_destroy(self.h)
-            self.h = C.c_void_p()
+        self.h = C.c_void_p()
 
     def __del__(self):
         try:
             self.close()
         except Exception:
             pass
+
+    def stage_views(self, n, av, ov):
+        """stage packages described by ready-made view arrays (e.g. views onto the reference's structs)"""
+        self._check(self.lib.jrb_stage(self.h, n, av, ov), "jrb_stage")
 
     def set_control(self, ctl):
         v = ctl.view()
@@ -445,3 +493,107 @@ class Context:
         s = abi.Stats()
         self._check(self.lib.jrb_get_stats(self.h, C.byref(s)), "jrb_get_stats")
         return {f[0]: getattr(s, f[0]) for f in abi.Stats._fields_}
+
+
+def host_register(arr):
+    """page-lock the memory of a numpy array (jrb_host_register); batches whose arrays are all registered run in direct mode"""
+    rc = load_core().jrb_host_register(arr.ctypes.data_as(C.c_void_p), arr.nbytes)
+    if rc != 0:
+        raise JrbError(f"jrb_host_register failed ({rc}): {load_core().jrb_last_error(None).decode()}")
+
+
+def host_unregister_all():
+    load_core().jrb_host_unregister_all()
+
+
+def register_package(pkg):
+    """page-lock every array of a Package"""
+    for name in ("atm_time", "z", "lon", "lat", "p", "t", "q", "k", "time", "obsz", "obslon", "obslat", "vpz", "vplon", "vplat",
+                 "tpz", "tplon", "tplat", "rad", "tau"):
+        host_register(getattr(pkg, name))
+
+
+class Group:
+    """devices x lanes behind one handle (jrb_group_*)"""
+
+    def __init__(self, ndev=1, devices=None, nlanes=1):
+        self.lib = load_core()
+        self.h = C.c_void_p()
+        dev = None if devices is None else (C.c_int * len(devices))(*devices)
+        rc = self.lib.jrb_group_create(C.byref(self.h), ndev, dev, nlanes)
+        if rc != 0:
+            raise JrbError(f"jrb_group_create failed ({rc}): {self.lib.jrb_last_error(None).decode()}")
+
+    def _check(self, rc, what):
+        if rc != 0:
+            raise JrbError(f"{what} failed ({rc}): {self.lib.jrb_group_last_error(self.h).decode()}")
+
+    def close(self):
+        if self.h:
+            self.lib.jrb_group_destroy(self.h)
+            self.h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def size(self):
+        a, b = C.c_int(), C.c_int()
+        self.lib.jrb_group_size(self.h, C.byref(a), C.byref(b))
+        return a.value, b.value
+
+    def set_tables(self, ctl, tbl):
+        cv, tv = ctl.view(), tbl.view()
+        self._check(self.lib.jrb_group_set_tables(self.h, C.byref(cv), C.byref(tv)), "jrb_group_set_tables")
+
+    def set_fov(self, dz, w):
+        dz, w = np.ascontiguousarray(dz, dtype=np.float64), np.ascontiguousarray(w, dtype=np.float64)
+        self._check(self.lib.jrb_group_set_fov(self.h, len(dz), _dp(dz), _dp(w)), "jrb_group_set_fov")
+
+    def formod_batch(self, packages, ctl=None, use_fov=0):
+        n = len(packages)
+        av = (abi.AtmView * n)(*[p.atm_view() for p in packages])
+        ov = (abi.ObsView * n)(*[p.obs_view() for p in packages])
+        cv = ctl.view() if ctl is not None else None
+        self._check(self.lib.jrb_group_formod_batch(self.h, C.byref(cv) if cv is not None else None, n, av, ov, use_fov),
+                    "jrb_group_formod_batch")
+
+    def context_stats(self, dev=0, lane=0):
+        s = abi.Stats()
+        c = self.lib.jrb_group_context(self.h, dev, lane)
+        self.lib.jrb_get_stats(c, C.byref(s))
+        return {f[0]: getattr(s, f[0]) for f in abi.Stats._fields_}
+
+    def stats(self):
+        s = abi.GroupStats()
+        self._check(self.lib.jrb_group_get_stats(self.h, C.byref(s)), "jrb_group_get_stats")
+        return {f[0]: getattr(s, f[0]) for f in abi.GroupStats._fields_}
+
+    # rank style
+    def dist_init(self, rank, nranks, uid):
+        buf = (C.c_char * 128).from_buffer_copy(bytes(uid)[:128].ljust(128, b"\0"))
+        self._check(self.lib.jrb_group_dist_init(self.h, rank, nranks, buf, 128), "jrb_group_dist_init")
+
+    def dist_set_tables(self, ctl, tbl, root=0):
+        cv = ctl.view()
+        tv = tbl.view() if tbl is not None else None
+        self._check(self.lib.jrb_group_dist_set_tables(self.h, C.byref(cv), C.byref(tv) if tv is not None else None, root),
+                    "jrb_group_dist_set_tables")
+
+    def dist_gather(self, counts, packages_all=None, root=0):
+        cnt = (C.c_int * len(counts))(*counts)
+        if packages_all is None:
+            self._check(self.lib.jrb_group_dist_gather(self.h, root, cnt, sum(counts), None), "jrb_group_dist_gather")
+            return
+        n = len(packages_all)
+        ov = (abi.ObsView * n)(*[p.obs_view() for p in packages_all])
+        self._check(self.lib.jrb_group_dist_gather(self.h, root, cnt, n, ov), "jrb_group_dist_gather")
+
+
+def dist_unique_id():
+    buf = (C.c_char * 128)()
+    if load_core().jrb_dist_unique_id(buf, 128) != 0:
+        raise JrbError("jrb_dist_unique_id failed (NCCL missing?)")
+    return bytes(buf)

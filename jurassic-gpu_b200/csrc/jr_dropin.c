@@ -34,9 +34,9 @@ static get_tbl_fn find_get_tbl(void) {
     exit(EXIT_FAILURE);                                                                        \
   } while (0)
 
-static jrb_context *g_ctx = NULL;
+static jrb_group *g_grp = NULL; /* devices x lanes; created on first use */
 static int g_have_tables = 0;
-static pthread_mutex_t g_lock = PTHREAD_MUTEX_INITIALIZER;
+static pthread_mutex_t g_lock = PTHREAD_MUTEX_INITIALIZER; /* initialisation only: forward-model calls run concurrently */
 
 /* find_emitter (src/jurassic.c:198-207): case-insensitive, -1 if absent */
 static int emitter_index(ctl_t const *ctl, char const *name) {
@@ -82,25 +82,37 @@ static void fill_obs_view(obs_t *o, jrb_obs_view *v) {
   v->row_stride = ND; v->nd_reset = ND;
 }
 
-/* control values can change between calls (the reference re-uploads ctl_t on every call, src/GPUdrivers.cu:355) */
-static void push_control(ctl_t const *ctl) {
-  jrb_ctl_view cv;
-  fill_ctl_view(ctl, &cv);
-  if (jrb_set_control(g_ctx, &cv) != JRB_OK) JR_FATAL(jrb_last_error(g_ctx));
+/* lanes per device: the reference hands out up to 4 (src/GPUdrivers.cu:292-296) */
+static int lanes_wanted(void) {
+  char const *s = getenv("JRB_LANES");
+  int n = s ? atoi(s) : 4;
+  return n < 1 ? 1 : (n > 8 ? 8 : n);
 }
 
-static void init_locked(ctl_t const *ctl, tbl_t const *tbl, int device) {
-  if (!g_ctx) {
+/* ndev == 1: the device `device` (< 0: ctl->MPIlocalrank like the reference, src/GPUdrivers.cu:288); ndev > 1: devices
+ * 0..ndev-1; ndev <= 0: all visible devices */
+static void make_group_locked(ctl_t const *ctl, int device, int ndev) {
+  if (g_grp) return;
+  int const avail = jrb_device_count();
+  if (avail < 1) JR_FATAL("no CUDA device available (there is no CPU fallback in this library)");
+  if (ndev <= 0) ndev = avail;
+  if (ndev > avail) JR_FATAL("More devices requested than visible. Abort.");
+  if (ndev == 1) {
     if (device < 0) device = ctl->MPIlocalrank;
-    int const ndev = jrb_device_count();
-    if (ndev < 1) JR_FATAL("no CUDA device available (there is no CPU fallback in this library)");
-    if (device >= ndev) JR_FATAL("More MPI-Ranks on Node than GPUs. Abort."); /* src/GPUdrivers.cu:284-287 */
-    if (jrb_create(&g_ctx, device) != JRB_OK) JR_FATAL(jrb_last_error(NULL));
+    if (device >= avail) JR_FATAL("More MPI-Ranks on Node than GPUs. Abort."); /* src/GPUdrivers.cu:284-287 */
+    if (jrb_group_create(&g_grp, 1, &device, lanes_wanted()) != JRB_OK) JR_FATAL(jrb_last_error(NULL));
+  } else {
+    if (jrb_group_create(&g_grp, ndev, NULL, lanes_wanted()) != JRB_OK) JR_FATAL(jrb_last_error(NULL));
   }
-  push_control(ctl);
+}
+
+static void init_locked(ctl_t const *ctl, tbl_t const *tbl, int device, int ndev) {
+  make_group_locked(ctl, device, ndev);
+  jrb_ctl_view cv;
+  fill_ctl_view(ctl, &cv);
   jrb_tbl_view tv;
   fill_tbl_view(tbl, &tv);
-  if (jrb_set_tables(g_ctx, &tv) != JRB_OK) JR_FATAL(jrb_last_error(g_ctx));
+  if (jrb_group_set_tables(g_grp, &cv, &tv) != JRB_OK) JR_FATAL(jrb_group_last_error(g_grp));
   g_have_tables = 1;
 }
 
@@ -137,13 +149,10 @@ int jr_b200_init_from_files(ctl_t const *ctl, int device) {
   }
   jrb_host_tables_view(ht, &tv, NULL);
   pthread_mutex_lock(&g_lock);
-  if (!g_ctx) {
-    if (device < 0) device = ctl->MPIlocalrank;
-    if (jrb_device_count() < 1) JR_FATAL("no CUDA device available (there is no CPU fallback in this library)");
-    if (jrb_create(&g_ctx, device) != JRB_OK) JR_FATAL(jrb_last_error(NULL));
-  }
-  push_control(ctl);
-  if (jrb_set_tables(g_ctx, &tv) != JRB_OK) JR_FATAL(jrb_last_error(g_ctx));
+  make_group_locked(ctl, device, 1);
+  jrb_ctl_view cv;
+  fill_ctl_view(ctl, &cv);
+  if (jrb_group_set_tables(g_grp, &cv, &tv) != JRB_OK) JR_FATAL(jrb_group_last_error(g_grp));
   g_have_tables = 1;
   pthread_mutex_unlock(&g_lock);
   jrb_host_tables_free(ht);
@@ -153,26 +162,88 @@ int jr_b200_init_from_files(ctl_t const *ctl, int device) {
 int jr_b200_init(ctl_t const *ctl, tbl_t const *tbl, int device) {
   if (!ctl || !tbl) JR_FATAL("jr_b200_init: NULL argument");
   pthread_mutex_lock(&g_lock);
-  init_locked(ctl, tbl, device);
+  init_locked(ctl, tbl, device, 1);
   pthread_mutex_unlock(&g_lock);
   return 0;
 }
 
-/* FOV shape file of ctl->fov, parsed like read_shape (src/jurassic.c:1134-1150); kept for the last file name seen */
-static void push_fov(ctl_t const *ctl, int enable) {
-  static char loaded[LEN] = "";
-  static double dz[NSHAPE], w[NSHAPE];
-  static int n = 0;
-  if (!enable || ctl->fov[0] == '-') { /* "-": do not take the FOV into account (src/jurassic.c:219) */
-    if (jrb_set_fov(g_ctx, 0, NULL, NULL) != JRB_OK) JR_FATAL(jrb_last_error(g_ctx));
-    return;
+/* all devices of the node behind the same calls: one context set and one host thread per device, tables packed once and
+ * broadcast with NCCL, batches cut into contiguous package slices (SURVEY.md 8b "needed extension", 8e) */
+int jr_b200_init_multi(ctl_t const *ctl, tbl_t const *tbl, int ndevices) {
+  if (!ctl || !tbl) JR_FATAL("jr_b200_init_multi: NULL argument");
+  pthread_mutex_lock(&g_lock);
+  if (g_grp) JR_FATAL("jr_b200_init_multi: already initialised (call jr_b200_finalize first)");
+  init_locked(ctl, tbl, -1, ndevices <= 0 ? 0 : ndevices);
+  pthread_mutex_unlock(&g_lock);
+  int nd_ = 0;
+  jrb_group_size(g_grp, &nd_, NULL);
+  return nd_;
+}
+
+/* ---- rank style (one process per GPU) ---------------------------------------------------------------------------------- */
+int jr_b200_dist_unique_id(char id[128]) { return jrb_dist_unique_id(id, 128) == JRB_OK ? 0 : -1; }
+
+int jr_b200_dist_init(ctl_t const *ctl, tbl_t const *tbl, int rank, int nranks, char const id[128], int device, int root) {
+  if (!ctl) JR_FATAL("jr_b200_dist_init: NULL argument");
+  pthread_mutex_lock(&g_lock);
+  if (g_grp) JR_FATAL("jr_b200_dist_init: already initialised (call jr_b200_finalize first)");
+  make_group_locked(ctl, device, 1);
+  if (jrb_group_dist_init(g_grp, rank, nranks, id, 128) != JRB_OK) JR_FATAL(jrb_group_last_error(g_grp));
+  jrb_ctl_view cv;
+  fill_ctl_view(ctl, &cv);
+  jrb_tbl_view tv;
+  if (tbl) fill_tbl_view(tbl, &tv);
+  if (jrb_group_dist_set_tables(g_grp, &cv, tbl ? &tv : NULL, root) != JRB_OK) JR_FATAL(jrb_group_last_error(g_grp));
+  g_have_tables = 1;
+  pthread_mutex_unlock(&g_lock);
+  return 0;
+}
+
+void jr_b200_dist_gather(obs_t *const obs_all[], int const counts[], int nranks, int root) {
+  if (!g_grp) JR_FATAL("jr_b200_dist_gather: not initialised");
+  int total = 0;
+  for (int r = 0; r < nranks; r++) total += counts[r];
+  jrb_obs_view *ov = NULL;
+  if (obs_all) {
+    ov = (jrb_obs_view *)malloc(sizeof(jrb_obs_view) * (size_t)(total ? total : 1));
+    if (!ov) JR_FATAL("Out of memory!");
+    for (int i = 0; i < total; i++) fill_obs_view(obs_all[i], &ov[i]);
   }
+  if (jrb_group_dist_gather(g_grp, root, counts, total, ov) != JRB_OK) JR_FATAL(jrb_group_last_error(g_grp));
+  free(ov);
+}
+
+/* ---- page-locking of the caller's structs (direct I/O, see jurassic_b200.h) ------------------------------------------- */
+int jr_b200_pin_packages(atm_t *const atm[], obs_t *const obs[], int npackages) {
+  for (int i = 0; i < npackages; i++) {
+    if (atm && atm[i] && jrb_host_register(atm[i], sizeof(atm_t)) != JRB_OK) return -1;
+    if (obs && obs[i] && jrb_host_register(obs[i], sizeof(obs_t)) != JRB_OK) return -1;
+  }
+  return 0;
+}
+void jr_b200_unpin_all(void) { jrb_host_unregister_all(); }
+
+void *jr_b200_shared_alloc(char const *name, size_t bytes, int create) {
+  void *p = NULL;
+  if (jrb_shared_alloc(name, bytes, create, &p) != JRB_OK) return NULL;
+  return p;
+}
+void jr_b200_shared_free(char const *name, void *ptr, size_t bytes, int unlink_it) { jrb_shared_free(name, ptr, bytes, unlink_it); }
+
+/* FOV shape file of ctl->fov, parsed like read_shape (src/jurassic.c:1134-1150); kept for the last file name seen.
+ * Returns 1 if the convolution is to be applied. */
+static char g_fov_loaded[LEN] = "";
+static int push_fov(ctl_t const *ctl, int enable) {
+  char *const loaded = g_fov_loaded;
+  if (!enable || ctl->fov[0] == '-') return 0; /* "-": do not take the FOV into account (src/jurassic.c:219) */
+  pthread_mutex_lock(&g_lock);
   if (strncmp(loaded, ctl->fov, LEN) != 0) {
+    static double dz[NSHAPE], w[NSHAPE];
     printf("Read shape function: %s\n", ctl->fov);
     FILE *in = fopen(ctl->fov, "r");
     if (!in) JR_FATAL("Cannot open file!");
     char line[LEN];
-    n = 0;
+    int n = 0;
     while (fgets(line, LEN, in)) {
       double a, b;
       if (sscanf(line, "%lg %lg", &a, &b) == 2) {
@@ -182,35 +253,44 @@ static void push_fov(ctl_t const *ctl, int enable) {
     }
     fclose(in);
     if (n < 1) JR_FATAL("Could not read any data!");
+    if (jrb_group_set_fov(g_grp, n, dz, w) != JRB_OK) JR_FATAL(jrb_group_last_error(g_grp));
     strncpy(loaded, ctl->fov, LEN - 1);
   }
-  if (jrb_set_fov(g_ctx, n, dz, w) != JRB_OK) JR_FATAL(jrb_last_error(g_ctx));
+  pthread_mutex_unlock(&g_lock);
+  return 1;
 }
 
-/* internal entry: exported names are reached through these statics so that a formod_GPU/… symbol of another library
+/* internal entry: exported names are reached through these statics so that a formod_GPU/... symbol of another library
  * in the global scope (e.g. the CPU-only stub of the reference, src/CPUdrivers.c:156-176) can never interpose them */
 static void formod_batch_impl(ctl_t const *ctl, atm_t *const atm[], obs_t *const obs[], int npackages, int fov) {
   if (ctl->checkmode) { printf("# %s: no operation in checkmode\n", __func__); return; }
   if (npackages <= 0) return;
   struct timespec ts0, ts1, ts2;
   clock_gettime(CLOCK_MONOTONIC, &ts0);
-  pthread_mutex_lock(&g_lock); /* concurrent callers (OpenMP host threads of a retrieval) are serialised */
-  if (!g_have_tables) {
-    get_tbl_fn const gt = find_get_tbl();
-    if (!gt) JR_FATAL("tables not initialised: call jr_b200_init() or link the reference's get_tbl()");
-    init_locked(ctl, gt(ctl), -1);
-  } else {
-    push_control(ctl);
+  if (!g_have_tables) { /* first call without jr_b200_init: tables from the reference's get_tbl, like its own first call */
+    pthread_mutex_lock(&g_lock);
+    if (!g_have_tables) {
+      get_tbl_fn const gt = find_get_tbl();
+      if (!gt) JR_FATAL("tables not initialised: call jr_b200_init() or link the reference's get_tbl()");
+      int ndev = 1;
+      if (getenv("JRB_NDEVICES")) ndev = atoi(getenv("JRB_NDEVICES"));
+      init_locked(ctl, gt(ctl), -1, ndev);
+    }
+    pthread_mutex_unlock(&g_lock);
   }
-  push_fov(ctl, fov);
+  /* control values can change between calls (the reference re-uploads ctl_t on every call, src/GPUdrivers.cu:355): they
+   * travel with the call and are applied to the lane that serves it */
+  jrb_ctl_view cv;
+  fill_ctl_view(ctl, &cv);
+  int const use_fov = push_fov(ctl, fov);
   jrb_atm_view *av = (jrb_atm_view *)malloc(sizeof(jrb_atm_view) * (size_t)npackages);
   jrb_obs_view *ov = (jrb_obs_view *)malloc(sizeof(jrb_obs_view) * (size_t)npackages);
   if (!av || !ov) JR_FATAL("Out of memory!");
   for (int i = 0; i < npackages; i++) { fill_atm_view(atm[i], &av[i]); fill_obs_view(obs[i], &ov[i]); }
   clock_gettime(CLOCK_MONOTONIC, &ts1);
-  if (jrb_formod_batch(g_ctx, npackages, av, ov) != JRB_OK) JR_FATAL(jrb_last_error(g_ctx));
+  /* concurrent callers (OpenMP host threads of a retrieval) are served by different lanes (src/GPUdrivers.cu:331-334) */
+  if (jrb_group_formod_batch(g_grp, &cv, npackages, av, ov, use_fov) != JRB_OK) JR_FATAL(jrb_group_last_error(g_grp));
   free(av); free(ov);
-  pthread_mutex_unlock(&g_lock);
   if (getenv("JRB_DEBUG_TIMING")) {
     clock_gettime(CLOCK_MONOTONIC, &ts2);
     fprintf(stderr, "[jr_dropin] prepare %.2f ms, core call %.2f ms\n", (ts1.tv_sec - ts0.tv_sec) * 1e3 + (ts1.tv_nsec - ts0.tv_nsec) * 1e-6,
@@ -325,11 +405,11 @@ void jr_b200_kernel(ctl_t const *ctl, atm_t *atm, obs_t *obs, double *k, size_t 
       ov[b].tpz = tp + b * (size_t)nr * 3; ov[b].tplon = ov[b].tpz + nr; ov[b].tplat = ov[b].tplon + nr;
       for (int ir = 0; ir < nr; ir++) memcpy(ov[b].rad + (size_t)ir * nd, obs->rad[ir], sizeof(double) * (size_t)nd); /* NaN mask */
     }
-    pthread_mutex_lock(&g_lock);
-    push_control(ctl);
-    push_fov(ctl, 0);
-    if (jrb_formod_batch(g_ctx, (int)nb, av, ov) != JRB_OK) JR_FATAL(jrb_last_error(g_ctx));
-    pthread_mutex_unlock(&g_lock);
+    {
+      jrb_ctl_view cv;
+      fill_ctl_view(ctl, &cv);
+      if (jrb_group_formod_batch(g_grp, &cv, (int)nb, av, ov, 0) != JRB_OK) JR_FATAL(jrb_group_last_error(g_grp));
+    }
     for (size_t b = 0; b < nb; b++) { /* K[:, j] = (y1 - y0) / h over the finite radiances (obs2y order) */
       size_t i = 0;
       for (int ir = 0; ir < nr; ir++)
@@ -342,8 +422,8 @@ void jr_b200_kernel(ctl_t const *ctl, atm_t *atm, obs_t *obs, double *k, size_t 
 
 void jr_b200_finalize(void) {
   pthread_mutex_lock(&g_lock);
-  if (g_ctx) jrb_destroy(g_ctx);
-  g_ctx = NULL; g_have_tables = 0;
+  if (g_grp) jrb_group_destroy(g_grp);
+  g_grp = NULL; g_have_tables = 0; g_fov_loaded[0] = 0;
   pthread_mutex_unlock(&g_lock);
 }
 
@@ -353,4 +433,5 @@ void jr_b200_dims(int dims[11], long long sizes[4]) {
   sizes[0] = sizeof(ctl_t); sizes[1] = sizeof(atm_t); sizes[2] = sizeof(obs_t); sizes[3] = sizeof(tbl_t);
 }
 
-void *jr_b200_core_context(void) { return g_ctx; }
+void *jr_b200_core_context(void) { return g_grp ? (void *)jrb_group_context(g_grp, 0, 0) : NULL; }
+void *jr_b200_core_group(void) { return g_grp; }

@@ -17,6 +17,13 @@ bool ega_fast_available(int ng, int ctm_mask) {
   return ng >= 0 && ng <= 32 && ctm_mask >= 0 && ctm_mask < 16 && ((JRB_MASK_LIST >> ctm_mask) & 1);
 }
 
+// can the specialised kernel run at all for this shape?  (a one-warp CTA is its smallest configuration: rpw staged
+// records per warp plus 16 B of state per gas and thread must fit the opt-in shared memory)
+bool ega_fast_fits(int ng, int los_head, int cpw, size_t smem_max) {
+  const int rpw = cpw < 32 ? 32 / (cpw < 1 ? 1 : cpw) : 1;
+  return ega_fast_smem_bytes(ng, los_head, 32, rpw) <= smem_max;
+}
+
 template <int M>
 static cudaError_t call_mask(const EgaArgs &a, cudaStream_t s, int sm, int *ngb) {
   if constexpr (((JRB_MASK_LIST) >> M) & 1) return launch_ega_fast_mask<M>(a, s, sm, ngb);

@@ -24,6 +24,7 @@
 // do not depend on the hints.
 #pragma once
 #include "jrb_ega_common.cuh"
+#include <atomic>
 #include <cstdlib>
 
 namespace jrb {
@@ -363,7 +364,7 @@ __global__ void __launch_bounds__(kEgaBlock, JRB_EGA_MINBLOCKS) ega_fast_kernel(
       const double p = R[0], t = R[1], ds = R[2];
       const double u_co2 = (MASK & 8) ? R[L.u0 + a.ig_co2] : 0.0;
       const double u_h2o = (MASK & 4) ? R[L.u0 + a.ig_h2o] : 0.0;
-      const double beta_ds = continuum_beta_ds(MASK, a.chan, nd, id, p, t, ds, R[4 + win], u_co2, u_h2o, R[3]);
+      const double beta_ds = continuum_beta_ds(MASK, a.chan, nd, id, p, t, ds, a.nw > 0 ? R[4 + win] : 0.0, u_co2, u_h2o, R[3]);
 
       double tau_gas = 1.0;
       bool any_opaque = false;
@@ -443,6 +444,10 @@ __global__ void __launch_bounds__(kEgaBlock, JRB_EGA_MINBLOCKS) ega_fast_kernel(
     if (lane_on) {
       a.rad[(size_t)ir * nd + id] = rad;
       a.tau[(size_t)ir * nd + id] = tau;
+      if (a.rad_host) { // the ray's rows in host-mapped memory: the result lands there while the kernel keeps running
+        a.rad_host[ir][id] = rad;
+        a.tau_host[ir][id] = tau;
+      }
     }
   }
 }
@@ -489,11 +494,21 @@ cudaError_t launch_ega_fast_tm(const EgaArgs &a, cudaStream_t stream, int sm_cou
   cudaDeviceGetAttribute(&smem_max, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev);
   int block = kEgaBlock;
   if (const char *s = getenv("JRB_EGA_THREADS")) { const int v = atoi(s); if (v >= 32 && v <= kEgaBlock && v % 32 == 0) block = v; } // experiments
-  else if (n_items < 16ll * sm_count * (kEgaBlock / 32) || ega_fast_smem_bytes(a.ng, a.los.head, kEgaBlock, rpw) > (size_t)smem_max)
-    block = kEgaSmallBlock;
+  else if (n_items < 16ll * sm_count * (kEgaBlock / 32)) block = kEgaSmallBlock;
+  // few channels x many gases (rpw records per warp + 16 B of state per gas and thread) can exceed even the small CTA's
+  // shared memory: shrink the CTA until it fits (jrb_stage has checked that a one-warp CTA fits, else the generic kernel runs)
+  while (block > 32 && ega_fast_smem_bytes(a.ng, a.los.head, block, rpw) > (size_t)smem_max) block = block > kEgaSmallBlock ? kEgaSmallBlock : block / 2;
   const size_t smem = ega_fast_smem_bytes(a.ng, a.los.head, block, rpw);
-  cudaError_t e = cudaFuncSetAttribute(ega_fast_kernel<MASK, MULTI, ROBUST>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-  if (e != cudaSuccess) return e;
+  if (smem > (size_t)smem_max) return cudaErrorInvalidConfiguration;
+  // the dynamic shared-memory limit is a per-device property of the function: set once to the opt-in maximum, so that
+  // contexts launching concurrently with different sizes (lanes, several host threads) cannot lower it under each other
+  static std::atomic<unsigned long long> attr_done{0};
+  cudaError_t e = cudaSuccess;
+  if (!((attr_done.load(std::memory_order_acquire) >> (dev & 63)) & 1ull)) {
+    e = cudaFuncSetAttribute(ega_fast_kernel<MASK, MULTI, ROBUST>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_max);
+    if (e != cudaSuccess) return e;
+    attr_done.fetch_or(1ull << (dev & 63), std::memory_order_release);
+  }
   if (const char *s = getenv("JRB_EGA_CARVEOUT")) { // experiments: shared-memory carve-out in percent (the rest of the 256 KB is L1)
     const int v = atoi(s);
     if (v >= 0 && v <= 100) cudaFuncSetAttribute(ega_fast_kernel<MASK, MULTI, ROBUST>, cudaFuncAttributePreferredSharedMemoryCarveout, v);

@@ -80,7 +80,7 @@ __global__ void __launch_bounds__(128) ega_generic_kernel(EgaArgs a) {
     const double p = rec[0], t = rec[1], ds = rec[2];
     const double u_co2 = (a.ctm_mask & 8) ? rec[L.u0 + a.ig_co2] : 0.0;
     const double u_h2o = (a.ctm_mask & 4) ? rec[L.u0 + a.ig_h2o] : 0.0;
-    const double beta_ds = continuum_beta_ds(a.ctm_mask, a.chan, a.nd, id, p, t, ds, rec[4 + win], u_co2, u_h2o, rec[3]);
+    const double beta_ds = continuum_beta_ds(a.ctm_mask, a.chan, a.nd, id, p, t, ds, a.nw > 0 ? rec[4 + win] : 0.0, u_co2, u_h2o, rec[3]);
     double tau_gas = 1.0;
     for (int ig = 0; ig < a.ng; ig++) { // apply_ega_core (src/jr_common.h:270-280)
       const double f = ega_factor_generic(a.tbl, tau_path[ig], t, rec[L.u0 + ig], p, ig, id);
@@ -93,6 +93,10 @@ __global__ void __launch_bounds__(128) ega_generic_kernel(EgaArgs a) {
   epilogue(rad, tau, a.ray_tsurf[ir], a.tbl.sr, a.nd, id, a.write_bbt, a.chan[CH_NU * a.nd + id]);
   a.rad[idx] = rad;
   a.tau[idx] = tau;
+  if (a.rad_host) {
+    a.rad_host[ir][id] = rad;
+    a.tau_host[ir][id] = tau;
+  }
 }
 
 } // namespace

@@ -301,7 +301,14 @@ int jrb_tables_read_binary(const char *filename, int ng, const char *const *emit
   for (int id = 0; id < nd; id++) if (!nu_found[id]) { bad("channel not in file: " + std::to_string(nu[id])); break; }
   if (G < 1 || P < 1 || T < 1 || U < 1 || D < 1) bad("extents NG/TBLNP/TBLNT/TBLNU/ND missing");
   if (S != kTBLNS) bad("TBLNS must be 1201");
-  if (header_size < (long long)kBinHeaderLen) header_size = (long long)kBinHeaderLen;
+  if (header_size < 0) header_size = (long long)kBinHeaderLen; // key absent: the reference's fixed header length
+  // the header is untrusted input: the reference writes exactly one header length, and every extent is a small
+  // compile-time constant there (TBLNU = 304 is its largest) -- bounded here so that the size products cannot overflow
+  // and the array views behind the header stay 8-byte aligned
+  if (header_size != (long long)kBinHeaderLen) bad("header_size must be 16384");
+  if (G > 4096 || P > 4096 || T > 4096 || U > 4096 || D > 4096) bad("extents NG/TBLNP/TBLNT/TBLNU/ND above 4096");
+  else if (G >= 1 && P >= 1 && T >= 1 && U >= 1 && D >= 1 &&
+           (long double)G * P * T * U * D * 8.0L + (long double)G * P * T * D * 12.0L > 4.0e12L) bad("table extents describe more than 4 TB");
   BinLayout L{};
   if (problems.empty()) {
     L = bin_layout(G, P, T, U, D, S);

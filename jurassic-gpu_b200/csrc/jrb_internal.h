@@ -30,6 +30,8 @@ struct TraceArgs {
   int *ray_level0;  // [n_rays] first atmosphere level of the ray's profile (relative to its package)
   double *ray_tsurf;
   double *tp;       // rows tpz, tplon, tplat ; row stride geo_stride
+  double *const *tp_host; // optional [3][geo_stride] per-ray addresses in host-mapped memory (the caller's obs_t or the
+                          // pinned result buffer): the tangent point is also stored there -- no device-to-host copy phase
   TblDev tbl;       // used when los.fast
 };
 
@@ -48,6 +50,10 @@ struct EgaArgs {
   const int *window;    // [nd]
   TblDev tbl;
   double *rad, *tau;    // [n_rays][nd]
+  // optional per-ray row addresses in host-mapped memory (the caller's registered obs_t rows, or the library's pinned
+  // result buffer): every ray's rad/tau row is ALSO stored there by the kernel when the ray finishes, so results land in
+  // host memory while the kernel is still running (zero-copy over PCIe) and there is no device-to-host copy phase
+  double *const *rad_host, *const *tau_host;
   unsigned long long *work_counter; // dynamic work distribution (zeroed before launch)
   int work_chunk;                   // consecutive items a CTA draws at a time (1..200); 0 = one per warp of the CTA
   unsigned long long *balance;      // [2] scratch (zeroed before launch): idle / total segment slots of lock-step execution
@@ -66,6 +72,30 @@ struct FovArgs { // optional epilogue: field-of-view convolution (formod_fov, sr
   int *error;                  // bit 0: a ray with fewer than 2 rays of its own time in its +-NFOV window
 };
 cudaError_t launch_fov(const FovArgs &a, cudaStream_t stream);
+
+// ---- package I/O (jrb_io.cu) --------------------------------------------------------------------------------------------
+// Per-package output addresses in host-mapped memory
+struct OutTab { double *rad, *tau, *tpz, *tplon, *tplat; long long stride; };
+struct StageArgs {
+  int npk;
+  int n_geo, n_atm_fields;          // 7 ; 6 + ng + nw
+  const long long *ray_off, *atm_off; // [npk+1]
+  // direct mode: src[pk*(n_geo+n_atm_fields) + f] = device-visible address of field f of package pk in the caller's
+  // registered (page-locked, mapped) atm_t / obs_t; NULL = inputs were packed on the host and copied (staged mode)
+  const double *const *src;
+  double *geo; long long R;         // [7][R]
+  double *atm; long long A;         // [n_atm_fields][A]
+  int *ray_pkg;                     // [R]
+  int *pkg_atm_np;                  // [npk]
+  const OutTab *out;                // [npk]
+  double **ray_out;                 // [5][R]: per-ray addresses of the rad row, tau row, tpz, tplon, tplat
+};
+// fills ray_pkg, pkg_atm_np, the per-ray output addresses and -- in direct mode -- gathers the populated prefixes of the
+// packages' arrays straight from the caller's registered host memory into the device SoA (no host-side packing)
+cudaError_t launch_stage(const StageArgs &a, cudaStream_t stream);
+// copy device-resident results to their host rows (used after the FOV epilogue and by the multi-rank gather)
+cudaError_t launch_publish(const double *rad, const double *tau, double *const *rad_host, double *const *tau_host, long long n_rays,
+                           int nd, cudaStream_t stream);
 cudaError_t launch_nan_mask(double *rad, const long long *flat, long long n, cudaStream_t stream);
 
 // three launches: level slopes, ray stepping (thread per ray), LOS finalisation (thread per ray x segment)
@@ -74,5 +104,6 @@ cudaError_t launch_ega_generic(const EgaArgs &a, cudaStream_t stream);
 // fast path: returns cudaErrorInvalidValue if (ng, ctm_mask) has no instantiation
 cudaError_t launch_ega_fast(const EgaArgs &a, cudaStream_t stream, int *ngb_out);
 bool ega_fast_available(int ng, int ctm_mask);
+bool ega_fast_fits(int ng, int los_head, int cpw, size_t smem_max);
 
 } // namespace jrb

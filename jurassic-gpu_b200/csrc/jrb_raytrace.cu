@@ -261,6 +261,11 @@ __global__ void __launch_bounds__(128) ray_step_kernel(TraceArgs a) {
   a.tp[0 * a.geo_stride + r] = tpz;
   a.tp[1 * a.geo_stride + r] = tplon;
   a.tp[2 * a.geo_stride + r] = tplat;
+  if (a.tp_host) { // the caller's obs_t (or the pinned result buffer), host-mapped: no copy phase afterwards
+    *a.tp_host[0 * a.geo_stride + r] = tpz;
+    *a.tp_host[1 * a.geo_stride + r] = tplon;
+    *a.tp_host[2 * a.geo_stride + r] = tplat;
+  }
 }
 
 // thread per (ray, segment)

@@ -1,20 +1,27 @@
 // jrb_runtime.cu -- host runtime behind the C ABI of include/jurassic_b200.h: context, table residency,
-// staging of packages into compact device arrays, kernel sequencing, result scatter.
+// staging of packages into compact device arrays, kernel sequencing, result landing.
 //
 // Replaces the reference's lane machinery (gpuLane_t / formod_one_package / formod_GPU,
-// src/GPUdrivers.cu:176-360): instead of copying whole atm_t/obs_t structs (2.8 MB + 1.8 MB per 1088 rays, mostly
-// unused NP/NR/ND padding) per call, any number of packages is packed into one pinned staging buffer holding only
-// the populated prefixes, moved with a single H2D copy, processed by two kernels per LOS chunk (ray tracer, EGA) and
-// returned with a single D2H copy.
+// src/GPUdrivers.cu:176-360).  The reference copies whole atm_t/obs_t structs (2.8 MB + 1.8 MB per 1088 rays, mostly
+// unused NP/NR/ND padding) in and out per call.  Here any number of packages is one device batch and there are two I/O
+// modes, chosen per batch:
+//   staged : the populated prefixes of the packages are packed into one pinned buffer and moved with a single H2D copy;
+//            results are stored by the kernels into a pinned, host-mapped result buffer as each ray finishes and are
+//            scattered from there into the caller's obs_t rows;
+//   direct : when the caller's atm_t / obs_t blocks are page-locked (jrb_host_register), a staging kernel gathers the
+//            inputs straight from them over PCIe and the compute kernels store every ray's results straight into the
+//            caller's obs_t rows -- no host-side packing, no copy phase, no scatter.
 #include "jrb_host.h"
 
 #include <algorithm>
 #include <cmath>
 #include <cstdio>
 #include <cstring>
+#include <memory>
 #include <mutex>
 #include <chrono>
 #include <thread>
+#include <unistd.h>
 
 using namespace jrb;
 
@@ -33,19 +40,52 @@ struct DevBuf {
   }
   void release() { if (p) cudaFree(p); p = nullptr; cap = 0; }
 };
-struct PinBuf {
+struct PinBuf { // page-locked and mapped into the device address space (unified addressing: device address == host address)
   void *p = nullptr;
   size_t cap = 0;
   cudaError_t ensure(size_t n) {
     if (n <= cap) return cudaSuccess;
     if (p) cudaFreeHost(p);
     p = nullptr; cap = 0;
-    cudaError_t e = cudaMallocHost(&p, n);
+    cudaError_t e = cudaHostAlloc(&p, n, cudaHostAllocPortable | cudaHostAllocMapped);
     if (e == cudaSuccess) cap = n;
     return e;
   }
   void release() { if (p) cudaFreeHost(p); p = nullptr; cap = 0; }
 };
+
+// packed tables of one device; shared by the contexts (lanes) of that device
+struct TableSet {
+  int device = 0;
+  DevBuf blob;
+  size_t blob_bytes = 0;
+  bool adopted = false;
+  TblHeader th;
+  TblDev td;
+  ~TableSet() { cudaSetDevice(device); blob.release(); }
+};
+
+// ---- registry of caller memory page-locked with jrb_host_register (process-wide) -------------------------------------
+struct HostRange { uintptr_t lo, hi; char *dev; }; // [lo, hi) page aligned; dev = device address of lo
+std::mutex g_reg_mtx;
+std::vector<HostRange> g_reg; // sorted by lo, disjoint
+
+// device address of host block [p, p+n) if it lies inside registered memory (seamlessly adjacent ranges are walked), else NULL
+void *registered_dev_ptr(const void *p, size_t n) {
+  if (g_reg.empty() || !p) return nullptr;
+  const uintptr_t a = (uintptr_t)p, b = a + (n ? n : 1);
+  size_t lo = 0, hi = g_reg.size();
+  while (lo < hi) { const size_t m = (lo + hi) / 2; if (g_reg[m].hi <= a) lo = m + 1; else hi = m; }
+  if (lo >= g_reg.size() || g_reg[lo].lo > a) return nullptr;
+  char *dev = g_reg[lo].dev + (a - g_reg[lo].lo);
+  uintptr_t covered = g_reg[lo].hi;
+  for (size_t i = lo; covered < b;) {
+    const HostRange &cur = g_reg[i];
+    if (++i >= g_reg.size() || g_reg[i].lo != covered || g_reg[i].dev != cur.dev + (cur.hi - cur.lo)) return nullptr;
+    covered = g_reg[i].hi;
+  }
+  return dev;
+}
 
 std::string g_create_error;
 
@@ -59,6 +99,7 @@ inline double now_ms() {
 struct jrb_context {
   int device = 0;
   int sm_count = 148;
+  int l2_bytes = 0, smem_optin = 0;
   cudaStream_t stream = nullptr;
   std::string err;
   std::mutex mtx;
@@ -71,13 +112,11 @@ struct jrb_context {
   std::vector<int> window;
   DevBuf d_chan, d_window;
 
-  // tables
-  bool have_tbl = false;
-  DevBuf d_blob;
-  size_t blob_bytes = 0;
-  TblHeader th;
-  TblDev td;
+  // tables (shared between the contexts of a device)
+  std::shared_ptr<TableSet> tbl;
+  bool have_tbl() const { return tbl && tbl->adopted; }
   int variant_req = -1;
+  double los_limit_gb = 0; // 0: JRB_LOS_GB or the default
 
   // optional field-of-view epilogue (jrb_set_fov)
   int fov_n = 0;
@@ -86,23 +125,27 @@ struct jrb_context {
 
   // staged batch
   bool staged = false, ran = false;
+  bool direct = false;          // I/O mode of the staged batch
   int npk = 0;
   long long n_rays = 0, n_atm = 0;
   std::vector<int> pk_nr;
   std::vector<long long> pk_ray_off;
+  std::vector<jrb_obs_view> st_obs;                // the obs views of the staged batch (direct mode: where results land)
   std::vector<std::pair<long long, int>> nan_mask; // (global ray, channel) whose input radiance was non-finite
-  PinBuf h_in, h_out;
-  DevBuf d_in, d_out, d_los, d_np, d_tsurf, d_counter, d_slope, d_level0;
-  // pointers into d_in / d_out
+  PinBuf h_in, h_out, h_tab;
+  DevBuf d_in, d_tab, d_out, d_rayout, d_los, d_np, d_tsurf, d_counter, d_slope, d_level0, d_raypkg, d_pkgnp;
+  // pointers into d_in / d_tab / d_out
   double *geo = nullptr, *atm = nullptr;
   int *ray_pkg = nullptr, *pkg_atm_np = nullptr;
   long long *pkg_atm_off = nullptr;
   double *o_rad = nullptr, *o_tau = nullptr, *o_tp = nullptr;
+  double **ray_out = nullptr; // [5][R] per-ray host-mapped addresses: rad row, tau row, tpz, tplon, tplat
   long long chunk_rays = 0;
   int nbuf = 1;                 // LOS buffers: 1 = chunks run back to back, 3 = tracer(c+1) overlaps EGA(c)
   cudaStream_t s_trace = nullptr, s_ega[2] = {nullptr, nullptr};
   LosLayout los;
   int use_fast = 0;
+  int cpw = 32;
   std::vector<cudaEvent_t> events;
   jrb_stats stats;
   bool np_fetched = false;
@@ -112,6 +155,7 @@ struct jrb_context {
     err = std::string(what) + ": " + cudaGetErrorString(e);
     return JRB_ERR_CUDA;
   }
+  void invalidate() { staged = false; ran = false; }
 };
 
 #define CU(call)                                                \
@@ -122,7 +166,7 @@ struct jrb_context {
 
 extern "C" {
 
-const char *jrb_version(void) { return "jurassic-b200 0.1 (sm_100a)"; }
+const char *jrb_version(void) { return "jurassic-b200 0.2 (sm_100a)"; }
 
 int jrb_device_count(void) {
   int n = 0;
@@ -149,6 +193,8 @@ int jrb_create(jrb_context **out, int device) {
   jrb_context *ctx = new jrb_context();
   ctx->device = device;
   cudaDeviceGetAttribute(&ctx->sm_count, cudaDevAttrMultiProcessorCount, device);
+  cudaDeviceGetAttribute(&ctx->l2_bytes, cudaDevAttrL2CacheSize, device);
+  cudaDeviceGetAttribute(&ctx->smem_optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, device);
   e = cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking);
   if (e != cudaSuccess) { g_create_error = std::string("cudaStreamCreate: ") + cudaGetErrorString(e); delete ctx; return JRB_ERR_CUDA; }
   int lo_prio = 0, hi_prio = 0;
@@ -168,15 +214,19 @@ void jrb_destroy(jrb_context *ctx) {
   cudaSetDevice(ctx->device);
   cudaStreamSynchronize(ctx->stream);
   for (auto ev : ctx->events) cudaEventDestroy(ev);
-  ctx->d_chan.release(); ctx->d_window.release(); ctx->d_blob.release();
-  ctx->d_in.release(); ctx->d_out.release(); ctx->d_los.release(); ctx->d_np.release(); ctx->d_tsurf.release();
-  ctx->d_counter.release(); ctx->d_slope.release(); ctx->d_level0.release(); ctx->h_in.release(); ctx->h_out.release();
+  ctx->d_chan.release(); ctx->d_window.release(); ctx->tbl.reset();
+  ctx->d_in.release(); ctx->d_tab.release(); ctx->d_out.release(); ctx->d_rayout.release(); ctx->d_los.release();
+  ctx->d_np.release(); ctx->d_tsurf.release(); ctx->d_counter.release(); ctx->d_slope.release(); ctx->d_level0.release();
+  ctx->d_raypkg.release(); ctx->d_pkgnp.release();
+  ctx->h_in.release(); ctx->h_out.release(); ctx->h_tab.release();
   ctx->d_fov.release(); ctx->d_fov_out.release(); ctx->d_mask.release(); ctx->d_flag.release();
   cudaStreamDestroy(ctx->stream);
   if (ctx->s_trace) cudaStreamDestroy(ctx->s_trace);
   for (auto st : ctx->s_ega) if (st) cudaStreamDestroy(st);
   delete ctx;
 }
+
+int jrb_context_device(const jrb_context *ctx) { return ctx ? ctx->device : -1; }
 
 int jrb_set_control(jrb_context *ctx, const jrb_ctl_view *c) {
   if (!ctx || !c) return JRB_ERR_ARG;
@@ -188,13 +238,20 @@ int jrb_set_control(jrb_context *ctx, const jrb_ctl_view *c) {
   if (c->ip != 1) return ctx->fail(JRB_ERR_ARG, "only IP=1 (1-D profiles) is supported (reference asserts the same, src/jr_common.h:573)");
   for (int id = 0; id < c->nd; id++)
     if (c->window[id] < 0 || c->window[id] >= (c->nw > 0 ? c->nw : 1)) return ctx->fail(JRB_ERR_ARG, "window index out of range");
+  const int mask = ((1 == c->ctm_co2) && (c->ig_co2 >= 0)) * 8 + ((1 == c->ctm_h2o) && (c->ig_h2o >= 0)) * 4 +
+                   (1 == c->ctm_n2) * 2 + (1 == c->ctm_o2) * 1; // fourbit of the reference (src/CPUdrivers.c:130-134)
+  // unchanged control (the drop-in layer pushes it on every call, like the reference re-uploads ctl_t): nothing to do
+  if (ctx->have_ctl && ctx->ng == c->ng && ctx->nd == c->nd && ctx->nw == c->nw && ctx->ig_co2 == c->ig_co2 && ctx->ig_h2o == c->ig_h2o &&
+      ctx->ctm_mask == mask && ctx->refrac == c->refrac && ctx->rayds == c->rayds && ctx->raydz == c->raydz && ctx->hydz == c->hydz &&
+      ctx->write_bbt == c->write_bbt && std::equal(ctx->nu.begin(), ctx->nu.end(), c->nu) &&
+      std::equal(ctx->window.begin(), ctx->window.end(), c->window))
+    return JRB_OK;
   CU(cudaSetDevice(ctx->device));
-  if (ctx->have_ctl && (ctx->ng != c->ng || ctx->nd != c->nd)) ctx->have_tbl = false; // tables must be re-packed
+  ctx->invalidate();
+  if (ctx->have_ctl && (ctx->ng != c->ng || ctx->nd != c->nd)) ctx->tbl.reset(); // tables must be re-packed
   ctx->ng = c->ng; ctx->nd = c->nd; ctx->nw = c->nw;
   ctx->ig_co2 = c->ig_co2; ctx->ig_h2o = c->ig_h2o;
-  // fourbit of the reference (src/CPUdrivers.c:130-134)
-  ctx->ctm_mask = ((1 == c->ctm_co2) && (c->ig_co2 >= 0)) * 8 + ((1 == c->ctm_h2o) && (c->ig_h2o >= 0)) * 4 +
-                  (1 == c->ctm_n2) * 2 + (1 == c->ctm_o2) * 1;
+  ctx->ctm_mask = mask;
   ctx->refrac = c->refrac; ctx->rayds = c->rayds; ctx->raydz = c->raydz; ctx->hydz = c->hydz;
   ctx->write_bbt = c->write_bbt;
   ctx->nu.assign(c->nu, c->nu + c->nd);
@@ -207,20 +264,31 @@ int jrb_set_control(jrb_context *ctx, const jrb_ctl_view *c) {
   CU(cudaMemcpyAsync(ctx->d_window.p, ctx->window.data(), ctx->nd * sizeof(int), cudaMemcpyHostToDevice, ctx->stream));
   CU(cudaStreamSynchronize(ctx->stream));
   ctx->have_ctl = true;
-  ctx->staged = false;
   return JRB_OK;
 }
 
 static int adopt_blob_locked(jrb_context *ctx) {
+  TableSet &ts = *ctx->tbl;
+  ts.adopted = false;
+  ctx->invalidate();
   unsigned char hdr[sizeof(TblHeader)];
-  CU(cudaMemcpy(hdr, ctx->d_blob.p, sizeof(TblHeader), cudaMemcpyDeviceToHost));
-  int rc = resolve_tables(hdr, (const unsigned char *)ctx->d_blob.p, ctx->th, ctx->td, ctx->err);
+  CU(cudaMemcpy(hdr, ts.blob.p, sizeof(TblHeader), cudaMemcpyDeviceToHost));
+  int rc = resolve_tables(hdr, (const unsigned char *)ts.blob.p, ts.th, ts.td, ctx->err);
   if (rc != JRB_OK) return rc;
-  if (ctx->th.nbytes > ctx->blob_bytes) return ctx->fail(JRB_ERR_ARG, "table blob truncated");
-  if (ctx->th.ng != ctx->ng || ctx->th.nd != ctx->nd) return ctx->fail(JRB_ERR_ARG, "table blob was packed for another ng/nd");
-  ctx->have_tbl = true;
-  ctx->staged = false;
-  ctx->stats.table_blob_bytes = (long long)ctx->th.nbytes;
+  if (ts.th.nbytes > ts.blob_bytes) return ctx->fail(JRB_ERR_ARG, "table blob truncated");
+  if (ts.th.ng != ctx->ng || ts.th.nd != ctx->nd) return ctx->fail(JRB_ERR_ARG, "table blob was packed for another ng/nd");
+  ts.adopted = true;
+  ctx->stats.table_blob_bytes = (long long)ts.th.nbytes;
+  return JRB_OK;
+}
+
+// a fresh table set for this context (other contexts sharing the previous one keep it)
+static int new_blob_locked(jrb_context *ctx, size_t nbytes) {
+  ctx->invalidate();
+  ctx->tbl = std::make_shared<TableSet>();
+  ctx->tbl->device = ctx->device;
+  CU(ctx->tbl->blob.ensure(nbytes));
+  ctx->tbl->blob_bytes = nbytes;
   return JRB_OK;
 }
 
@@ -232,9 +300,9 @@ int jrb_set_tables(jrb_context *ctx, const jrb_tbl_view *tbl) {
   std::vector<unsigned char> blob;
   int rc = pack_tables(*tbl, ctx->ng, ctx->nd, blob, ctx->err);
   if (rc != JRB_OK) return rc;
-  CU(ctx->d_blob.ensure(blob.size()));
-  ctx->blob_bytes = blob.size();
-  CU(cudaMemcpy(ctx->d_blob.p, blob.data(), blob.size(), cudaMemcpyHostToDevice));
+  rc = new_blob_locked(ctx, blob.size());
+  if (rc != JRB_OK) return rc;
+  CU(cudaMemcpy(ctx->tbl->blob.p, blob.data(), blob.size(), cudaMemcpyHostToDevice));
   return adopt_blob_locked(ctx);
 }
 
@@ -277,17 +345,17 @@ int jrb_tables_upload_blob(jrb_context *ctx, const void *host_blob, size_t nbyte
   std::lock_guard<std::mutex> lk(ctx->mtx);
   if (!ctx->have_ctl) return ctx->fail(JRB_ERR_STATE, "jrb_set_control must be called first");
   CU(cudaSetDevice(ctx->device));
-  CU(ctx->d_blob.ensure(nbytes));
-  ctx->blob_bytes = nbytes;
-  CU(cudaMemcpy(ctx->d_blob.p, host_blob, nbytes, cudaMemcpyHostToDevice));
+  int rc = new_blob_locked(ctx, nbytes);
+  if (rc != JRB_OK) return rc;
+  CU(cudaMemcpy(ctx->tbl->blob.p, host_blob, nbytes, cudaMemcpyHostToDevice));
   return adopt_blob_locked(ctx);
 }
 
 int jrb_tables_blob(jrb_context *ctx, void **dev_ptr, size_t *nbytes) {
   if (!ctx || !dev_ptr || !nbytes) return JRB_ERR_ARG;
   std::lock_guard<std::mutex> lk(ctx->mtx);
-  if (!ctx->have_tbl) return ctx->fail(JRB_ERR_STATE, "no tables set");
-  *dev_ptr = ctx->d_blob.p; *nbytes = ctx->blob_bytes;
+  if (!ctx->have_tbl()) return ctx->fail(JRB_ERR_STATE, "no tables set");
+  *dev_ptr = ctx->tbl->blob.p; *nbytes = ctx->tbl->blob_bytes;
   return JRB_OK;
 }
 
@@ -295,10 +363,9 @@ int jrb_tables_alloc_blob(jrb_context *ctx, size_t nbytes, void **dev_ptr) {
   if (!ctx || !dev_ptr || nbytes < sizeof(TblHeader)) return JRB_ERR_ARG;
   std::lock_guard<std::mutex> lk(ctx->mtx);
   CU(cudaSetDevice(ctx->device));
-  CU(ctx->d_blob.ensure(nbytes));
-  ctx->blob_bytes = nbytes;
-  ctx->have_tbl = false;
-  *dev_ptr = ctx->d_blob.p;
+  int rc = new_blob_locked(ctx, nbytes);
+  if (rc != JRB_OK) return rc;
+  *dev_ptr = ctx->tbl->blob.p;
   return JRB_OK;
 }
 
@@ -306,16 +373,42 @@ int jrb_tables_adopt_blob(jrb_context *ctx) {
   if (!ctx) return JRB_ERR_ARG;
   std::lock_guard<std::mutex> lk(ctx->mtx);
   if (!ctx->have_ctl) return ctx->fail(JRB_ERR_STATE, "jrb_set_control must be called first");
-  if (!ctx->d_blob.p) return ctx->fail(JRB_ERR_STATE, "no blob allocated");
+  if (!ctx->tbl || !ctx->tbl->blob.p) return ctx->fail(JRB_ERR_STATE, "no blob allocated");
   CU(cudaSetDevice(ctx->device));
   return adopt_blob_locked(ctx);
+}
+
+// lanes: a second context of the same device uses the tables of the first (no copy, shared ownership)
+int jrb_tables_share(jrb_context *ctx, jrb_context *from) {
+  if (!ctx || !from || ctx == from) return JRB_ERR_ARG;
+  std::shared_ptr<TableSet> t;
+  {
+    std::lock_guard<std::mutex> lk(from->mtx);
+    if (!from->have_tbl()) return from->fail(JRB_ERR_STATE, "no tables set");
+    t = from->tbl;
+  }
+  std::lock_guard<std::mutex> lk(ctx->mtx);
+  if (ctx->device != t->device) return ctx->fail(JRB_ERR_ARG, "jrb_tables_share: contexts live on different devices");
+  if (!ctx->have_ctl) return ctx->fail(JRB_ERR_STATE, "jrb_set_control must be called first");
+  if (t->th.ng != ctx->ng || t->th.nd != ctx->nd) return ctx->fail(JRB_ERR_ARG, "tables were packed for another ng/nd");
+  ctx->invalidate();
+  ctx->tbl = t;
+  ctx->stats.table_blob_bytes = (long long)t->th.nbytes;
+  return JRB_OK;
 }
 
 int jrb_set_kernel_variant(jrb_context *ctx, int variant) {
   if (!ctx || variant < -1 || variant > 1) return JRB_ERR_ARG;
   std::lock_guard<std::mutex> lk(ctx->mtx);
   ctx->variant_req = variant;
-  ctx->staged = false;
+  ctx->invalidate();
+  return JRB_OK;
+}
+
+int jrb_set_los_limit_gb(jrb_context *ctx, double gb) {
+  if (!ctx || gb < 0) return JRB_ERR_ARG;
+  std::lock_guard<std::mutex> lk(ctx->mtx);
+  ctx->los_limit_gb = gb;
   return JRB_OK;
 }
 
@@ -333,6 +426,70 @@ int jrb_set_fov(jrb_context *ctx, int n, const double *dz, const double *w) {
   }
   ctx->fov_n = n;
   return JRB_OK;
+}
+
+// ---- page-locking of caller memory ---------------------------------------------------------------------------------------
+// Registers the pages of [ptr, ptr+bytes) that are not registered yet (blocks may share pages or overlap earlier calls).
+int jrb_host_register(void *ptr, size_t bytes) {
+  if (!ptr || bytes == 0) return JRB_ERR_ARG;
+  int ndev = 0;
+  if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev < 1) { cudaGetLastError(); g_create_error = "jrb_host_register: no CUDA device"; return JRB_ERR_CUDA; }
+  const uintptr_t page = (uintptr_t)sysconf(_SC_PAGESIZE);
+  uintptr_t lo = (uintptr_t)ptr / page * page, hi = ((uintptr_t)ptr + bytes + page - 1) / page * page;
+  std::lock_guard<std::mutex> lk(g_reg_mtx);
+  // subtract what is registered already; register the remaining pieces
+  std::vector<std::pair<uintptr_t, uintptr_t>> todo;
+  uintptr_t cur = lo;
+  for (const HostRange &r : g_reg) {
+    if (r.hi <= cur) continue;
+    if (r.lo >= hi) break;
+    if (r.lo > cur) todo.push_back({cur, r.lo});
+    cur = std::max(cur, r.hi);
+    if (cur >= hi) break;
+  }
+  if (cur < hi) todo.push_back({cur, hi});
+  for (auto &t : todo) {
+    cudaError_t e = cudaHostRegister((void *)t.first, t.second - t.first, cudaHostRegisterPortable | cudaHostRegisterMapped);
+    if (e != cudaSuccess) {
+      cudaGetLastError();
+      g_create_error = std::string("cudaHostRegister: ") + cudaGetErrorString(e);
+      return JRB_ERR_CUDA;
+    }
+    void *dev = nullptr;
+    e = cudaHostGetDevicePointer(&dev, (void *)t.first, 0);
+    if (e != cudaSuccess) { cudaGetLastError(); cudaHostUnregister((void *)t.first); g_create_error = std::string("cudaHostGetDevicePointer: ") + cudaGetErrorString(e); return JRB_ERR_CUDA; }
+    HostRange r{t.first, t.second, (char *)dev};
+    g_reg.insert(std::upper_bound(g_reg.begin(), g_reg.end(), r, [](const HostRange &a, const HostRange &b) { return a.lo < b.lo; }), r);
+  }
+  return JRB_OK;
+}
+
+// releases the registered ranges that lie completely inside [ptr, ptr+bytes) (page granular)
+int jrb_host_unregister(void *ptr, size_t bytes) {
+  if (!ptr || bytes == 0) return JRB_ERR_ARG;
+  const uintptr_t page = (uintptr_t)sysconf(_SC_PAGESIZE);
+  const uintptr_t lo = (uintptr_t)ptr / page * page, hi = ((uintptr_t)ptr + bytes + page - 1) / page * page;
+  std::lock_guard<std::mutex> lk(g_reg_mtx);
+  for (size_t i = 0; i < g_reg.size();) {
+    if (g_reg[i].lo >= lo && g_reg[i].hi <= hi) {
+      if (cudaHostUnregister((void *)g_reg[i].lo) != cudaSuccess) cudaGetLastError();
+      g_reg.erase(g_reg.begin() + (long)i);
+    } else ++i;
+  }
+  return JRB_OK;
+}
+
+int jrb_host_unregister_all(void) {
+  std::lock_guard<std::mutex> lk(g_reg_mtx);
+  for (const HostRange &r : g_reg) if (cudaHostUnregister((void *)r.lo) != cudaSuccess) cudaGetLastError();
+  g_reg.clear();
+  return JRB_OK;
+}
+
+// 1 if [ptr, ptr+bytes) lies in memory registered with jrb_host_register
+int jrb_host_is_registered(const void *ptr, size_t bytes) {
+  std::lock_guard<std::mutex> lk(g_reg_mtx);
+  return registered_dev_ptr(ptr, bytes) != nullptr;
 }
 
 // ---- hydrostatic adjustment on the host (hydrostatic_1d_h2o, src/jr_common.h:714-761; default off) -----------
@@ -370,110 +527,222 @@ static void hydrostatic_host(const jrb_atm_view &a, double hydz, int ig_h2o) {
   }
 }
 
-int jrb_stage(jrb_context *ctx, int npk, const jrb_atm_view *atm, const jrb_obs_view *obs) {
-  if (!ctx || npk < 0 || (npk > 0 && (!atm || !obs))) return JRB_ERR_ARG;
-  std::lock_guard<std::mutex> lk(ctx->mtx);
-  if (!ctx->have_ctl || !ctx->have_tbl) return ctx->fail(JRB_ERR_STATE, "control and tables must be set before staging");
+// channels per warp of the specialised kernel: all of them for few-channel instruments; otherwise 32 unless the tables of
+// (32 channels x ng gases) cannot stay in L2 -- then narrower channel groups with several rays per warp (channel-group-major
+// order keeps the hot set at cpw x ng pairs).  Hot bytes per (gas, channel) pair: ~30 % of its brackets (measured on the
+// synthetic sets: a package touches 357 KB of a 1.26 MB pair); budget 0.7 x L2, which reproduces the measured optima
+// (Config D, 57 MB at 32 channels: 32 = 16 > 8; Config E, 94 MB: 16 best, -4 %; 30 gases, 343 MB: 8 best, -14 %).
+static int choose_cpw(const jrb_context *ctx) {
+  const int nd = ctx->nd, ng = ctx->ng;
+  int cpw = nd <= 16 ? nd : 32;
+  if (nd > 16 && ng > 0) {
+    const double pair_hot = 0.3 * 16.0 * (double)ctx->tbl->th.n_entries / ((double)ng * nd);
+    while (cpw > 4 && pair_hot * cpw * ng > 0.7 * (double)ctx->l2_bytes) cpw >>= 1;
+  }
+  if (const char *s = getenv("JRB_EGA_CPW")) { const int v = atoi(s); if (v >= 1 && v <= 32 && (v == nd || (32 % v == 0 && v <= nd))) cpw = v; } // experiments
+  return cpw;
+}
+
+// save_mask (src/jr_common.h:193-200) for one package: the (ray, channel) pairs whose input radiance is not finite; the
+// columns [nd, nd_reset) are reset here in direct mode (the kernels only write the first nd)
+static void scan_package(const jrb_obs_view &o, long long r0, int nd, bool reset_tail, std::vector<std::pair<long long, int>> &mask) {
+  for (int ir = 0; ir < o.nr; ir++) {
+    const double *row = o.rad + (size_t)ir * o.row_stride;
+    // a row is finite iff its sum of (x - x) is 0; only rows that fail this cheap test are inspected element-wise
+    double probe = 0.0;
+    for (int id = 0; id < nd; id++) probe += row[id] - row[id];
+    if (probe != 0.0 || probe != probe)
+      for (int id = 0; id < nd; id++)
+        if (!std::isfinite(row[id])) mask.push_back({r0 + ir, id});
+    if (reset_tail) {
+      double *rr = o.rad + (size_t)ir * o.row_stride, *tt = o.tau + (size_t)ir * o.row_stride;
+      for (int id = nd; id < o.nd_reset; id++) { rr[id] = 0.0; tt[id] = 1.0; } // all ND columns are reset (src/CPUdrivers.c:58-60)
+    }
+  }
+}
+
+static int stage_locked(jrb_context *ctx, int npk, const jrb_atm_view *atm, const jrb_obs_view *obs) {
+  ctx->invalidate(); // whatever was staged before is gone, whether or not this call succeeds
+  if (!ctx->have_ctl || !ctx->have_tbl()) return ctx->fail(JRB_ERR_STATE, "control and tables must be set before staging");
   CU(cudaSetDevice(ctx->device));
   const int ng = ctx->ng, nd = ctx->nd, nw = ctx->nw;
+  const TblHeader &th = ctx->tbl->th;
+  const double t_begin = now_ms();
 
-  ctx->npk = npk;
-  ctx->pk_nr.resize(npk);
-  ctx->pk_ray_off.resize(npk + 1);
-  std::vector<long long> atm_off(npk + 1);
   long long R = 0, A = 0;
   for (int k = 0; k < npk; k++) {
     if (obs[k].nr < 0 || atm[k].np < 1) return ctx->fail(JRB_ERR_ARG, "package with nr < 0 or empty atmosphere");
-    ctx->pk_nr[k] = obs[k].nr;
-    ctx->pk_ray_off[k] = R; atm_off[k] = A;
     R += obs[k].nr; A += atm[k].np;
   }
-  ctx->pk_ray_off[npk] = R; atm_off[npk] = A;
-  ctx->n_rays = R; ctx->n_atm = A;
+
+  // ---- kernel choice (before anything is allocated) ----
+  const int cpw = choose_cpw(ctx);
+  const LosLayout los_fast = make_los_layout(ng, nw, 1, th.gas_axes_same);
+  const bool fits = ega_fast_fits(ng, los_fast.head, cpw, (size_t)ctx->smem_optin);
+  const bool fast_ok = th.all_shared && th.max_nu <= 1023 && ega_fast_available(ng, ctx->ctm_mask) && fits;
+  if (ctx->variant_req == 1 && !fast_ok)
+    return ctx->fail(JRB_ERR_STATE, std::string("specialised kernel not applicable: shared_axes=") + std::to_string(th.all_shared) +
+                     " monotone=" + std::to_string(th.monotone) + " max_nu=" + std::to_string(th.max_nu) + " ng=" + std::to_string(ng) + " mask=" + std::to_string(ctx->ctm_mask) +
+                     " built=" + std::to_string((int)ega_fast_available(ng, ctx->ctm_mask)) + " fits_shared_memory=" + std::to_string((int)fits));
+  const int use_fast = (ctx->variant_req == 0) ? 0 : (fast_ok ? 1 : 0);
+
+  // ---- package tables (offsets, output addresses, input addresses) in one small pinned buffer ----
+  const int n_geo = 7, n_af = 6 + ng + nw, n_src = n_geo + n_af;
+  const size_t off_roff = 0, off_aoff = off_roff + (size_t)(npk + 1) * 8, off_out = off_aoff + (size_t)(npk + 1) * 8;
+  const size_t off_src = off_out + (size_t)npk * sizeof(OutTab);
+  const size_t tab_bytes = align_up(off_src + (size_t)npk * n_src * 8, 256) + 256;
+  CU(ctx->h_tab.ensure(tab_bytes));
+  CU(ctx->d_tab.ensure(tab_bytes));
+  unsigned char *HT = (unsigned char *)ctx->h_tab.p;
+  long long *h_roff = (long long *)(HT + off_roff), *h_aoff = (long long *)(HT + off_aoff);
+  OutTab *h_outtab = (OutTab *)(HT + off_out);
+  const double **h_src = (const double **)(HT + off_src);
+
+  ctx->pk_nr.resize(npk);
+  ctx->pk_ray_off.resize(npk + 1);
+  {
+    long long r = 0, a = 0;
+    for (int k = 0; k < npk; k++) {
+      ctx->pk_nr[k] = obs[k].nr;
+      ctx->pk_ray_off[k] = r; h_roff[k] = r; h_aoff[k] = a;
+      r += obs[k].nr; a += atm[k].np;
+    }
+    ctx->pk_ray_off[npk] = r; h_roff[npk] = r; h_aoff[npk] = a;
+  }
+
+  // ---- I/O mode: direct if every array of every package lies in registered (page-locked, mapped) memory ----
+  bool direct = npk > 0 && !getenv("JRB_NO_DIRECT_IO");
+  if (direct) {
+    std::lock_guard<std::mutex> rl(g_reg_mtx);
+    if (g_reg.empty()) direct = false;
+    for (int k = 0; k < npk && direct; k++) {
+      const jrb_obs_view &o = obs[k];
+      const jrb_atm_view &a = atm[k];
+      const size_t nrb = (size_t)o.nr * 8, npb = (size_t)a.np * 8;
+      const double **s = h_src + (size_t)k * n_src;
+      const double *geo_in[7] = {o.obsz, o.obslon, o.obslat, o.vpz, o.vplon, o.vplat, o.time};
+      for (int f = 0; f < 7; f++) s[f] = (const double *)registered_dev_ptr(geo_in[f], nrb);
+      const double *atm_in[6] = {a.time, a.z, a.lon, a.lat, a.p, a.t};
+      for (int f = 0; f < 6; f++) s[7 + f] = (const double *)registered_dev_ptr(atm_in[f], npb);
+      for (int ig = 0; ig < ng; ig++)
+        s[13 + ig] = (const double *)registered_dev_ptr(a.q_rows ? a.q_rows[ig] : a.q + (size_t)ig * a.q_stride, npb);
+      for (int iw = 0; iw < nw; iw++)
+        s[13 + ng + iw] = (const double *)registered_dev_ptr(a.k_rows ? a.k_rows[iw] : a.k + (size_t)iw * a.k_stride, npb);
+      for (int f = 0; f < n_src; f++) if (!s[f]) direct = false;
+      OutTab &t = h_outtab[k];
+      const size_t rows = o.nr > 0 ? ((size_t)(o.nr - 1) * o.row_stride + nd) * 8 : 8;
+      t.rad = (double *)registered_dev_ptr(o.rad, rows); t.tau = (double *)registered_dev_ptr(o.tau, rows);
+      t.tpz = (double *)registered_dev_ptr(o.tpz, nrb); t.tplon = (double *)registered_dev_ptr(o.tplon, nrb);
+      t.tplat = (double *)registered_dev_ptr(o.tplat, nrb);
+      t.stride = o.row_stride;
+      if (!t.rad || !t.tau || !t.tpz || !t.tplon || !t.tplat) direct = false;
+    }
+  }
 
   if (ctx->hydz >= 0) // modifies the caller's atm->p like the reference's CPU path (src/CPUdrivers.c:97-103)
     for (int k = 0; k < npk; k++) hydrostatic_host(atm[k], ctx->hydz, ctx->ig_h2o);
 
-  // staging buffer layout (doubles first, then integers)
-  const size_t n_geo = 7 * (size_t)R, n_atm = (size_t)(6 + ng + nw) * A;
-  const size_t off_geo = 0, off_atm = off_geo + n_geo * 8, off_poff = align_up(off_atm + n_atm * 8, 8);
-  const size_t off_rpk = off_poff + (size_t)npk * 8, off_pnp = off_rpk + (size_t)R * 4;
-  const size_t in_bytes = align_up(off_pnp + (size_t)npk * 4, 256) + 256;
-  CU(ctx->h_in.ensure(in_bytes));
+  // ---- device arrays ----
+  const size_t n_geo_d = 7 * (size_t)R, n_atm_d = (size_t)n_af * A;
+  const size_t off_geo = 0, off_atm = off_geo + n_geo_d * 8;
+  const size_t in_bytes = align_up(off_atm + n_atm_d * 8, 256) + 256;
   CU(ctx->d_in.ensure(in_bytes));
-  unsigned char *H = (unsigned char *)ctx->h_in.p;
-  double *hgeo = (double *)(H + off_geo), *hatm = (double *)(H + off_atm);
-  long long *hpoff = (long long *)(H + off_poff);
-  int *hrpk = (int *)(H + off_rpk), *hpnp = (int *)(H + off_pnp);
-
-  const double t_pack0 = now_ms();
-  ctx->nan_mask.clear();
-  std::vector<std::vector<std::pair<long long, int>>> masks(npk);
-#pragma omp parallel for schedule(dynamic, 4) num_threads(host_threads())
-  for (int k = 0; k < npk; k++) {
-    const jrb_obs_view &o = obs[k];
-    const jrb_atm_view &a = atm[k];
-    const long long r0 = ctx->pk_ray_off[k], a0 = atm_off[k];
-    const size_t nrb = (size_t)o.nr * 8, npb = (size_t)a.np * 8;
-    std::memcpy(hgeo + 0 * R + r0, o.obsz, nrb);
-    std::memcpy(hgeo + 1 * R + r0, o.obslon, nrb);
-    std::memcpy(hgeo + 2 * R + r0, o.obslat, nrb);
-    std::memcpy(hgeo + 3 * R + r0, o.vpz, nrb);
-    std::memcpy(hgeo + 4 * R + r0, o.vplon, nrb);
-    std::memcpy(hgeo + 5 * R + r0, o.vplat, nrb);
-    std::memcpy(hgeo + 6 * R + r0, o.time, nrb);
-    std::memcpy(hatm + 0 * A + a0, a.time, npb);
-    std::memcpy(hatm + 1 * A + a0, a.z, npb);
-    std::memcpy(hatm + 2 * A + a0, a.lon, npb);
-    std::memcpy(hatm + 3 * A + a0, a.lat, npb);
-    std::memcpy(hatm + 4 * A + a0, a.p, npb);
-    std::memcpy(hatm + 5 * A + a0, a.t, npb);
-    for (int ig = 0; ig < ng; ig++)
-      std::memcpy(hatm + (size_t)(6 + ig) * A + a0, a.q_rows ? a.q_rows[ig] : a.q + (size_t)ig * a.q_stride, npb);
-    for (int iw = 0; iw < nw; iw++)
-      std::memcpy(hatm + (size_t)(6 + ng + iw) * A + a0, a.k_rows ? a.k_rows[iw] : a.k + (size_t)iw * a.k_stride, npb);
-    hpoff[k] = a0; hpnp[k] = a.np;
-    for (int ir = 0; ir < o.nr; ir++) {
-      hrpk[r0 + ir] = k;
-      const double *row = o.rad + (size_t)ir * o.row_stride; // save_mask (src/jr_common.h:193-200)
-      // a row is finite iff its sum of (x - x) is 0; only rows that fail this cheap test are inspected element-wise
-      double probe = 0.0;
-      for (int id = 0; id < nd; id++) probe += row[id] - row[id];
-      if (probe != 0.0 || probe != probe)
-        for (int id = 0; id < nd; id++)
-          if (!std::isfinite(row[id])) masks[k].push_back({r0 + ir, id});
-    }
-  }
-  for (int k = 0; k < npk; k++) ctx->nan_mask.insert(ctx->nan_mask.end(), masks[k].begin(), masks[k].end());
-
-  const double t_pack1 = now_ms();
-  CU(cudaMemcpyAsync(ctx->d_in.p, H, in_bytes, cudaMemcpyHostToDevice, ctx->stream));
   unsigned char *Dv = (unsigned char *)ctx->d_in.p;
   ctx->geo = (double *)(Dv + off_geo); ctx->atm = (double *)(Dv + off_atm);
-  ctx->pkg_atm_off = (long long *)(Dv + off_poff); ctx->ray_pkg = (int *)(Dv + off_rpk); ctx->pkg_atm_np = (int *)(Dv + off_pnp);
-
-  // outputs
+  CU(ctx->d_raypkg.ensure((size_t)(R ? R : 1) * 4));
+  CU(ctx->d_pkgnp.ensure((size_t)(npk ? npk : 1) * 4));
+  ctx->ray_pkg = (int *)ctx->d_raypkg.p; ctx->pkg_atm_np = (int *)ctx->d_pkgnp.p;
+  unsigned char *DT = (unsigned char *)ctx->d_tab.p;
+  ctx->pkg_atm_off = (long long *)(DT + off_aoff);
   const size_t out_bytes = ((size_t)2 * R * nd + 3 * (size_t)R) * 8 + 256;
   CU(ctx->d_out.ensure(out_bytes));
   ctx->o_rad = (double *)ctx->d_out.p; ctx->o_tau = ctx->o_rad + (size_t)R * nd; ctx->o_tp = ctx->o_tau + (size_t)R * nd;
+  CU(ctx->d_rayout.ensure((size_t)5 * (R ? R : 1) * 8));
+  ctx->ray_out = (double **)ctx->d_rayout.p;
   CU(ctx->d_np.ensure((size_t)(R ? R : 1) * 4));
   CU(ctx->d_tsurf.ensure((size_t)(R ? R : 1) * 8));
   CU(ctx->d_slope.ensure((size_t)(A ? A : 1) * 16));
   CU(ctx->d_level0.ensure((size_t)(R ? R : 1) * 4));
 
-  // kernel choice + LOS buffer
-  const bool fast_ok = ctx->th.all_shared && ctx->th.max_nu <= 1023 && ega_fast_available(ng, ctx->ctm_mask);
-  if (ctx->variant_req == 1 && !fast_ok)
-    return ctx->fail(JRB_ERR_STATE, std::string("specialised kernel not applicable: shared_axes=") + std::to_string(ctx->th.all_shared) +
-                     " monotone=" + std::to_string(ctx->th.monotone) + " max_nu=" + std::to_string(ctx->th.max_nu) + " ng=" + std::to_string(ng) + " mask=" + std::to_string(ctx->ctm_mask) +
-                     " built=" + std::to_string((int)ega_fast_available(ng, ctx->ctm_mask)));
-  ctx->use_fast = (ctx->variant_req == 0) ? 0 : (fast_ok ? 1 : 0);
-  ctx->los = make_los_layout(ng, nw, ctx->use_fast, ctx->th.gas_axes_same);
+  double t_pack0 = now_ms(), t_pack1 = t_pack0;
+  ctx->nan_mask.clear();
+  std::vector<std::vector<std::pair<long long, int>>> masks(npk);
+  size_t h2d_bytes = tab_bytes;
+  if (!direct) {
+    // staged mode: pack the populated prefixes into the pinned buffer; results go to the pinned result buffer
+    CU(ctx->h_in.ensure(in_bytes));
+    CU(ctx->h_out.ensure(out_bytes));
+    unsigned char *H = (unsigned char *)ctx->h_in.p;
+    double *hgeo = (double *)(H + off_geo), *hatm = (double *)(H + off_atm);
+    double *hrad = (double *)ctx->h_out.p, *htau = hrad + (size_t)R * nd, *htp = htau + (size_t)R * nd;
+#pragma omp parallel for schedule(dynamic, 4) num_threads(host_threads())
+    for (int k = 0; k < npk; k++) {
+      const jrb_obs_view &o = obs[k];
+      const jrb_atm_view &a = atm[k];
+      const long long r0 = ctx->pk_ray_off[k], a0 = h_aoff[k];
+      const size_t nrb = (size_t)o.nr * 8, npb = (size_t)a.np * 8;
+      std::memcpy(hgeo + 0 * R + r0, o.obsz, nrb);
+      std::memcpy(hgeo + 1 * R + r0, o.obslon, nrb);
+      std::memcpy(hgeo + 2 * R + r0, o.obslat, nrb);
+      std::memcpy(hgeo + 3 * R + r0, o.vpz, nrb);
+      std::memcpy(hgeo + 4 * R + r0, o.vplon, nrb);
+      std::memcpy(hgeo + 5 * R + r0, o.vplat, nrb);
+      std::memcpy(hgeo + 6 * R + r0, o.time, nrb);
+      std::memcpy(hatm + 0 * A + a0, a.time, npb);
+      std::memcpy(hatm + 1 * A + a0, a.z, npb);
+      std::memcpy(hatm + 2 * A + a0, a.lon, npb);
+      std::memcpy(hatm + 3 * A + a0, a.lat, npb);
+      std::memcpy(hatm + 4 * A + a0, a.p, npb);
+      std::memcpy(hatm + 5 * A + a0, a.t, npb);
+      for (int ig = 0; ig < ng; ig++)
+        std::memcpy(hatm + (size_t)(6 + ig) * A + a0, a.q_rows ? a.q_rows[ig] : a.q + (size_t)ig * a.q_stride, npb);
+      for (int iw = 0; iw < nw; iw++)
+        std::memcpy(hatm + (size_t)(6 + ng + iw) * A + a0, a.k_rows ? a.k_rows[iw] : a.k + (size_t)iw * a.k_stride, npb);
+      scan_package(o, r0, nd, false, masks[k]);
+      OutTab &t = h_outtab[k]; // device address == host address for cudaHostAlloc'ed mapped memory (unified addressing)
+      t.rad = hrad + (size_t)r0 * nd; t.tau = htau + (size_t)r0 * nd;
+      t.tpz = htp + 0 * R + r0; t.tplon = htp + 1 * R + r0; t.tplat = htp + 2 * R + r0;
+      t.stride = nd;
+    }
+    t_pack1 = now_ms();
+    CU(cudaMemcpyAsync(ctx->d_in.p, H, in_bytes, cudaMemcpyHostToDevice, ctx->stream));
+    h2d_bytes += in_bytes;
+  }
+  CU(cudaMemcpyAsync(ctx->d_tab.p, HT, tab_bytes, cudaMemcpyHostToDevice, ctx->stream));
+  {
+    StageArgs sa;
+    sa.npk = npk; sa.n_geo = n_geo; sa.n_atm_fields = n_af;
+    sa.ray_off = (const long long *)(DT + off_roff); sa.atm_off = (const long long *)(DT + off_aoff);
+    sa.src = direct ? (const double *const *)(DT + off_src) : nullptr;
+    sa.geo = ctx->geo; sa.R = R; sa.atm = ctx->atm; sa.A = A;
+    sa.ray_pkg = ctx->ray_pkg; sa.pkg_atm_np = ctx->pkg_atm_np;
+    sa.out = (const OutTab *)(DT + off_out); sa.ray_out = ctx->ray_out;
+    CU(launch_stage(sa, ctx->stream));
+  }
+  if (direct) {
+    // the staging kernel is pulling the inputs over PCIe meanwhile: NaN-mask scan and reset of the columns beyond nd
+    // (both touch only the caller's rad/tau rows, which the device does not read)
+#pragma omp parallel for schedule(dynamic, 4) num_threads(host_threads())
+    for (int k = 0; k < npk; k++) scan_package(obs[k], ctx->pk_ray_off[k], nd, obs[k].nd_reset > nd, masks[k]);
+    t_pack1 = now_ms();
+    long long in_b = 0;
+    for (int k = 0; k < npk; k++) in_b += (long long)obs[k].nr * 8 * 7 + (long long)atm[k].np * 8 * n_af;
+    h2d_bytes += (size_t)in_b; // read by the staging kernel from the caller's memory
+  }
+  for (int k = 0; k < npk; k++) ctx->nan_mask.insert(ctx->nan_mask.end(), masks[k].begin(), masks[k].end());
+  ctx->st_obs.assign(obs, obs + npk);
+
+  // ---- LOS buffer ----
+  ctx->use_fast = use_fast;
+  ctx->cpw = cpw;
+  ctx->los = make_los_layout(ng, nw, use_fast, th.gas_axes_same);
   const size_t per_ray = (size_t)kNLOS * ctx->los.rec * 8;
-  // LOS scratch: JRB_LOS_GB (default 24 GB), but never more than half of what is free on the device.  The driver is only
-  // asked (cudaMemGetInfo takes a device-wide lock and was seen to stall for tens of ms) when the buffer has to grow.
-  double los_gb = 24.0;
+  // LOS scratch: JRB_LOS_GB / jrb_set_los_limit_gb (default 72 GB: the 1 000 960 rays of BASELINE's config D need 64 GB),
+  // but never more than half of what is free on the device.  The driver is only asked (cudaMemGetInfo takes a
+  // device-wide lock and was seen to stall for tens of ms) when the buffer has to grow.
+  double los_gb = 72.0;
   if (const char *s = getenv("JRB_LOS_GB")) { double v = atof(s); if (v > 0.01) los_gb = v; }
+  if (ctx->los_limit_gb > 0) los_gb = ctx->los_limit_gb;
   if ((double)R * (double)per_ray > (double)ctx->d_los.cap) {
     size_t free_b = 0, total_b = 0;
     if (cudaMemGetInfo(&free_b, &total_b) == cudaSuccess) {
@@ -499,6 +768,8 @@ int jrb_stage(jrb_context *ctx, int npk, const jrb_atm_view *atm, const jrb_obs_
   }
   if (chunk < 1024) chunk = 1024;
   if (chunk > R) chunk = R;
+  // equal chunks: the last one is not a short straggler
+  if (chunk > 0 && ctx->nbuf == 1) { const long long nch = (R + chunk - 1) / chunk; chunk = (R + nch - 1) / nch; }
   ctx->chunk_rays = chunk;
   CU(ctx->d_los.ensure((size_t)(chunk ? chunk : 1) * per_ray * ctx->nbuf));
   {
@@ -507,23 +778,36 @@ int jrb_stage(jrb_context *ctx, int npk, const jrb_atm_view *atm, const jrb_obs_
   }
 
   CU(cudaStreamSynchronize(ctx->stream));
+  ctx->npk = npk; ctx->n_rays = R; ctx->n_atm = A;
+  ctx->direct = direct;
   ctx->stats.host_ms_pack = (float)(t_pack1 - t_pack0);
   ctx->stats.host_ms_h2d = (float)(now_ms() - t_pack1);
-  ctx->stats.h2d_bytes = (long long)in_bytes;
+  ctx->stats.host_ms_stage = (float)(now_ms() - t_begin);
+  ctx->stats.h2d_bytes = (long long)h2d_bytes;
+  ctx->stats.io_direct = direct ? 1 : 0;
   ctx->stats.n_packages = npk; ctx->stats.n_rays = R; ctx->stats.n_ray_channels = R * nd;
-  ctx->staged = true; ctx->ran = false; ctx->np_fetched = false;
+  ctx->stats.cum_runs = ctx->stats.cum_launches = ctx->stats.cum_ega_launches = 0;
+  ctx->stats.cum_ms_ega = ctx->stats.cum_ms_raytrace = ctx->stats.cum_ms_device = 0.0;
+  ctx->staged = true; ctx->np_fetched = false;
   return JRB_OK;
 }
 
-int jrb_run_staged(jrb_context *ctx) {
-  if (!ctx) return JRB_ERR_ARG;
+int jrb_stage(jrb_context *ctx, int npk, const jrb_atm_view *atm, const jrb_obs_view *obs) {
+  if (!ctx || npk < 0 || (npk > 0 && (!atm || !obs))) return JRB_ERR_ARG;
   std::lock_guard<std::mutex> lk(ctx->mtx);
+  return stage_locked(ctx, npk, atm, obs);
+}
+
+static int run_locked(jrb_context *ctx) {
   if (!ctx->staged) return ctx->fail(JRB_ERR_STATE, "nothing staged");
+  ctx->ran = false;
   CU(cudaSetDevice(ctx->device));
   const long long R = ctx->n_rays, A = ctx->n_atm;
   const int ng = ctx->ng, nd = ctx->nd, nw = ctx->nw;
+  const TblHeader &th = ctx->tbl->th;
   const long long nchunks = R > 0 ? (R + ctx->chunk_rays - 1) / ctx->chunk_rays : 0;
   const bool pipe = ctx->nbuf > 1 && nchunks > 1;
+  const bool fov = ctx->fov_n > 0 && R > 0;
   // events: [0] start, [1] end, per chunk: tracer start / tracer done / EGA start / EGA done
   const size_t need_ev = 2 + 4 * (size_t)nchunks;
   while (ctx->events.size() < need_ev) { cudaEvent_t ev; CU(cudaEventCreate(&ev)); ctx->events.push_back(ev); }
@@ -555,7 +839,8 @@ int jrb_run_staged(jrb_context *ctx) {
     t.ray_np = (int *)ctx->d_np.p + r0; t.ray_tsurf = (double *)ctx->d_tsurf.p + r0;
     t.ray_level0 = (int *)ctx->d_level0.p + r0;
     t.tp = ctx->o_tp + r0;
-    t.tbl = ctx->td;
+    t.tp_host = ctx->ray_out + 2 * R + r0;
+    t.tbl = ctx->tbl->td;
     if (pipe && c >= ctx->nbuf) CU(cudaStreamWaitEvent(st_tr, EV(c - ctx->nbuf, 3), 0)); // LOS buffer free again
     CU(cudaEventRecord(EV(c, 0), st_tr));
     int nl = 0;
@@ -567,29 +852,20 @@ int jrb_run_staged(jrb_context *ctx) {
     e.n_rays = r1 - r0; e.ng = ng; e.nd = nd; e.nw = nw;
     e.ctm_mask = ctx->ctm_mask; e.ig_co2 = ctx->ig_co2 >= 0 ? ctx->ig_co2 : 0; e.ig_h2o = ctx->ig_h2o >= 0 ? ctx->ig_h2o : 0;
     e.write_bbt = ctx->write_bbt;
-    e.unsorted_columns = ctx->th.monotone ? 0 : 1;
+    e.unsorted_columns = th.monotone ? 0 : 1;
     e.los = ctx->los; e.los_data = los_buf;
     e.ray_np = (const int *)ctx->d_np.p + r0; e.ray_tsurf = (const double *)ctx->d_tsurf.p + r0;
     e.chan = (const double *)ctx->d_chan.p; e.window = (const int *)ctx->d_window.p;
-    e.tbl = ctx->td;
+    e.tbl = ctx->tbl->td;
     e.rad = ctx->o_rad + (size_t)r0 * nd; e.tau = ctx->o_tau + (size_t)r0 * nd;
+    // with the FOV epilogue the pencil-beam values stay on the device; the convolved ones are published afterwards
+    e.rad_host = fov ? nullptr : ctx->ray_out + 0 * R + r0;
+    e.tau_host = fov ? nullptr : ctx->ray_out + 1 * R + r0;
     e.work_counter = (unsigned long long *)ctx->d_counter.p + 4 * c;
     e.balance = e.work_counter + 1;
     e.phase_lock_mode = -1;
     if (const char *s = getenv("JRB_EGA_LOCKSTEP")) { const int v = atoi(s); if (v == 0 || v == 1) e.phase_lock_mode = v; } // experiments
-    // channels per warp: all of them for few-channel instruments; otherwise 32 unless the tables of (32 channels x ng
-    // gases) cannot stay in L2 -- then narrower channel groups with several rays per warp (channel-group-major order keeps
-    // the hot set at cpw x ng pairs).  Hot bytes per (gas, channel) pair: ~30 % of its brackets (measured on the synthetic
-    // sets: a package touches 357 KB of a 1.26 MB pair); budget 0.7 x L2, which reproduces the measured optima (Config D,
-    // 57 MB at 32 channels: 32 = 16 > 8; Config E, 94 MB: 16 best, -4 %; 30 gases, 343 MB: 8 best, -14 %).
-    e.cpw = nd <= 16 ? nd : 32;
-    if (nd > 16 && ng > 0) {
-      const double pair_hot = 0.3 * 16.0 * (double)ctx->th.n_entries / ((double)ng * nd);
-      int l2 = 0;
-      cudaDeviceGetAttribute(&l2, cudaDevAttrL2CacheSize, ctx->device);
-      while (e.cpw > 4 && pair_hot * e.cpw * ng > 0.7 * (double)l2) e.cpw >>= 1;
-    }
-    if (const char *s = getenv("JRB_EGA_CPW")) { const int v = atoi(s); if (v >= 1 && v <= 32 && (v == nd || (32 % v == 0 && v <= nd))) e.cpw = v; } // experiments
+    e.cpw = ctx->cpw;
     ctx->stats.ega_channels_per_warp = ctx->use_fast ? e.cpw : 0;
     e.work_chunk = 0; // 0: the launcher picks one item per warp of the CTA
     if (const char *s = getenv("JRB_EGA_CHUNK")) { const int v = atoi(s); if (v >= 1 && v <= 200) e.work_chunk = v; } // experiments
@@ -605,7 +881,7 @@ int jrb_run_staged(jrb_context *ctx) {
     if (nchunks > 1) CU(cudaStreamWaitEvent(ctx->stream, EV(nchunks - 2, 3), 0));
   }
   ctx->fov_applied = false;
-  if (ctx->fov_n > 0 && R > 0) { // formod(); formod_fov(); of the reference: mask first, then convolve
+  if (fov) { // formod(); formod_fov(); of the reference: mask first, then convolve
     const size_t n_out = (size_t)R * nd;
     CU(ctx->d_fov_out.ensure(2 * n_out * 8));
     CU(ctx->d_flag.ensure(256));
@@ -629,6 +905,8 @@ int jrb_run_staged(jrb_context *ctx) {
     CU(launch_fov(f, ctx->stream));
     launches++;
     CU(cudaMemcpyAsync(ctx->o_rad, f.rad_out, 2 * n_out * 8, cudaMemcpyDeviceToDevice, ctx->stream)); // o_tau follows o_rad
+    CU(launch_publish(ctx->o_rad, ctx->o_tau, ctx->ray_out + 0 * R, ctx->ray_out + 1 * R, R, nd, ctx->stream));
+    launches++;
     ctx->fov_applied = true;
   }
   CU(cudaEventRecord(ctx->events[1], ctx->stream));
@@ -637,6 +915,22 @@ int jrb_run_staged(jrb_context *ctx) {
     int flag = 0;
     CU(cudaMemcpy(&flag, ctx->d_flag.p, 4, cudaMemcpyDeviceToHost));
     if (flag) return ctx->fail(JRB_ERR_ARG, "Cannot apply FOV convolution!"); // src/jurassic.c:236
+  }
+  // apply_mask (src/jr_common.h:203-210) where the results have landed: the caller's rows (direct) or the pinned buffer
+  // (with the FOV epilogue the mask went in on the device, before the convolution)
+  if (!ctx->fov_applied && !ctx->nan_mask.empty()) {
+    const double nan = std::nan("");
+    if (ctx->direct) {
+      size_t k = 0;
+      for (auto &m : ctx->nan_mask) {
+        while (m.first >= ctx->pk_ray_off[k + 1]) ++k;
+        const jrb_obs_view &o = ctx->st_obs[k];
+        o.rad[(size_t)(m.first - ctx->pk_ray_off[k]) * o.row_stride + m.second] = nan;
+      }
+    } else {
+      double *hrad = (double *)ctx->h_out.p;
+      for (auto &m : ctx->nan_mask) hrad[(size_t)m.first * nd + m.second] = nan;
+    }
   }
   float ms_rt = 0, ms_ega = 0, ms_tot = 0, ms;
   for (long long c = 0; c < nchunks; c++) {
@@ -647,6 +941,8 @@ int jrb_run_staged(jrb_context *ctx) {
   // with pipelined chunks the per-kernel spans overlap each other: ms_raytrace + ms_ega may exceed ms_total_device
   ctx->stats.ms_raytrace = ms_rt; ctx->stats.ms_ega = ms_ega; ctx->stats.ms_total_device = ms_tot;
   ctx->stats.n_kernel_launches = launches;
+  ctx->stats.cum_runs++; ctx->stats.cum_launches += launches; ctx->stats.cum_ega_launches += nchunks;
+  ctx->stats.cum_ms_ega += ms_ega; ctx->stats.cum_ms_raytrace += ms_rt; ctx->stats.cum_ms_device += ms_tot;
   ctx->stats.n_chunks = (int)nchunks; ctx->stats.pipelined = pipe ? 1 : 0;
   ctx->stats.ega_kernel_variant = ctx->use_fast; ctx->stats.ega_ngb = ctx->use_fast ? ngb : 0;
   ctx->stats.ega_ctm_mask = ctx->ctm_mask;
@@ -654,30 +950,43 @@ int jrb_run_staged(jrb_context *ctx) {
   return JRB_OK;
 }
 
-int jrb_fetch_staged(jrb_context *ctx, int npk, const jrb_obs_view *obs) {
-  if (!ctx || (npk > 0 && !obs)) return JRB_ERR_ARG;
+int jrb_run_staged(jrb_context *ctx) {
+  if (!ctx) return JRB_ERR_ARG;
   std::lock_guard<std::mutex> lk(ctx->mtx);
+  return run_locked(ctx);
+}
+
+// staged mode: scatter the pinned result buffer into the caller's obs_t rows; direct mode: the results are there already
+static int fetch_locked(jrb_context *ctx, int npk, const jrb_obs_view *obs) {
   if (!ctx->ran) return ctx->fail(JRB_ERR_STATE, "jrb_run_staged has not completed");
   if (npk != ctx->npk) return ctx->fail(JRB_ERR_ARG, "package count differs from the staged batch");
-  CU(cudaSetDevice(ctx->device));
+  for (int k = 0; k < npk; k++)
+    if (obs[k].nr != ctx->pk_nr[k]) return ctx->fail(JRB_ERR_ARG, "obs[k].nr changed between stage and fetch");
   const long long R = ctx->n_rays;
   const int nd = ctx->nd;
-  const size_t out_bytes = ((size_t)2 * R * nd + 3 * (size_t)R) * 8;
-  CU(ctx->h_out.ensure(out_bytes + 256));
-  const double t_d2h0 = now_ms();
-  CU(cudaMemcpyAsync(ctx->h_out.p, ctx->d_out.p, out_bytes, cudaMemcpyDeviceToHost, ctx->stream));
-  CU(cudaStreamSynchronize(ctx->stream));
-  const double t_d2h1 = now_ms();
-  double *hrad = (double *)ctx->h_out.p, *htau = hrad + (size_t)R * nd, *htp = htau + (size_t)R * nd;
-  const double nan = std::nan("");
-  if (!ctx->fov_applied) // (with the FOV epilogue the mask went in on the device, before the convolution)
-    for (auto &m : ctx->nan_mask) hrad[(size_t)m.first * nd + m.second] = nan; // apply_mask (src/jr_common.h:203-210)
+  const double t0 = now_ms();
+  ctx->stats.d2h_bytes = (long long)(((size_t)2 * R * nd + 3 * (size_t)R) * 8); // stored by the kernels into host memory
+  ctx->stats.host_ms_d2h = 0.f;
+  bool same = ctx->direct;
+  for (int k = 0; k < npk && same; k++)
+    same = obs[k].rad == ctx->st_obs[k].rad && obs[k].tau == ctx->st_obs[k].tau && obs[k].tpz == ctx->st_obs[k].tpz;
+  if (same) { ctx->stats.host_ms_scatter = 0.f; return JRB_OK; }
+  if (ctx->direct) { // results were landed in other (registered) blocks than the ones asked for now: copy from the device
+    CU(cudaSetDevice(ctx->device));
+    const size_t out_bytes = ((size_t)2 * R * nd + 3 * (size_t)R) * 8;
+    CU(ctx->h_out.ensure(out_bytes + 256));
+    CU(cudaMemcpyAsync(ctx->h_out.p, ctx->d_out.p, out_bytes, cudaMemcpyDeviceToHost, ctx->stream));
+    CU(cudaStreamSynchronize(ctx->stream));
+    ctx->stats.host_ms_d2h = (float)(now_ms() - t0);
+    if (!ctx->fov_applied) { const double nan = std::nan(""); for (auto &m : ctx->nan_mask) ((double *)ctx->h_out.p)[(size_t)m.first * nd + m.second] = nan; }
+  }
+  const double *hrad = (const double *)ctx->h_out.p, *htau = hrad + (size_t)R * nd, *htp = htau + (size_t)R * nd;
+  const double t1 = now_ms();
 #pragma omp parallel for schedule(dynamic, 4) num_threads(host_threads())
   for (int k = 0; k < npk; k++) {
     const jrb_obs_view &o = obs[k];
     const long long r0 = ctx->pk_ray_off[k];
     const int nr = ctx->pk_nr[k];
-    if (o.nr != nr) continue;
     std::memcpy(o.tpz, htp + 0 * R + r0, (size_t)nr * 8);
     std::memcpy(o.tplon, htp + 1 * R + r0, (size_t)nr * 8);
     std::memcpy(o.tplat, htp + 2 * R + r0, (size_t)nr * 8);
@@ -693,27 +1002,31 @@ int jrb_fetch_staged(jrb_context *ctx, int npk, const jrb_obs_view *obs) {
       }
     }
   }
-  for (int k = 0; k < npk; k++)
-    if (obs[k].nr != ctx->pk_nr[k]) return ctx->fail(JRB_ERR_ARG, "obs[k].nr changed between stage and fetch");
-  ctx->stats.d2h_bytes = (long long)out_bytes;
-  ctx->stats.host_ms_d2h = (float)(t_d2h1 - t_d2h0);
-  ctx->stats.host_ms_scatter = (float)(now_ms() - t_d2h1);
+  ctx->stats.host_ms_scatter = (float)(now_ms() - t1);
   return JRB_OK;
 }
 
+int jrb_fetch_staged(jrb_context *ctx, int npk, const jrb_obs_view *obs) {
+  if (!ctx || (npk > 0 && !obs)) return JRB_ERR_ARG;
+  std::lock_guard<std::mutex> lk(ctx->mtx);
+  return fetch_locked(ctx, npk, obs);
+}
+
 int jrb_formod_batch(jrb_context *ctx, int npk, const jrb_atm_view *atm, const jrb_obs_view *obs) {
+  if (!ctx || npk < 0 || (npk > 0 && (!atm || !obs))) return JRB_ERR_ARG;
+  std::lock_guard<std::mutex> lk(ctx->mtx); // one batch at a time per context; concurrency = several contexts (lanes)
   const double t0 = now_ms();
-  int rc = jrb_stage(ctx, npk, atm, obs);
+  int rc = stage_locked(ctx, npk, atm, obs);
   if (rc != JRB_OK) return rc;
   const double t1 = now_ms();
-  rc = jrb_run_staged(ctx);
+  rc = run_locked(ctx);
   if (rc != JRB_OK) return rc;
   const double t2 = now_ms();
-  rc = jrb_fetch_staged(ctx, npk, obs);
+  rc = fetch_locked(ctx, npk, obs);
   if (getenv("JRB_DEBUG_TIMING"))
-    fprintf(stderr, "[jrb] stage %.2f ms  run %.2f ms  fetch %.2f ms (pack %.2f h2d %.2f dev %.2f d2h %.2f scatter %.2f)\n", t1 - t0,
-            t2 - t1, now_ms() - t2, ctx->stats.host_ms_pack, ctx->stats.host_ms_h2d, ctx->stats.ms_total_device, ctx->stats.host_ms_d2h,
-            ctx->stats.host_ms_scatter);
+    fprintf(stderr, "[jrb] %s stage %.2f ms  run %.2f ms  fetch %.2f ms (pack %.2f h2d %.2f dev %.2f scatter %.2f)\n",
+            ctx->direct ? "direct" : "staged", t1 - t0, t2 - t1, now_ms() - t2, ctx->stats.host_ms_pack, ctx->stats.host_ms_h2d,
+            ctx->stats.ms_total_device, ctx->stats.host_ms_scatter);
   return rc;
 }
 
@@ -723,6 +1036,18 @@ int jrb_staged_results(jrb_context *ctx, double **rad_dev, double **tau_dev, lon
   if (!ctx->staged) return ctx->fail(JRB_ERR_STATE, "nothing staged");
   if (rad_dev) *rad_dev = ctx->o_rad;
   if (tau_dev) *tau_dev = ctx->o_tau;
+  if (n_rays) *n_rays = ctx->n_rays;
+  if (nd) *nd = ctx->nd;
+  return JRB_OK;
+}
+
+// the compact device results of the last run as one block: rad[R][nd], tau[R][nd], tpz[R], tplon[R], tplat[R]
+int jrb_staged_results_blob(jrb_context *ctx, void **dev, size_t *bytes, long long *n_rays, int *nd) {
+  if (!ctx) return JRB_ERR_ARG;
+  std::lock_guard<std::mutex> lk(ctx->mtx);
+  if (!ctx->ran) return ctx->fail(JRB_ERR_STATE, "no completed run");
+  if (dev) *dev = ctx->d_out.p;
+  if (bytes) *bytes = ((size_t)2 * ctx->n_rays * ctx->nd + 3 * (size_t)ctx->n_rays) * 8;
   if (n_rays) *n_rays = ctx->n_rays;
   if (nd) *nd = ctx->nd;
   return JRB_OK;
