@@ -104,6 +104,8 @@ typedef struct {
   /* accumulated over all runs since the batch was staged (CUDA-event times; one EGA launch per run and LOS chunk) */
   long long cum_runs, cum_launches, cum_ega_launches;
   double cum_ms_ega, cum_ms_raytrace, cum_ms_device;
+  int ega_per_channel_axes; /* 1: the (p,T) axes of the tables depend on the channel; the specialised kernel located the cells per lane */
+  int ega_gas_blocks;      /* > 1: split mode -- gas-block passes + combine kernel (many gases, or a batch too small to fill the GPU) */
 } jrb_stats;
 
 typedef struct jrb_context jrb_context;
@@ -119,8 +121,8 @@ int jrb_set_control(jrb_context *ctx, const jrb_ctl_view *ctl);
 /* pack tbl_t into per-(gas,channel) slabs and upload (requires jrb_set_control first) */
 int jrb_set_tables(jrb_context *ctx, const jrb_tbl_view *tbl);
 /* host-only (no GPU needed): properties of the packed form of a table set.  all_shared: the (p,T) axes of every gas do
- * not depend on the channel; monotone: every column is non-decreasing in u and eps (both are preconditions of the
- * specialised kernel); gas_axes_same: all gases share one (p,T) grid (one table cell per LOS segment instead of ng) */
+ * not depend on the channel (else the specialised kernel locates the table cell per channel); monotone: every column is
+ * non-decreasing in u and eps (else the flagged columns are searched by plain bisection); gas_axes_same: all gases share one (p,T) grid (one table cell per LOS segment instead of ng) */
 int jrb_tables_pack_info(const jrb_tbl_view *tbl, int ng, int nd, size_t *nbytes, int *all_shared, int *monotone,
                          unsigned long long *n_entries, int *gas_axes_same);
 /* host-only: the packed blob itself (out == NULL: query the size); deterministic, so ranks can compare checksums */

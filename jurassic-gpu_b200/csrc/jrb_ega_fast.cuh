@@ -186,6 +186,53 @@ __device__ __forceinline__ unsigned long long remap_hints(const unsigned long lo
   return out;
 }
 
+// ---- channel-dependent (p,T) axes -----------------------------------------------------------------------------------------
+// init_tbl stores the pressure and temperature axes per (gas, channel) (src/jurassic.c:383-384), and the reference locates
+// them per channel (locate_id, src/jr_common.h:237-247).  When the axes of a table set really differ between channels the
+// table cell cannot be resolved once per ray and segment by the tracer; each lane (= channel) then locates its own cell,
+// starting from the cell it used for the previous segment (kept in the hint word), and computes its own interpolation
+// weights.  The axis arrays are channel-innermost, so the lanes of a warp read them coalesced.
+//
+// reference bisection result for an ascending axis of n points: max{i <= n-2 : ax[i] <= x}, 0 if x < ax[0]
+static __device__ __noinline__ int axis_bisect(const double *__restrict__ ax, const int stride, const int n, const double x) {
+  int ilo = 0, ihi = n - 1;
+  while (ihi > ilo + 1) {
+    const int i = (ihi + ilo) >> 1;
+    if (ax[(size_t)i * stride] > x) ihi = i; else ilo = i;
+  }
+  return ilo;
+}
+// index as above, tried at `guess` and its neighbours first; returns the weight (x - ax[i]) / (ax[i+1] - ax[i])
+__device__ __forceinline__ int axis_locate(const double *__restrict__ ax, const int stride, const int n, const double x, const int guess,
+                                           double &w) {
+  int i = min(guess, n - 2);
+  double x0 = ax[(size_t)i * stride], x1 = ax[(size_t)(i + 1) * stride];
+  if (!((x0 <= x || i == 0) && (x1 > x || i == n - 2))) {
+    i = (x0 > x) ? max(i - 1, 0) : min(i + 1, n - 2);
+    x0 = ax[(size_t)i * stride]; x1 = ax[(size_t)(i + 1) * stride];
+    if (!((x0 <= x || i == 0) && (x1 > x || i == n - 2))) {
+      i = axis_bisect(ax, stride, n, x);
+      x0 = ax[(size_t)i * stride]; x1 = ax[(size_t)(i + 1) * stride];
+    }
+  }
+  w = (x - x0) * fast_rcp(x1 - x0);
+  return i;
+}
+// this lane's table cell of gas ig at (p, t) and its three interpolation weights; kCellInvalid if an axis is too short
+__device__ __forceinline__ unsigned locate_cell_lane(const TblDev &T, const int ig, const int nd, const int id, const double p, const double t,
+                                                     const unsigned guess, double &wp, double &wt0, double &wt1) {
+  const int np = T.np[ig * nd + id];
+  if (np < 2) return kCellInvalid;
+  const size_t gbase = (size_t)ig * T.npmax;
+  const int ipr = axis_locate(T.pax + gbase * nd + id, nd, np, p, (int)(guess & 0xff), wp);
+  const int nt0 = T.nt[(gbase + ipr) * nd + id], nt1 = T.nt[(gbase + ipr + 1) * nd + id];
+  if (nt0 < 2 || nt1 < 2) return kCellInvalid;
+  const double *__restrict__ t0ax = T.tax + (gbase + ipr) * T.ntmax * nd + id;
+  const int it0 = axis_locate(t0ax, nd, nt0, t, (int)((guess >> 8) & 0xff), wt0);
+  const int it1 = axis_locate(t0ax + (size_t)T.ntmax * nd, nd, nt1, t, (int)((guess >> 16) & 0xff), wt1);
+  return (unsigned)ipr | ((unsigned)it0 << 8) | ((unsigned)it1 << 16);
+}
+
 // Work distribution.  Items (rays, or ray x channel group) are handed out in CHUNKS of consecutive items per CTA: the
 // warps of a CTA draw single items from the CTA's current chunk (shared-memory word: chunk base << 8 | items taken) and
 // whoever finds it exhausted fetches the next chunk from the global counter.  Consecutive items are neighbouring rays of
@@ -243,13 +290,26 @@ __host__ __device__ inline size_t ega_fast_smem_bytes(int ng, int rec, int threa
 // ROBUST = true: the table set contains columns that are not sorted in u or eps (flagged kColNonMonotone at pack time);
 //                cells touching such a column are evaluated with the reference's plain bisection.  The ROBUST = false
 //                instantiation is used for fully sorted table sets and carries no trace of this.
-template <int MASK, bool MULTI, bool ROBUST>
+// SPLIT = true : gas-block pass.  The gases are cut into a.n_gas_blocks blocks of a.gases_per_block and a work item is
+//                (gas block, channel group, ray): the warp runs the EGA recurrence for ITS gases only and stores, per
+//                segment, the product of their factors to a.partial[block][ray][segment][channel] (continuum, source and
+//                accumulation are left to ega_combine_kernel).  The gases of a ray do not depend on each other, so this
+//                (a) multiplies the number of independent warps by the number of blocks -- a single 1088-ray package fills
+//                the GPU (latency mode) -- and (b) bounds the per-thread state (16 B per gas) and the hot table set
+//                (channels per warp x gases per block) for many-gas set-ups such as the 30-gas refspec shape.  With one
+//                gas per block the combine step multiplies the factors in the same order as the fused kernel: bit-identical.
+//                MASK plays no role in this pass (instantiated for MASK = 0 only).
+// PERCH = true : the (p,T) axes of the tables depend on the channel: every lane locates its own table cell and weights
+//                (locate_cell_lane) instead of taking the ray's cell from the line-of-sight record.  Instantiated with
+//                ROBUST = true only (such table sets are rare; one variant serves sorted and unsorted columns).
+template <int MASK, bool MULTI, bool ROBUST, bool SPLIT = false, bool PERCH = false>
 __global__ void __launch_bounds__(kEgaBlock, JRB_EGA_MINBLOCKS) ega_fast_kernel(const EgaArgs a) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, nwarps = blockDim.x >> 5;
   const LosLayout L = a.los;
   const TblDev &T = a.tbl;
   const int nd = a.nd, ng = a.ng;
+  const int ngs = SPLIT ? a.gases_per_block : ng;   // gases whose state a thread holds
   const unsigned rec_bytes = (unsigned)L.head * 8u; // only the head of a record is staged
 
   const int cpw = MULTI ? a.cpw : 32;           // channels of a ray handled by one warp
@@ -259,7 +319,7 @@ __global__ void __launch_bounds__(kEgaBlock, JRB_EGA_MINBLOCKS) ega_fast_kernel(
   unsigned long long *bars = reinterpret_cast<unsigned long long *>(smem_raw + 16) + warp * 2;
   double *recbuf = reinterpret_cast<double *>(smem_raw + 16 + (size_t)nwarps * 16) + (size_t)warp * 2 * bufstride;
   double *tau_s = reinterpret_cast<double *>(smem_raw + 16 + (size_t)nwarps * 16 + (size_t)nwarps * 2 * bufstride * 8) + tid;
-  unsigned long long *hint_s = reinterpret_cast<unsigned long long *>(tau_s - tid + (size_t)ng * blockDim.x) + tid;
+  unsigned long long *hint_s = reinterpret_cast<unsigned long long *>(tau_s - tid + (size_t)ngs * blockDim.x) + tid;
   const int sstride = blockDim.x;
 
   if (lane == 0) { fast::mbar_init(&bars[0], 1); fast::mbar_init(&bars[1], 1); }
@@ -273,7 +333,8 @@ __global__ void __launch_bounds__(kEgaBlock, JRB_EGA_MINBLOCKS) ega_fast_kernel(
 
   const int ngroups = (nd + cpw - 1) / cpw;
   const unsigned long long n_blocks = MULTI ? (unsigned long long)((a.n_rays + rpw - 1) / rpw) : (unsigned long long)a.n_rays;
-  const unsigned long long n_items = n_blocks * ngroups; // channel-group major: item = group * n_blocks + ray block
+  const unsigned long long n_items_blk = n_blocks * ngroups; // channel-group major: item = group * n_blocks + ray block
+  const unsigned long long n_items = SPLIT ? n_items_blk * (unsigned long long)a.n_gas_blocks : n_items_blk; // gas-block major
   const int sub = MULTI ? lane / cpw : 0;       // ray of this lane within the warp
 
   for (;;) {
@@ -293,6 +354,13 @@ __global__ void __launch_bounds__(kEgaBlock, JRB_EGA_MINBLOCKS) ega_fast_kernel(
       if (lane == 0) item = fast::next_item(chunk_state, a.work_counter, (unsigned)a.work_chunk);
       item = __shfl_sync(0xffffffffu, item, 0);
       if (item >= n_items) break;
+    }
+    int g0 = 0, g1 = ng, gblk = 0; // gases of this item
+    if (SPLIT) {
+      gblk = (int)(item / n_items_blk);
+      item -= (unsigned long long)gblk * n_items_blk;
+      g0 = gblk * a.gases_per_block;
+      g1 = min(ng, g0 + a.gases_per_block);
     }
     long long ir;
     int id;
@@ -322,13 +390,16 @@ __global__ void __launch_bounds__(kEgaBlock, JRB_EGA_MINBLOCKS) ega_fast_kernel(
     const bool head_lane = MULTI ? (ray_on && lane == sub * cpw) : (lane == 0); // issues the record copies of its ray
     const int win = a.window[id];
 
-    for (int ig = 0; ig < ng; ig++) {
+    for (int ig = g0; ig < g1; ig++) {
       // a (gas, channel) pair without table (np < 2) contributes the factor 1 (src/jr_common.h:240): hint = all ones
-      tau_s[ig * sstride] = 1.0;
-      hint_s[ig * sstride] = (T.np[ig * nd + id] >= 2) ? 0ull : ~0ull;
+      tau_s[(ig - g0) * sstride] = 1.0;
+      hint_s[(ig - g0) * sstride] = (T.np[ig * nd + id] >= 2) ? 0ull : ~0ull;
     }
     double rad = 0.0, tau = 1.0;
     bool dead = false; // a gas went opaque (tau_path < 1e-9): nothing changes any more (src/jr_common.h:239,295)
+    int n_done = 0;    // SPLIT: segments for which this lane stored a block product
+    double *__restrict__ part = nullptr;
+    if (SPLIT) part = a.partial + (((size_t)gblk * (size_t)a.n_rays + (size_t)ir) * kNLOS) * (size_t)nd + id;
 
     __syncwarp();
     // one copy per ray of the warp and segment; the barrier of a buffer expects the bytes of all copies aimed at it
@@ -361,10 +432,15 @@ __global__ void __launch_bounds__(kEgaBlock, JRB_EGA_MINBLOCKS) ega_fast_kernel(
       if (dead || ip >= np) continue;
 
       const double *__restrict__ R = recbuf + (size_t)b * bufstride + (size_t)sub * L.head;
-      const double p = R[0], t = R[1], ds = R[2];
-      const double u_co2 = (MASK & 8) ? R[L.u0 + a.ig_co2] : 0.0;
-      const double u_h2o = (MASK & 4) ? R[L.u0 + a.ig_h2o] : 0.0;
-      const double beta_ds = continuum_beta_ds(MASK, a.chan, nd, id, p, t, ds, a.nw > 0 ? R[4 + win] : 0.0, u_co2, u_h2o, R[3]);
+      double t = 0.0, beta_ds = 0.0;
+      const double p_seg = PERCH ? R[0] : 0.0, t_seg = PERCH ? R[1] : 0.0; // per-lane cell location needs them in every pass
+      if (!SPLIT) {
+        const double p = R[0], ds = R[2];
+        t = R[1];
+        const double u_co2 = (MASK & 8) ? R[L.u0 + a.ig_co2] : 0.0;
+        const double u_h2o = (MASK & 4) ? R[L.u0 + a.ig_h2o] : 0.0;
+        beta_ds = continuum_beta_ds(MASK, a.chan, nd, id, p, t, ds, a.nw > 0 ? R[4 + win] : 0.0, u_co2, u_h2o, R[3]);
+      }
 
       double tau_gas = 1.0;
       bool any_opaque = false;
@@ -372,31 +448,37 @@ __global__ void __launch_bounds__(kEgaBlock, JRB_EGA_MINBLOCKS) ega_fast_kernel(
       unsigned ncell;
 #ifdef JRB_PREFETCH_NEXT_GAS
       // column descriptors of gas 0; inside the loop those of gas ig+1 are requested before gas ig is computed
-      ncell = fast::load_cell(R, L, 0);
-      fast::load_coldesc(T, 0, ncell, nd, id, n00, n01, n10, n11);
+      ncell = fast::load_cell(R, L, g0);
+      fast::load_coldesc(T, g0, ncell, nd, id, n00, n01, n10, n11);
 #endif
 #pragma unroll 1
-      for (int ig = 0; ig < ng; ig++) {
+      for (int ig = g0; ig < g1; ig++) {
+        double wl_p = 0.0, wl_t0 = 0.0, wl_t1 = 0.0; // PERCH: this lane's interpolation weights
 #ifndef JRB_PREFETCH_NEXT_GAS
-        ncell = fast::load_cell(R, L, ig);
+        if (PERCH) {
+          const unsigned long long h0 = hint_s[(ig - g0) * sstride];
+          ncell = (h0 == ~0ull) ? kCellInvalid : fast::locate_cell_lane(T, ig, nd, id, p_seg, t_seg, (unsigned)(h0 >> 40), wl_p, wl_t0, wl_t1);
+        } else {
+          ncell = fast::load_cell(R, L, ig);
+        }
         fast::load_coldesc(T, ig, ncell, nd, id, n00, n01, n10, n11);
 #endif
         const uint2 c00 = n00, c01 = n01, c10 = n10, c11 = n11;
         const unsigned cell = ncell;
 #ifdef JRB_PREFETCH_NEXT_GAS // measured: no gain at 3 CTAs/SM (profiles/README.md), costs registers
-        if (ig + 1 < ng) {
+        if (ig + 1 < g1) {
           ncell = fast::load_cell(R, L, ig + 1);
           fast::load_coldesc(T, ig + 1, ncell, nd, id, n00, n01, n10, n11);
         }
 #endif
-        const double tp = tau_s[ig * sstride];
+        const double tp = tau_s[(ig - g0) * sstride];
         double f;
         if (tp < 1e-9) {
           f = 0.0;
           any_opaque = true;
         } else {
           f = 1.0;
-          unsigned long long h = hint_s[ig * sstride];
+          unsigned long long h = hint_s[(ig - g0) * sstride];
           const unsigned unsorted = ROBUST ? ((c00.y | c01.y | c10.y | c11.y) & kColNonMonotone) : 0u;
           const unsigned nmask = ROBUST ? ~kColNonMonotone : ~0u;
           const unsigned n00u = c00.y & nmask, n01u = c01.y & nmask, n10u = c10.y & nmask, n11u = c11.y & nmask;
@@ -422,23 +504,33 @@ __global__ void __launch_bounds__(kEgaBlock, JRB_EGA_MINBLOCKS) ega_fast_kernel(
               e10 = fast::column_finish_bisect(brk + c10.x, (int)n10u, eps, useg);
               e11 = fast::column_finish_bisect(brk + c11.x, (int)n11u, eps, useg);
             }
-            hint_s[ig * sstride] = (unsigned long long)k00 | ((unsigned long long)k01 << 10) | ((unsigned long long)k10 << 20) |
+            hint_s[(ig - g0) * sstride] = (unsigned long long)k00 | ((unsigned long long)k01 << 10) | ((unsigned long long)k10 << 20) |
                                    ((unsigned long long)k11 << 30) | ((unsigned long long)cell << 40);
-            const double ep0 = clamp01(fma(cw[1], e01 - e00, e00));
-            const double ep1 = clamp01(fma(cw[2], e11 - e10, e10));
-            const double ept = clamp01(fma(cw[0], ep1 - ep0, ep0));
+            const double ep0 = clamp01(fma(PERCH ? wl_t0 : cw[1], e01 - e00, e00));
+            const double ep1 = clamp01(fma(PERCH ? wl_t1 : cw[2], e11 - e10, e10));
+            const double ept = clamp01(fma(PERCH ? wl_p : cw[0], ep1 - ep0, ep0));
             f = (1. - ept) * fast_rcp(tp);
           }
           const double tn = tp * f;
-          tau_s[ig * sstride] = tn;
+          tau_s[(ig - g0) * sstride] = tn;
           any_opaque |= tn < 1e-9;
         }
         tau_gas *= f;
       }
       // an opaque gas keeps its factor 0 for the rest of the ray: tau_gas stays 0, accumulate() is skipped for good
       if (tau_gas == 0.0 && any_opaque) dead = true;
+      if (SPLIT) {
+        if (lane_on) part[(size_t)ip * nd] = tau_gas; // product of this block's factors (0 from here on once a gas is opaque)
+        n_done = ip + 1;
+        continue;
+      }
       const double src = planck_source(T.sr, nd, id, t);
       accumulate(rad, tau, beta_ds, src, tau_gas);
+    }
+    if (SPLIT) {
+      // segments [0, n_done) carry a product; beyond it the block's factor is 0 (a gas went opaque at n_done - 1)
+      if (lane_on) a.partial_len[((size_t)gblk * (size_t)a.n_rays + (size_t)ir) * nd + id] = n_done;
+      continue;
     }
     epilogue(rad, tau, a.ray_tsurf[ir], T.sr, nd, id, a.write_bbt, a.chan[CH_NU * nd + id]);
     if (lane_on) {
@@ -478,11 +570,12 @@ static __global__ void chunk_balance_kernel(const int *__restrict__ ray_np, cons
   if ((threadIdx.x & 31) == 0 && total) { atomicAdd(&balance[0], idle); atomicAdd(&balance[1], total); }
 }
 
-template <int MASK, bool MULTI, bool ROBUST>
+template <int MASK, bool MULTI, bool ROBUST, bool SPLIT = false, bool PERCH = false>
 cudaError_t launch_ega_fast_tm(const EgaArgs &a, cudaStream_t stream, int sm_count) {
   const int cpw = MULTI ? a.cpw : 32, rpw = 32 / cpw;
   const int ngroups = (a.nd + cpw - 1) / cpw;
-  const long long n_items = ((a.n_rays + rpw - 1) / rpw) * ngroups;
+  const long long n_items = ((a.n_rays + rpw - 1) / rpw) * ngroups * (SPLIT ? a.n_gas_blocks : 1);
+  const int ng_state = SPLIT ? a.gases_per_block : a.ng; // gases whose state a thread holds
   // Block size.  Large batches: ONE 768-thread CTA per SM, so that all 24 warps share one work chunk.  Small batches (fewer
   // than 16 rounds of work per SM: the coarser chunks would cost more in the tail than the L1 sharing gains, measured
   // cross-over between 35 k and 125 k items) and gas counts whose per-thread state (16 B per gas and thread) does not
@@ -497,24 +590,24 @@ cudaError_t launch_ega_fast_tm(const EgaArgs &a, cudaStream_t stream, int sm_cou
   else if (n_items < 16ll * sm_count * (kEgaBlock / 32)) block = kEgaSmallBlock;
   // few channels x many gases (rpw records per warp + 16 B of state per gas and thread) can exceed even the small CTA's
   // shared memory: shrink the CTA until it fits (jrb_stage has checked that a one-warp CTA fits, else the generic kernel runs)
-  while (block > 32 && ega_fast_smem_bytes(a.ng, a.los.head, block, rpw) > (size_t)smem_max) block = block > kEgaSmallBlock ? kEgaSmallBlock : block / 2;
-  const size_t smem = ega_fast_smem_bytes(a.ng, a.los.head, block, rpw);
+  while (block > 32 && ega_fast_smem_bytes(ng_state, a.los.head, block, rpw) > (size_t)smem_max) block = block > kEgaSmallBlock ? kEgaSmallBlock : block / 2;
+  const size_t smem = ega_fast_smem_bytes(ng_state, a.los.head, block, rpw);
   if (smem > (size_t)smem_max) return cudaErrorInvalidConfiguration;
   // the dynamic shared-memory limit is a per-device property of the function: set once to the opt-in maximum, so that
   // contexts launching concurrently with different sizes (lanes, several host threads) cannot lower it under each other
   static std::atomic<unsigned long long> attr_done{0};
   cudaError_t e = cudaSuccess;
   if (!((attr_done.load(std::memory_order_acquire) >> (dev & 63)) & 1ull)) {
-    e = cudaFuncSetAttribute(ega_fast_kernel<MASK, MULTI, ROBUST>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_max);
+    e = cudaFuncSetAttribute(ega_fast_kernel<MASK, MULTI, ROBUST, SPLIT, PERCH>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_max);
     if (e != cudaSuccess) return e;
     attr_done.fetch_or(1ull << (dev & 63), std::memory_order_release);
   }
   if (const char *s = getenv("JRB_EGA_CARVEOUT")) { // experiments: shared-memory carve-out in percent (the rest of the 256 KB is L1)
     const int v = atoi(s);
-    if (v >= 0 && v <= 100) cudaFuncSetAttribute(ega_fast_kernel<MASK, MULTI, ROBUST>, cudaFuncAttributePreferredSharedMemoryCarveout, v);
+    if (v >= 0 && v <= 100) cudaFuncSetAttribute(ega_fast_kernel<MASK, MULTI, ROBUST, SPLIT, PERCH>, cudaFuncAttributePreferredSharedMemoryCarveout, v);
   }
   int blocks_per_sm = 0;
-  e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&blocks_per_sm, ega_fast_kernel<MASK, MULTI, ROBUST>, block, smem);
+  e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&blocks_per_sm, ega_fast_kernel<MASK, MULTI, ROBUST, SPLIT, PERCH>, block, smem);
   if (e != cudaSuccess) return e;
   if (blocks_per_sm < 1) return cudaErrorInvalidConfiguration;
   if (const char *s = getenv("JRB_EGA_CTAS_PER_SM")) { const int v = atoi(s); if (v >= 1 && v < blocks_per_sm) blocks_per_sm = v; } // occupancy experiments
@@ -529,17 +622,22 @@ cudaError_t launch_ega_fast_tm(const EgaArgs &a, cudaStream_t stream, int sm_cou
   const long long need = (n_items + per_cta - 1) / per_cta;
   if (grid > need) grid = need;
   if (grid < 1) grid = 1;
-  ega_fast_kernel<MASK, MULTI, ROBUST><<<(unsigned)grid, block, smem, stream>>>(args);
+  ega_fast_kernel<MASK, MULTI, ROBUST, SPLIT, PERCH><<<(unsigned)grid, block, smem, stream>>>(args);
   return cudaGetLastError();
 }
 
 template <int MASK>
 cudaError_t launch_ega_fast_t(const EgaArgs &a, cudaStream_t stream, int sm_count) {
   const bool multi = a.cpw < 32; // several rays per warp
+  if (a.per_channel_axes)
+    return multi ? launch_ega_fast_tm<MASK, true, true, false, true>(a, stream, sm_count) : launch_ega_fast_tm<MASK, false, true, false, true>(a, stream, sm_count);
   if (a.unsorted_columns)
     return multi ? launch_ega_fast_tm<MASK, true, true>(a, stream, sm_count) : launch_ega_fast_tm<MASK, false, true>(a, stream, sm_count);
   return multi ? launch_ega_fast_tm<MASK, true, false>(a, stream, sm_count) : launch_ega_fast_tm<MASK, false, false>(a, stream, sm_count);
 }
+
+// gas-block pass (SPLIT): independent of the continuum mask, one set of instantiations (jrb_ega_split.cu)
+cudaError_t launch_ega_split(const EgaArgs &a, cudaStream_t stream, int sm_count);
 
 // one translation unit per MASK
 template <int MASK>

@@ -42,6 +42,7 @@ struct EgaArgs {
   int ig_co2, ig_h2o;
   int write_bbt;
   int unsorted_columns; // the table set has columns flagged kColNonMonotone -> ROBUST kernel instantiation
+  int per_channel_axes; // the (p,T) axes depend on the channel -> PERCH instantiation (lanes locate their own table cells)
   LosLayout los;
   const double *los_data;
   const int *ray_np;
@@ -59,6 +60,10 @@ struct EgaArgs {
   unsigned long long *balance;      // [2] scratch (zeroed before launch): idle / total segment slots of lock-step execution
   int phase_lock_mode;              // -1 decide on the device from `balance`, 0 never, 1 always
   int cpw;                          // channels of a ray per warp: 32, or less (= several rays per warp, see jrb_ega_fast.cuh)
+  // gas-block passes (split mode, see ega_fast_kernel<SPLIT>): block b holds gases [b*gases_per_block, ...)
+  int n_gas_blocks, gases_per_block;
+  double *partial;                  // [n_gas_blocks][n_rays][NLOS][nd] per-segment product of the block's gas factors
+  int *partial_len;                 // [n_gas_blocks][n_rays][nd] segments that carry a product (a gas went opaque at len-1 if < np)
 };
 
 struct FovArgs { // optional epilogue: field-of-view convolution (formod_fov, src/jurassic.c:214-258)
@@ -103,6 +108,10 @@ cudaError_t launch_raytrace(const TraceArgs &a, cudaStream_t stream, int *launch
 cudaError_t launch_ega_generic(const EgaArgs &a, cudaStream_t stream);
 // fast path: returns cudaErrorInvalidValue if (ng, ctm_mask) has no instantiation
 cudaError_t launch_ega_fast(const EgaArgs &a, cudaStream_t stream, int *ngb_out);
+// split mode: gas-block passes of the specialised kernel (a.partial / a.partial_len filled), then the combine kernel that
+// multiplies the block products per segment and does continuum, Planck source, accumulation and the epilogues
+cudaError_t launch_ega_split_passes(const EgaArgs &a, cudaStream_t stream);
+cudaError_t launch_ega_combine(const EgaArgs &a, cudaStream_t stream);
 bool ega_fast_available(int ng, int ctm_mask);
 bool ega_fast_fits(int ng, int los_head, int cpw, size_t smem_max);
 

@@ -146,6 +146,8 @@ struct jrb_context {
   LosLayout los;
   int use_fast = 0;
   int cpw = 32;
+  int n_gas_blocks = 1, gases_per_block = 1; // split mode (jrb_ega_split.cu) when n_gas_blocks > 1
+  DevBuf d_partial;
   std::vector<cudaEvent_t> events;
   jrb_stats stats;
   bool np_fetched = false;
@@ -217,7 +219,7 @@ void jrb_destroy(jrb_context *ctx) {
   ctx->d_chan.release(); ctx->d_window.release(); ctx->tbl.reset();
   ctx->d_in.release(); ctx->d_tab.release(); ctx->d_out.release(); ctx->d_rayout.release(); ctx->d_los.release();
   ctx->d_np.release(); ctx->d_tsurf.release(); ctx->d_counter.release(); ctx->d_slope.release(); ctx->d_level0.release();
-  ctx->d_raypkg.release(); ctx->d_pkgnp.release();
+  ctx->d_raypkg.release(); ctx->d_pkgnp.release(); ctx->d_partial.release();
   ctx->h_in.release(); ctx->h_out.release(); ctx->h_tab.release();
   ctx->d_fov.release(); ctx->d_fov_out.release(); ctx->d_mask.release(); ctx->d_flag.release();
   cudaStreamDestroy(ctx->stream);
@@ -532,12 +534,12 @@ static void hydrostatic_host(const jrb_atm_view &a, double hydz, int ig_h2o) {
 // order keeps the hot set at cpw x ng pairs).  Hot bytes per (gas, channel) pair: ~30 % of its brackets (measured on the
 // synthetic sets: a package touches 357 KB of a 1.26 MB pair); budget 0.7 x L2, which reproduces the measured optima
 // (Config D, 57 MB at 32 channels: 32 = 16 > 8; Config E, 94 MB: 16 best, -4 %; 30 gases, 343 MB: 8 best, -14 %).
-static int choose_cpw(const jrb_context *ctx) {
+static int choose_cpw(const jrb_context *ctx, int gases_per_pass) {
   const int nd = ctx->nd, ng = ctx->ng;
   int cpw = nd <= 16 ? nd : 32;
   if (nd > 16 && ng > 0) {
     const double pair_hot = 0.3 * 16.0 * (double)ctx->tbl->th.n_entries / ((double)ng * nd);
-    while (cpw > 4 && pair_hot * cpw * ng > 0.7 * (double)ctx->l2_bytes) cpw >>= 1;
+    while (cpw > 4 && pair_hot * cpw * gases_per_pass > 0.7 * (double)ctx->l2_bytes) cpw >>= 1;
   }
   if (const char *s = getenv("JRB_EGA_CPW")) { const int v = atoi(s); if (v >= 1 && v <= 32 && (v == nd || (32 % v == 0 && v <= nd))) cpw = v; } // experiments
   return cpw;
@@ -576,10 +578,29 @@ static int stage_locked(jrb_context *ctx, int npk, const jrb_atm_view *atm, cons
   }
 
   // ---- kernel choice (before anything is allocated) ----
-  const int cpw = choose_cpw(ctx);
-  const LosLayout los_fast = make_los_layout(ng, nw, 1, th.gas_axes_same);
-  const bool fits = ega_fast_fits(ng, los_fast.head, cpw, (size_t)ctx->smem_optin);
-  const bool fast_ok = th.all_shared && th.max_nu <= 1023 && ega_fast_available(ng, ctx->ctm_mask) && fits;
+  // Split mode (gas-block passes + combine kernel, jrb_ega_split.cu).  (a) Many gases: blocks of at most 10, so that 24 warps
+  // per SM keep their per-gas state (16 B per gas and thread) in shared memory and the tables of one pass fit the L2.
+  // (b) Small batches -- above all the single 1088-ray package of an unmodified formod() caller: as many blocks as it takes
+  // to give the GPU about two rounds of warps, down to one gas per block (results then bit-identical to the fused kernel).
+  int gpb = ng > 0 ? ng : 1;
+  if (ng > 1 && !getenv("JRB_NO_SPLIT")) {
+    if (ng > 12) gpb = (ng + (ng + 9) / 10 - 1) / ((ng + 9) / 10);
+    const int cpw0 = nd <= 16 ? nd : 32, rpw0 = 32 / cpw0;
+    const long long items = ((R + rpw0 - 1) / rpw0) * ((nd + cpw0 - 1) / cpw0);
+    const long long slots = (long long)ctx->sm_count * 24;
+    if (items > 0 && items * ((ng + gpb - 1) / gpb) < 2 * slots) {
+      long long want = (2 * slots + items - 1) / items;
+      if (want > ng) want = ng;
+      gpb = (int)((ng + want - 1) / want);
+    }
+  }
+  if (const char *e = getenv("JRB_EGA_GAS_BLOCK")) { const int v = atoi(e); if (v >= 1 && v <= ng) gpb = v; } // experiments
+  const int nblk = ng > 0 ? (ng + gpb - 1) / gpb : 1;
+  const int cpw = choose_cpw(ctx, nblk > 1 ? gpb : ng);
+  // channel-dependent (p,T) axes: the specialised kernel locates the table cell per lane (PERCH) and the records carry no cell
+  const LosLayout los_fast = make_los_layout(ng, nw, th.all_shared ? 1 : 0, th.gas_axes_same);
+  const bool fits = ega_fast_fits(nblk > 1 ? gpb : ng, los_fast.head, cpw, (size_t)ctx->smem_optin);
+  const bool fast_ok = th.max_nu <= 1023 && ega_fast_available(ng, ctx->ctm_mask) && fits;
   if (ctx->variant_req == 1 && !fast_ok)
     return ctx->fail(JRB_ERR_STATE, std::string("specialised kernel not applicable: shared_axes=") + std::to_string(th.all_shared) +
                      " monotone=" + std::to_string(th.monotone) + " max_nu=" + std::to_string(th.max_nu) + " ng=" + std::to_string(ng) + " mask=" + std::to_string(ctx->ctm_mask) +
@@ -735,22 +756,26 @@ static int stage_locked(jrb_context *ctx, int npk, const jrb_atm_view *atm, cons
   // ---- LOS buffer ----
   ctx->use_fast = use_fast;
   ctx->cpw = cpw;
-  ctx->los = make_los_layout(ng, nw, use_fast, th.gas_axes_same);
-  const size_t per_ray = (size_t)kNLOS * ctx->los.rec * 8;
+  ctx->los = make_los_layout(ng, nw, use_fast && th.all_shared, th.gas_axes_same);
+  ctx->n_gas_blocks = use_fast ? nblk : 1;
+  ctx->gases_per_block = gpb;
+  // scratch per ray: the line-of-sight records, plus the per-segment block products in split mode
+  const size_t part_per_ray = ctx->n_gas_blocks > 1 ? (size_t)ctx->n_gas_blocks * ((size_t)kNLOS * nd * 8 + (size_t)nd * 4) : 0;
+  const size_t per_ray = (size_t)kNLOS * ctx->los.rec * 8 + part_per_ray;
   // LOS scratch: JRB_LOS_GB / jrb_set_los_limit_gb (default 72 GB: the 1 000 960 rays of BASELINE's config D need 64 GB),
   // but never more than half of what is free on the device.  The driver is only asked (cudaMemGetInfo takes a
   // device-wide lock and was seen to stall for tens of ms) when the buffer has to grow.
   double los_gb = 72.0;
   if (const char *s = getenv("JRB_LOS_GB")) { double v = atof(s); if (v > 0.01) los_gb = v; }
   if (ctx->los_limit_gb > 0) los_gb = ctx->los_limit_gb;
-  if ((double)R * (double)per_ray > (double)ctx->d_los.cap) {
+  if ((double)R * (double)(per_ray - part_per_ray) > (double)ctx->d_los.cap || (double)R * (double)part_per_ray > (double)ctx->d_partial.cap) {
     size_t free_b = 0, total_b = 0;
     if (cudaMemGetInfo(&free_b, &total_b) == cudaSuccess) {
-      const double avail = 0.5 * ((double)free_b + (double)ctx->d_los.cap) / 1e9;
+      const double avail = 0.5 * ((double)free_b + (double)ctx->d_los.cap + (double)ctx->d_partial.cap) / 1e9;
       if (avail < los_gb) los_gb = avail;
     }
-  } else if ((double)ctx->d_los.cap / 1e9 < los_gb) {
-    los_gb = (double)ctx->d_los.cap / 1e9 + 1e-9; // the existing buffer is enough for the whole batch
+  } else if ((double)(ctx->d_los.cap + ctx->d_partial.cap) / 1e9 < los_gb) {
+    los_gb = (double)R * (double)per_ray / 1e9 + 1e-9; // the existing buffers are enough for the whole batch
   }
   // Chunking.  By default a batch is one chunk (or as many as the LOS scratch limit requires), run back to back.
   // JRB_PIPELINE=1 cuts large batches into ~8 chunks held in 3 rotating LOS buffers so that the (latency-bound, low
@@ -771,7 +796,11 @@ static int stage_locked(jrb_context *ctx, int npk, const jrb_atm_view *atm, cons
   // equal chunks: the last one is not a short straggler
   if (chunk > 0 && ctx->nbuf == 1) { const long long nch = (R + chunk - 1) / chunk; chunk = (R + nch - 1) / nch; }
   ctx->chunk_rays = chunk;
-  CU(ctx->d_los.ensure((size_t)(chunk ? chunk : 1) * per_ray * ctx->nbuf));
+  CU(ctx->d_los.ensure((size_t)(chunk ? chunk : 1) * (per_ray - part_per_ray) * ctx->nbuf));
+  if (part_per_ray) {
+    if (ctx->nbuf > 1) return ctx->fail(JRB_ERR_STATE, "JRB_PIPELINE cannot be combined with split mode");
+    CU(ctx->d_partial.ensure((size_t)(chunk ? chunk : 1) * part_per_ray + 256));
+  }
   {
     const long long nch = R > 0 ? (R + chunk - 1) / chunk : 1;
     CU(ctx->d_counter.ensure((size_t)nch * 32 + 256)); // per LOS chunk: work counter, lock-step balance (idle, total), pad
@@ -853,6 +882,7 @@ static int run_locked(jrb_context *ctx) {
     e.ctm_mask = ctx->ctm_mask; e.ig_co2 = ctx->ig_co2 >= 0 ? ctx->ig_co2 : 0; e.ig_h2o = ctx->ig_h2o >= 0 ? ctx->ig_h2o : 0;
     e.write_bbt = ctx->write_bbt;
     e.unsorted_columns = th.monotone ? 0 : 1;
+    e.per_channel_axes = th.all_shared ? 0 : 1;
     e.los = ctx->los; e.los_data = los_buf;
     e.ray_np = (const int *)ctx->d_np.p + r0; e.ray_tsurf = (const double *)ctx->d_tsurf.p + r0;
     e.chan = (const double *)ctx->d_chan.p; e.window = (const int *)ctx->d_window.p;
@@ -871,7 +901,15 @@ static int run_locked(jrb_context *ctx) {
     if (const char *s = getenv("JRB_EGA_CHUNK")) { const int v = atoi(s); if (v >= 1 && v <= 200) e.work_chunk = v; } // experiments
     if (pipe) CU(cudaStreamWaitEvent(st_e, EV(c, 1), 0));
     CU(cudaEventRecord(EV(c, 2), st_e));
-    if (ctx->use_fast) CU(launch_ega_fast(e, st_e, &ngb));
+    e.n_gas_blocks = ctx->n_gas_blocks; e.gases_per_block = ctx->gases_per_block;
+    e.partial = nullptr; e.partial_len = nullptr;
+    if (ctx->use_fast && ctx->n_gas_blocks > 1) { // split mode: gas-block passes, then the combine kernel
+      e.partial = (double *)ctx->d_partial.p;
+      e.partial_len = (int *)((char *)ctx->d_partial.p + (size_t)ctx->n_gas_blocks * (size_t)e.n_rays * kNLOS * nd * 8);
+      CU(launch_ega_split_passes(e, st_e));
+      CU(launch_ega_combine(e, st_e));
+      launches++;
+    } else if (ctx->use_fast) CU(launch_ega_fast(e, st_e, &ngb));
     else CU(launch_ega_generic(e, st_e));
     launches += (ctx->use_fast && e.phase_lock_mode < 0 && e.n_rays > 0) ? 2 : 1; // + chunk_balance_kernel
     CU(cudaEventRecord(EV(c, 3), st_e));
@@ -946,6 +984,8 @@ static int run_locked(jrb_context *ctx) {
   ctx->stats.n_chunks = (int)nchunks; ctx->stats.pipelined = pipe ? 1 : 0;
   ctx->stats.ega_kernel_variant = ctx->use_fast; ctx->stats.ega_ngb = ctx->use_fast ? ngb : 0;
   ctx->stats.ega_ctm_mask = ctx->ctm_mask;
+  ctx->stats.ega_gas_blocks = ctx->use_fast ? ctx->n_gas_blocks : 0;
+  ctx->stats.ega_per_channel_axes = (ctx->use_fast && !th.all_shared) ? 1 : 0;
   ctx->ran = true; ctx->np_fetched = false;
   return JRB_OK;
 }

@@ -132,7 +132,9 @@ def test_opaque_cutoff(jr, oracle, gpu_ctx_factory):
     assert ref[0].tau.min() < 1e-9
 
 
-def test_channel_dependent_axes_use_generic_kernel(jr, oracle, gpu_ctx_factory):
+def test_channel_dependent_axes_are_located_per_lane(jr, oracle, gpu_ctx_factory):
+    """(p,T) axes that differ between channels (init_tbl stores them per channel, src/jurassic.c:383-384; the reference
+    locates them per channel, src/jr_common.h:237-247): the specialised kernel resolves the table cell per lane"""
     ctl = jr.synth.control_limb_example()
     tbl = jr.synth.make_tables(ctl, axis_jitter=True)
     assert jr.core.tables_pack_info(tbl, ctl.ng, ctl.nd)["all_shared"] == 0
@@ -140,8 +142,32 @@ def test_channel_dependent_axes_use_generic_kernel(jr, oracle, gpu_ctx_factory):
     ref = run_oracle(oracle, ctl, tbl, [pkg])
     ctx = gpu_ctx_factory()
     mine = run_cuda(ctx, ctl, tbl, [pkg], -1)
-    assert ctx.stats()["ega_kernel_variant"] == 0
-    assert_parity(mine[0], ref[0], "jitter")
+    st = ctx.stats()
+    assert st["ega_kernel_variant"] == 1 and st["ega_per_channel_axes"] == 1
+    assert_parity(mine[0], ref[0], "jitter, specialised kernel")
+    assert_parity(run_cuda(ctx, ctl, tbl, [pkg], 0)[0], ref[0], "jitter, generic kernel")
+
+
+def test_channel_dependent_axes_config_d_package(jr, oracle, gpu_ctx_factory):
+    """a full Config-D package (32 channels per warp, one ray per warp) on tables with channel-dependent axes, fused and
+    in gas-block passes; some pairs without a table, T below the axes (extrapolation + clamping)"""
+    import os
+    ctl = jr.synth.control_config_d()
+    tbl = jr.synth.make_tables(ctl, axis_jitter=True, skip_pairs=[(3, 5), (4, 31)])
+    pkg = jr.synth.limb_package(ctl, seed=4711)
+    ref = run_oracle(oracle, ctl, tbl, [pkg])[0]
+    ctx = gpu_ctx_factory()
+    split = run_cuda(ctx, ctl, tbl, [pkg], 1)[0]
+    st = ctx.stats()
+    assert st["ega_per_channel_axes"] == 1 and st["ega_gas_blocks"] == 5
+    assert_parity(split, ref, "jitter D, split")
+    os.environ["JRB_NO_SPLIT"] = "1"
+    try:
+        fused = run_cuda(ctx, ctl, tbl, [pkg], 1)[0]
+        assert ctx.stats()["ega_gas_blocks"] == 1
+    finally:
+        del os.environ["JRB_NO_SPLIT"]
+    assert np.array_equal(split.rad, fused.rad) and np.array_equal(split.tau, fused.tau)
 
 
 def test_gas_dependent_axes_use_per_gas_cells(jr, oracle, gpu_ctx_factory):

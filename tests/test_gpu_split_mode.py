@@ -1,0 +1,108 @@
+"""Split mode of the EGA step (jrb_ega_split.cu): gas-block passes + combine kernel.  Needs a GPU.
+
+* latency mode: a single package is cut into one-gas blocks so that it fills the GPU; bit-identical to the fused kernel;
+* many gases (30-gas refspec shape, example/refspec/template.ctl): blocks of 10 gases; equal to the fused kernel up to the
+  rounding of the regrouped product, and within the 1e-6 tolerance of the oracle on a full 66-ray x 100-channel x 30-gas package.
+"""
+import copy
+import os
+
+import numpy as np
+import pytest
+
+from helpers import assert_parity, run_cuda, run_oracle
+
+pytestmark = pytest.mark.gpu
+
+
+class env:
+    def __init__(self, **kv):
+        self.kv = kv
+
+    def __enter__(self):
+        self.old = {k: os.environ.get(k) for k in self.kv}
+        for k, v in self.kv.items():
+            if v is None:
+                os.environ.pop(k, None)
+            else:
+                os.environ[k] = str(v)
+
+    def __exit__(self, *a):
+        for k, v in self.old.items():
+            if v is None:
+                os.environ.pop(k, None)
+            else:
+                os.environ[k] = v
+
+
+def _same_bits(a, b, what):
+    for name in ("rad", "tau"):
+        assert np.array_equal(getattr(a, name), getattr(b, name), equal_nan=True), f"{what}: {name} differs"
+
+
+def test_single_package_runs_split_and_is_bit_identical_to_fused(jr, oracle, gpu_ctx_factory):
+    ctl = jr.synth.control_config_d()
+    tbl = jr.synth.make_tables(ctl)
+    pkg = jr.synth.limb_package(ctl, seed=20240517)
+    pkg.rad[100, 7] = np.nan
+    ctx = gpu_ctx_factory()
+    with env(JRB_NO_SPLIT=None, JRB_EGA_GAS_BLOCK=None):
+        split = run_cuda(ctx, ctl, tbl, [pkg], 1)[0]
+        st = ctx.stats()
+        assert st["ega_gas_blocks"] == 5, st  # 1088 rays x 1 channel group: one gas per block
+    with env(JRB_NO_SPLIT=1):
+        fused = run_cuda(ctx, ctl, tbl, [pkg], 1)[0]
+        assert ctx.stats()["ega_gas_blocks"] == 1
+    _same_bits(split, fused, "one-gas blocks vs fused")
+    assert np.isnan(split.rad[100, 7])
+    assert fused.tau.min() < 1e-6  # opaque rays: early termination of a block is covered
+    assert_parity(split, run_oracle(oracle, ctl, tbl, [pkg])[0], "split vs oracle")
+
+
+@pytest.mark.parametrize("gpb", [2, 3])
+def test_gas_blocks_of_several_gases(jr, gpu_ctx_factory, gpb):
+    """blocks of 2 / 3 gases (the last block is shorter): regrouped product, equal to fused within rounding"""
+    ctl = jr.synth.control_config_e()
+    tbl = jr.synth.make_tables(ctl)
+    pkg = jr.synth.nadir_package(ctl, n_profiles=4, rays_per_profile=17, dlat=0.7, seed=20240518)
+    ctx = gpu_ctx_factory()
+    with env(JRB_NO_SPLIT=1):
+        fused = run_cuda(ctx, ctl, tbl, [pkg], 1)[0]
+    with env(JRB_EGA_GAS_BLOCK=gpb):
+        split = run_cuda(ctx, ctl, tbl, [pkg], 1)[0]
+        assert ctx.stats()["ega_gas_blocks"] == (8 + gpb - 1) // gpb
+    assert np.max(np.abs(split.rad - fused.rad) / np.abs(fused.rad)) < 1e-13
+    assert np.max(np.abs(split.tau - fused.tau) / (np.abs(fused.tau) + 1e-300)) < 1e-13
+
+
+def test_few_channel_instrument_in_split_mode(jr, oracle, gpu_ctx_factory):
+    """nd = 2 (several rays per warp) in split mode"""
+    ctl = jr.synth.control_limb_example()
+    tbl = jr.synth.make_tables(ctl)
+    pkg = jr.synth.example_package("limb", ctl)
+    ctx = gpu_ctx_factory()
+    split = run_cuda(ctx, ctl, tbl, [pkg], 1)[0]
+    assert ctx.stats()["ega_gas_blocks"] == 5
+    with env(JRB_NO_SPLIT=1):
+        fused = run_cuda(ctx, ctl, tbl, [pkg], 1)[0]
+    _same_bits(split, fused, "nd=2 split vs fused")
+    assert_parity(split, run_oracle(oracle, ctl, tbl, [pkg])[0], "nd=2 split vs oracle")
+
+
+def test_refspec_shape_full_package(jr, oracle, gpu_ctx_factory):
+    """example/refspec shape at full size: 66 limb rays x 100 channels x 30 gases, every gas with a realistic profile
+    and a table for every (gas, channel) pair; window 2150.. cm^-1 (CO2, H2O and N2 continua)"""
+    gases = ["CO2", "H2O", "O3", "N2O", "CH4", "CO", "HNO3", "SO2", "F11", "CCl4"] + [f"X{i}" for i in range(20)]
+    ctl = jr.Control(gases, 2150.0 + np.arange(100))
+    assert ctl.ctm_mask == 14
+    tbl = jr.synth.make_tables(ctl)
+    pkg = jr.synth.limb_package(ctl, n_profiles=1, rays_per_profile=66, z0=3.0, dz=1.0, seed=77)  # Z0 3, Z1 68, DZ 1 (template.ctl)
+    for ig in range(10, 30):  # the unnamed emitters: profiles of the named ones, scaled
+        pkg.q[ig, :] = pkg.q[ig % 10, :] * (0.2 + 0.05 * ig)
+    ctx = gpu_ctx_factory()
+    mine = run_cuda(ctx, ctl, tbl, [pkg], 1)[0]
+    st = ctx.stats()
+    assert st["ega_gas_blocks"] >= 3 and st["ega_kernel_variant"] == 1
+    ref = run_oracle(oracle, ctl, tbl, [pkg])[0]
+    assert_parity(mine, ref, "refspec 66 x 100 x 30")
+    assert ref.tau.min() < 1e-3 and ref.tau.max() > 0.9  # from opaque to nearly transparent
