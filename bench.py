@@ -168,7 +168,7 @@ class _StructFiller:
             c.nu[i] = ctl.nu[i]; c.window[i] = int(ctl.window[i])
         c.hydz, c.ctm_co2, c.ctm_h2o, c.ctm_n2, c.ctm_o2 = ctl.hydz, ctl.ctm_co2, ctl.ctm_h2o, ctl.ctm_n2, ctl.ctm_o2
         c.ip, c.refrac, c.rayds, c.raydz, c.write_bbt, c.formod, c.useGPU = ctl.ip, ctl.refrac, ctl.rayds, ctl.raydz, ctl.write_bbt, ctl.formod, 1
-        c.fov.value = b"-"
+        c.fov = b"-"
         return c
 
     def atm(self, pkg, a=None):

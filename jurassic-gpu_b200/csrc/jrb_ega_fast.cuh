@@ -58,6 +58,20 @@ __device__ __forceinline__ void tma_load_1d(void *dst_smem, const void *src_gmem
                : "memory");
 }
 
+// the same with an L2 eviction-priority hint: line-of-sight records are read once per (ray, channel group) and should not
+// push the table brackets -- which every warp keeps coming back to -- out of the L2
+__device__ __forceinline__ unsigned long long l2_policy_evict_first() {
+  unsigned long long pol;
+  asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(pol));
+  return pol;
+}
+__device__ __forceinline__ void tma_load_1d_hint(void *dst_smem, const void *src_gmem, unsigned bytes, unsigned long long *bar,
+                                                 unsigned long long policy) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint [%0], [%1], %2, [%3], %4;" ::"r"(smem_addr(dst_smem)),
+               "l"(src_gmem), "r"(bytes), "r"(smem_addr(bar)), "l"(policy)
+               : "memory");
+}
+
 // ---- bracket search ------------------------------------------------------------------------------------------------
 // Exact comparison of a double x with float table values: for any float v,  v > x  <=>  v > rd(x), where rd() rounds x
 // to float toward -infinity.  The bracket tests therefore run in single precision -- no float->double conversion per
@@ -327,6 +341,7 @@ __global__ void __launch_bounds__(kEgaBlock, JRB_EGA_MINBLOCKS) ega_fast_kernel(
   asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   __syncthreads();
   unsigned parity0 = 0, parity1 = 0;
+  const unsigned long long los_policy = a.los_evict_first ? fast::l2_policy_evict_first() : 0ull;
   // balance[0] = idle segment slots, balance[1] = all segment slots if every chunk of blockDim/32 consecutive items ran in
   // lock step (chunk_balance_kernel): lock step is chosen when less than 1/32 of the slots would idle
   const bool phase_lock = a.phase_lock_mode == 1 || (a.phase_lock_mode < 0 && a.balance != nullptr && a.balance[0] * 32ull < a.balance[1]);
@@ -407,7 +422,10 @@ __global__ void __launch_bounds__(kEgaBlock, JRB_EGA_MINBLOCKS) ega_fast_kernel(
       const unsigned cnt = MULTI ? __popc(__ballot_sync(0xffffffffu, head_lane && np > 0)) : (np > 0 ? 1u : 0u);
       if (cnt && lane == 0) fast::mbar_expect_tx(&bars[0], cnt * rec_bytes);
       __syncwarp();
-      if (head_lane && np > 0) fast::tma_load_1d(recbuf + (size_t)sub * L.head, rec_g, rec_bytes, &bars[0]);
+      if (head_lane && np > 0) {
+        if (los_policy) fast::tma_load_1d_hint(recbuf + (size_t)sub * L.head, rec_g, rec_bytes, &bars[0], los_policy);
+        else fast::tma_load_1d(recbuf + (size_t)sub * L.head, rec_g, rec_bytes, &bars[0]);
+      }
     }
     for (int ip = 0; ip < np_max; ++ip) {
       const int b = ip & 1;
@@ -422,9 +440,14 @@ __global__ void __launch_bounds__(kEgaBlock, JRB_EGA_MINBLOCKS) ega_fast_kernel(
         } else if (want) {
           fast::mbar_expect_tx(&bars[b ^ 1], rec_bytes);
         }
-        if (want)
-          fast::tma_load_1d(recbuf + (size_t)(b ^ 1) * bufstride + (size_t)sub * L.head, rec_g + (size_t)(ip + 1) * L.rec, rec_bytes,
-                            &bars[b ^ 1]);
+        if (want) {
+          if (los_policy)
+            fast::tma_load_1d_hint(recbuf + (size_t)(b ^ 1) * bufstride + (size_t)sub * L.head, rec_g + (size_t)(ip + 1) * L.rec, rec_bytes,
+                                   &bars[b ^ 1], los_policy);
+          else
+            fast::tma_load_1d(recbuf + (size_t)(b ^ 1) * bufstride + (size_t)sub * L.head, rec_g + (size_t)(ip + 1) * L.rec, rec_bytes,
+                              &bars[b ^ 1]);
+        }
       }
       // the copies of segment ip are always in flight here (issued above one iteration earlier, or before the loop)
       if (b == 0) { fast::mbar_wait(&bars[0], parity0); parity0 ^= 1; } else { fast::mbar_wait(&bars[1], parity1); parity1 ^= 1; }

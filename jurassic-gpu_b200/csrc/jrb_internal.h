@@ -42,6 +42,7 @@ struct EgaArgs {
   int ig_co2, ig_h2o;
   int write_bbt;
   int unsorted_columns; // the table set has columns flagged kColNonMonotone -> ROBUST kernel instantiation
+  int los_evict_first;  // line-of-sight record copies carry the L2 evict_first hint (they are streamed, the tables are reused)
   int per_channel_axes; // the (p,T) axes depend on the channel -> PERCH instantiation (lanes locate their own table cells)
   LosLayout los;
   const double *los_data;

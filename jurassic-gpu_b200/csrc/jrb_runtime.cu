@@ -147,6 +147,8 @@ struct jrb_context {
   int use_fast = 0;
   int cpw = 32;
   int n_gas_blocks = 1, gases_per_block = 1; // split mode (jrb_ega_split.cu) when n_gas_blocks > 1
+  int los_evict_first = 0;   // L2 policy (see apply_l2_policy)
+  bool l2_window_set = false;
   DevBuf d_partial;
   std::vector<cudaEvent_t> events;
   jrb_stats stats;
@@ -827,10 +829,47 @@ int jrb_stage(jrb_context *ctx, int npk, const jrb_atm_view *atm, const jrb_obs_
   return stage_locked(ctx, npk, atm, obs);
 }
 
+// L2 residency (north star: "pinned in L2 via access-policy windows").  The table brackets are what every warp keeps coming
+// back to (98 % of the gathers hit the L2), the line-of-sight records are streamed through once per channel group:
+//   JRB_L2_PERSIST=1     : persisting-L2 carve-out + access-policy window over the bracket array on the compute stream
+//   JRB_LOS_EVICT_FIRST=1: the TMA copies of the records carry the L2::evict_first hint
+// Both are measured in profiles/ and default to what measured best.
+static void apply_l2_policy(jrb_context *ctx) {
+  const char *ef = getenv("JRB_LOS_EVICT_FIRST");
+  ctx->los_evict_first = ef ? (atoi(ef) != 0) : 0;
+  const char *ps = getenv("JRB_L2_PERSIST");
+  const bool want = ps ? (atoi(ps) != 0) : false;
+  if (want == ctx->l2_window_set && !want) return;
+  cudaStreamAttrValue attr;
+  std::memset(&attr, 0, sizeof(attr));
+  if (want) {
+    int max_persist = 0, max_window = 0;
+    cudaDeviceGetAttribute(&max_persist, cudaDevAttrMaxPersistingL2CacheSize, ctx->device);
+    cudaDeviceGetAttribute(&max_window, cudaDevAttrMaxAccessPolicyWindowSize, ctx->device);
+    if (max_persist <= 0 || max_window <= 0) return;
+    double frac = 0.75;
+    if (const char *f = getenv("JRB_L2_PERSIST_FRACTION")) { const double v = atof(f); if (v > 0 && v <= 1) frac = v; }
+    const size_t carve = (size_t)((double)max_persist * frac);
+    cudaDeviceSetLimit(cudaLimitPersistingL2CacheSize, carve);
+    const size_t brk_bytes = (size_t)ctx->tbl->th.n_entries * 16;
+    const size_t win = std::min(brk_bytes, (size_t)max_window);
+    attr.accessPolicyWindow.base_ptr = (void *)ctx->tbl->td.brk;
+    attr.accessPolicyWindow.num_bytes = win;
+    attr.accessPolicyWindow.hitRatio = (float)std::min(1.0, (double)carve / (double)win);
+    attr.accessPolicyWindow.hitProp = cudaAccessPropertyPersisting;
+    attr.accessPolicyWindow.missProp = cudaAccessPropertyStreaming;
+  } else {
+    attr.accessPolicyWindow.num_bytes = 0;
+  }
+  if (cudaStreamSetAttribute(ctx->stream, cudaStreamAttributeAccessPolicyWindow, &attr) != cudaSuccess) cudaGetLastError();
+  ctx->l2_window_set = want;
+}
+
 static int run_locked(jrb_context *ctx) {
   if (!ctx->staged) return ctx->fail(JRB_ERR_STATE, "nothing staged");
   ctx->ran = false;
   CU(cudaSetDevice(ctx->device));
+  apply_l2_policy(ctx);
   const long long R = ctx->n_rays, A = ctx->n_atm;
   const int ng = ctx->ng, nd = ctx->nd, nw = ctx->nw;
   const TblHeader &th = ctx->tbl->th;
@@ -891,6 +930,8 @@ static int run_locked(jrb_context *ctx) {
     // with the FOV epilogue the pencil-beam values stay on the device; the convolved ones are published afterwards
     e.rad_host = fov ? nullptr : ctx->ray_out + 0 * R + r0;
     e.tau_host = fov ? nullptr : ctx->ray_out + 1 * R + r0;
+    e.los_evict_first = ctx->los_evict_first;
+    if (getenv("JRB_NO_HOST_ROWS")) { e.rad_host = nullptr; e.tau_host = nullptr; } // measurement only: results stay on the device
     e.work_counter = (unsigned long long *)ctx->d_counter.p + 4 * c;
     e.balance = e.work_counter + 1;
     e.phase_lock_mode = -1;
