@@ -15,33 +15,54 @@ namespace jrb {
 
 namespace {
 
-// thread per (ray, channel): tau_gas = product of the block products in gas order, then what the fused kernel does per
-// segment (continua_core_bbbb, src_planck_core, new_obs_core) and per ray (add_surface_core, brightness_core)
+// Gas-independent part of a segment, fully parallel: thread per (ray, segment, channel) computes what the fused kernel
+// computes once per (segment, channel) -- exp(-beta_ds) of the continua / extinction (continua_core_bbbb) and the band
+// Planck source (src_planck_core) -- into a.seg_pre[ray][segment][channel] = {exp(-beta_ds), src}.  This takes the
+// transcendentals out of the sequential along-ray loop of the combine kernel.
+__global__ void __launch_bounds__(256) ega_segment_kernel(const EgaArgs a) {
+  const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  const int nd = a.nd;
+  const long long seg = idx / nd; // (ray, segment) pair
+  const int id = (int)(idx - seg * nd);
+  const long long ir = seg / kNLOS;
+  const int ip = (int)(seg - ir * kNLOS);
+  if (ir >= a.n_rays || ip >= a.ray_np[ir]) return;
+  const LosLayout L = a.los;
+  const double *__restrict__ rec = a.los_data + ((size_t)ir * kNLOS + ip) * L.rec;
+  const double p = rec[0], t = rec[1], ds = rec[2];
+  const double u_co2 = (a.ctm_mask & 8) ? rec[L.u0 + a.ig_co2] : 0.0;
+  const double u_h2o = (a.ctm_mask & 4) ? rec[L.u0 + a.ig_h2o] : 0.0;
+  const double beta_ds = continuum_beta_ds(a.ctm_mask, a.chan, nd, id, p, t, ds, a.nw > 0 ? rec[4 + a.window[id]] : 0.0, u_co2, u_h2o, rec[3]);
+  a.seg_pre[idx] = make_double2(exp(-beta_ds), planck_source(a.tbl.sr, nd, id, t));
+}
+
+// thread per (ray, channel): tau_gas = product of the block products in gas order, then the radiance update of the fused
+// kernel (new_obs_core) and its per-ray epilogues (add_surface_core, brightness_core).  Nothing in the loop but loads that
+// do not depend on the recurrence (unrolled: several segments in flight) and three multiply-adds.
 __global__ void __launch_bounds__(128) ega_combine_kernel(const EgaArgs a) {
   const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (idx >= a.n_rays * a.nd) return;
   const long long ir = idx / a.nd;
   const int id = (int)(idx - ir * a.nd), nd = a.nd;
-  const LosLayout L = a.los;
-  const double *__restrict__ rec = a.los_data + (size_t)ir * kNLOS * L.rec;
   const int np = a.ray_np[ir];
-  const int win = a.window[id];
   const int nb = a.n_gas_blocks;
   // segments every block has a product for; beyond it some block's factor is 0 and nothing is accumulated any more
   int n_live = np;
   for (int b = 0; b < nb; b++) n_live = min(n_live, a.partial_len[((size_t)b * a.n_rays + ir) * nd + id]);
   const size_t bstride = (size_t)a.n_rays * kNLOS * nd;
   const double *__restrict__ part = a.partial + ((size_t)ir * kNLOS) * nd + id;
+  const double2 *__restrict__ pre = a.seg_pre + ((size_t)ir * kNLOS) * nd + id;
   double rad = 0.0, tau = 1.0;
-  for (int ip = 0; ip < n_live; ++ip, rec += L.rec) {
+#pragma unroll 4
+  for (int ip = 0; ip < n_live; ++ip) {
     double tau_gas = 1.0;
     for (int b = 0; b < nb; b++) tau_gas *= part[(size_t)b * bstride + (size_t)ip * nd];
-    const double p = rec[0], t = rec[1], ds = rec[2];
-    const double u_co2 = (a.ctm_mask & 8) ? rec[L.u0 + a.ig_co2] : 0.0;
-    const double u_h2o = (a.ctm_mask & 4) ? rec[L.u0 + a.ig_h2o] : 0.0;
-    const double beta_ds = continuum_beta_ds(a.ctm_mask, a.chan, nd, id, p, t, ds, a.nw > 0 ? rec[4 + win] : 0.0, u_co2, u_h2o, rec[3]);
-    const double src = planck_source(a.tbl.sr, nd, id, t);
-    accumulate(rad, tau, beta_ds, src, tau_gas);
+    const double2 es = pre[(size_t)ip * nd];
+    if (tau_gas > 1e-50) { // new_obs_core (src/jr_common.h:293-300)
+      const double eps = 1. - tau_gas * es.x;
+      rad += es.y * eps * tau;
+      tau *= (1. - eps);
+    }
   }
   epilogue(rad, tau, a.ray_tsurf[ir], a.tbl.sr, nd, id, a.write_bbt, a.chan[CH_NU * nd + id]);
   a.rad[idx] = rad;
@@ -69,6 +90,14 @@ cudaError_t launch_ega_split_passes(const EgaArgs &a, cudaStream_t stream) {
   cudaGetDevice(&dev);
   cudaDeviceGetAttribute(&sm, cudaDevAttrMultiProcessorCount, dev);
   return launch_ega_split(a, stream, sm);
+}
+
+cudaError_t launch_ega_segments(const EgaArgs &a, cudaStream_t stream) {
+  const long long n = a.n_rays * kNLOS * a.nd;
+  if (n <= 0) return cudaSuccess;
+  if (!a.seg_pre) return cudaErrorInvalidValue;
+  ega_segment_kernel<<<(unsigned)((n + 255) / 256), 256, 0, stream>>>(a);
+  return cudaGetLastError();
 }
 
 cudaError_t launch_ega_combine(const EgaArgs &a, cudaStream_t stream) {

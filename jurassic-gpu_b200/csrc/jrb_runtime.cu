@@ -585,7 +585,9 @@ static int stage_locked(jrb_context *ctx, int npk, const jrb_atm_view *atm, cons
   // (b) Small batches -- above all the single 1088-ray package of an unmodified formod() caller: as many blocks as it takes
   // to give the GPU about two rounds of warps, down to one gas per block (results then bit-identical to the fused kernel).
   int gpb = ng > 0 ? ng : 1;
-  if (ng > 1 && !getenv("JRB_NO_SPLIT")) {
+  const char *pipe_env = getenv("JRB_PIPELINE");
+  const bool want_pipe = pipe_env && atoi(pipe_env) != 0 && R >= 32768; // (experimental chunk pipeline: fused kernel only)
+  if (ng > 1 && !getenv("JRB_NO_SPLIT") && !want_pipe) {
     if (ng > 12) gpb = (ng + (ng + 9) / 10 - 1) / ((ng + 9) / 10);
     const int cpw0 = nd <= 16 ? nd : 32, rpw0 = 32 / cpw0;
     const long long items = ((R + rpw0 - 1) / rpw0) * ((nd + cpw0 - 1) / cpw0);
@@ -762,7 +764,7 @@ static int stage_locked(jrb_context *ctx, int npk, const jrb_atm_view *atm, cons
   ctx->n_gas_blocks = use_fast ? nblk : 1;
   ctx->gases_per_block = gpb;
   // scratch per ray: the line-of-sight records, plus the per-segment block products in split mode
-  const size_t part_per_ray = ctx->n_gas_blocks > 1 ? (size_t)ctx->n_gas_blocks * ((size_t)kNLOS * nd * 8 + (size_t)nd * 4) : 0;
+  const size_t part_per_ray = ctx->n_gas_blocks > 1 ? (size_t)ctx->n_gas_blocks * ((size_t)kNLOS * nd * 8 + (size_t)nd * 4) + (size_t)kNLOS * nd * 16 : 0;
   const size_t per_ray = (size_t)kNLOS * ctx->los.rec * 8 + part_per_ray;
   // LOS scratch: JRB_LOS_GB / jrb_set_los_limit_gb (default 72 GB: the 1 000 960 rays of BASELINE's config D need 64 GB),
   // but never more than half of what is free on the device.  The driver is only asked (cudaMemGetInfo takes a
@@ -785,9 +787,7 @@ static int stage_locked(jrb_context *ctx, int npk, const jrb_atm_view *atm, cons
   // the extra EGA kernel tails cost more than the hidden tracer time (143.4 vs 138.3 ms), hence opt-in.
   long long chunk = (long long)(los_gb * 1e9 / (double)per_ray);
   ctx->nbuf = 1;
-  const char *pipe_env = getenv("JRB_PIPELINE");
-  const bool want_pipe = pipe_env && atoi(pipe_env) != 0;
-  if (want_pipe && R >= 32768) {
+  if (want_pipe) {
     long long pc = (R + 7) / 8;
     if (pc < 8192) pc = 8192;
     if (pc * 3 > chunk) pc = chunk / 3;
@@ -943,13 +943,16 @@ static int run_locked(jrb_context *ctx) {
     if (pipe) CU(cudaStreamWaitEvent(st_e, EV(c, 1), 0));
     CU(cudaEventRecord(EV(c, 2), st_e));
     e.n_gas_blocks = ctx->n_gas_blocks; e.gases_per_block = ctx->gases_per_block;
-    e.partial = nullptr; e.partial_len = nullptr;
+    e.partial = nullptr; e.partial_len = nullptr; e.seg_pre = nullptr;
     if (ctx->use_fast && ctx->n_gas_blocks > 1) { // split mode: gas-block passes, then the combine kernel
-      e.partial = (double *)ctx->d_partial.p;
-      e.partial_len = (int *)((char *)ctx->d_partial.p + (size_t)ctx->n_gas_blocks * (size_t)e.n_rays * kNLOS * nd * 8);
+      char *pb = (char *)ctx->d_partial.p;
+      e.seg_pre = (double2 *)pb; pb += (size_t)e.n_rays * kNLOS * nd * 16;
+      e.partial = (double *)pb; pb += (size_t)ctx->n_gas_blocks * (size_t)e.n_rays * kNLOS * nd * 8;
+      e.partial_len = (int *)pb;
+      CU(launch_ega_segments(e, st_e));
       CU(launch_ega_split_passes(e, st_e));
       CU(launch_ega_combine(e, st_e));
-      launches++;
+      launches += 2;
     } else if (ctx->use_fast) CU(launch_ega_fast(e, st_e, &ngb));
     else CU(launch_ega_generic(e, st_e));
     launches += (ctx->use_fast && e.phase_lock_mode < 0 && e.n_rays > 0) ? 2 : 1; // + chunk_balance_kernel

@@ -257,6 +257,7 @@ def test_pipelined_chunks_give_identical_results(jr, gpu_ctx_factory, monkeypatc
     tbl = jr.synth.make_tables(ctl)
     pkgs = [jr.synth.limb_package(ctl, seed=500 + i) for i in range(34)]  # 36 992 rays >= the pipelining threshold
     ctx = gpu_ctx_factory()
+    monkeypatch.setenv("JRB_NO_SPLIT", "1")  # the pipeline runs the fused kernel; gas blocks of several gases regroup the product
     plain = run_cuda(ctx, ctl, tbl, pkgs, 1)
     assert ctx.stats()["pipelined"] == 0
     monkeypatch.setenv("JRB_PIPELINE", "1")
@@ -485,8 +486,8 @@ def test_inputs_outside_the_reference_domain_stay_defined(jr, oracle, gpu_ctx_fa
 
 
 def test_full_baseline_size_in_one_call(jr, gpu_ctx_factory):
-    """BASELINE.json's full Config-D size in ONE call: 920 packages = 1 000 960 rays x 32 channels (the LOS scratch
-    limit forces several chunks).  Size-independent properties: the 8 copies of each of 115 distinct packages, scattered
+    """BASELINE.json's full Config-D size in ONE call: 920 packages = 1 000 960 rays x 32 channels (a LOS scratch
+    limit of 24 GB forces several chunks).  Size-independent properties: the 8 copies of each of 115 distinct packages, scattered
     over the batch, come back bit-identical (checksum of checksums), tau in [0,1], rad finite and >= 0, every ray traced."""
     ctl = jr.synth.control_config_d()
     tbl = jr.synth.make_tables(ctl)
@@ -496,6 +497,7 @@ def test_full_baseline_size_in_one_call(jr, gpu_ctx_factory):
     ctx = gpu_ctx_factory()
     ctx.set_control(ctl)
     ctx.set_tables(tbl)
+    jr.load_core().jrb_set_los_limit_gb(ctx.h, 24.0)  # the default (72 GB) would hold all rays in one chunk
     ctx.formod_batch(pkgs)
     st = ctx.stats()
     assert st["n_rays"] == 1000960 and st["n_ray_channels"] == 1000960 * 32 and st["ega_kernel_variant"] == 1
