@@ -45,7 +45,7 @@ __global__ void __launch_bounds__(128) ega_combine_kernel(const EgaArgs a) {
   const long long ir = idx / a.nd;
   const int id = (int)(idx - ir * a.nd), nd = a.nd;
   const int np = a.ray_np[ir];
-  const int nb = a.n_gas_blocks;
+  const int nb = a.n_gas_blocks, bpg = max(a.blocks_per_group, 1);
   // segments every block has a product for; beyond it some block's factor is 0 and nothing is accumulated any more
   int n_live = np;
   for (int b = 0; b < nb; b++) n_live = min(n_live, a.partial_len[((size_t)b * a.n_rays + ir) * nd + id]);
@@ -56,7 +56,11 @@ __global__ void __launch_bounds__(128) ega_combine_kernel(const EgaArgs a) {
 #pragma unroll 4
   for (int ip = 0; ip < n_live; ++ip) {
     double tau_gas = 1.0;
-    for (int b = 0; b < nb; b++) tau_gas *= part[(size_t)b * bstride + (size_t)ip * nd];
+    for (int b0 = 0; b0 < nb; b0 += bpg) { // product groups in order; inside a group a running product in gas order
+      double pg = 1.0;
+      for (int b = b0; b < min(b0 + bpg, nb); b++) pg *= part[(size_t)b * bstride + (size_t)ip * nd];
+      tau_gas *= pg;
+    }
     const double2 es = pre[(size_t)ip * nd];
     if (tau_gas > 1e-50) { // new_obs_core (src/jr_common.h:293-300)
       const double eps = 1. - tau_gas * es.x;

@@ -33,6 +33,7 @@ struct TraceArgs {
   double *const *tp_host; // optional [3][geo_stride] per-ray addresses in host-mapped memory (the caller's obs_t or the
                           // pinned result buffer): the tangent point is also stored there -- no device-to-host copy phase
   TblDev tbl;       // used when los.fast
+  int *error_flag;  // host-mapped word: bit 0 = a ray needs NLOS or more points (fatal "Too many LOS points!" in the reference's CPU path)
 };
 
 struct EgaArgs {
@@ -63,6 +64,7 @@ struct EgaArgs {
   int cpw;                          // channels of a ray per warp: 32, or less (= several rays per warp, see jrb_ega_fast.cuh)
   // gas-block passes (split mode, see ega_fast_kernel<SPLIT>): block b holds gases [b*gases_per_block, ...)
   int n_gas_blocks, gases_per_block;
+  int blocks_per_group;             // combine: the products of this many consecutive blocks are multiplied first (canonical order)
   double *partial;                  // [n_gas_blocks][n_rays][NLOS][nd] per-segment product of the block's gas factors
   int *partial_len;                 // [n_gas_blocks][n_rays][nd] segments that carry a product (a gas went opaque at len-1 if < np)
   double2 *seg_pre;                 // [n_rays][NLOS][nd] {exp(-beta_ds), Planck source} per segment and channel (ega_segment_kernel)

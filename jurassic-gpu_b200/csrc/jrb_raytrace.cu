@@ -227,7 +227,10 @@ __global__ void __launch_bounds__(128) ray_step_kernel(TraceArgs a) {
       }
     }
     if (np > 0 || stop) ++np;   // the reference increments after the loop (:692)
-    if (np > kNLOS) np = kNLOS; // (reference: fatal "Too many LOS points" on the CPU when np >= NLOS)
+    // the reference's CPU path is fatal here ("Too many LOS points!" when NLOS <= np, src/jr_common.h:693-695): reported
+    // through the error word, the run then fails instead of returning a truncated ray
+    if (np >= kNLOS && a.error_flag) *a.error_flag = 1;
+    if (np > kNLOS) np = kNLOS;
   }
 
   // ---- tangent point (from the raw step lengths; :502-539) ----

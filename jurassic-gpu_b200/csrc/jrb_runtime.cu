@@ -146,7 +146,8 @@ struct jrb_context {
   LosLayout los;
   int use_fast = 0;
   int cpw = 32;
-  int n_gas_blocks = 1, gases_per_block = 1; // split mode (jrb_ega_split.cu) when n_gas_blocks > 1
+  int n_gas_blocks = 1, gases_per_block = 1, blocks_per_group = 1; // split mode (jrb_ega_split.cu) when n_gas_blocks > 1
+  int *err_flag = nullptr;   // word in the pinned table buffer the tracer reports "too many LOS points" through
   int los_evict_first = 0;   // L2 policy (see apply_l2_policy)
   bool l2_window_set = false;
   DevBuf d_partial;
@@ -580,25 +581,28 @@ static int stage_locked(jrb_context *ctx, int npk, const jrb_atm_view *atm, cons
   }
 
   // ---- kernel choice (before anything is allocated) ----
-  // Split mode (gas-block passes + combine kernel, jrb_ega_split.cu).  (a) Many gases: blocks of at most 10, so that 24 warps
-  // per SM keep their per-gas state (16 B per gas and thread) in shared memory and the tables of one pass fit the L2.
-  // (b) Small batches -- above all the single 1088-ray package of an unmodified formod() caller: as many blocks as it takes
-  // to give the GPU about two rounds of warps, down to one gas per block (results then bit-identical to the fused kernel).
-  int gpb = ng > 0 ? ng : 1;
+  // Split mode (gas-block passes + combine kernel, jrb_ega_split.cu).  The ORDER in which the gas factors of a segment are
+  // multiplied is a function of ng alone, so that results do not depend on how a batch is cut (packages per call, devices):
+  // up to 12 gases one running product in gas order (what the fused kernel and the reference do); above, groups of at most
+  // 10 gases whose products are multiplied in group order.  What varies with the batch is only how the work is cut:
+  //  (a) many gases: one pass per group, so that 24 warps per SM keep their per-gas state (16 B per gas and thread) in
+  //      shared memory and the tables of one pass fit the L2;
+  //  (b) small batches -- above all the single 1088-ray package of an unmodified formod() caller: one gas per pass item, which
+  //      gives the GPU ng times more independent warps; the combine kernel multiplies the factors in the canonical order.
+  const int gcan = ng > 12 ? (ng + (ng + 9) / 10 - 1) / ((ng + 9) / 10) : (ng > 0 ? ng : 1); // gases per product group
+  int gpb = gcan;                                                                             // gases per pass item
   const char *pipe_env = getenv("JRB_PIPELINE");
   const bool want_pipe = pipe_env && atoi(pipe_env) != 0 && R >= 32768; // (experimental chunk pipeline: fused kernel only)
+  int bpg = 1; // pass blocks per product group
   if (ng > 1 && !getenv("JRB_NO_SPLIT") && !want_pipe) {
-    if (ng > 12) gpb = (ng + (ng + 9) / 10 - 1) / ((ng + 9) / 10);
     const int cpw0 = nd <= 16 ? nd : 32, rpw0 = 32 / cpw0;
     const long long items = ((R + rpw0 - 1) / rpw0) * ((nd + cpw0 - 1) / cpw0);
     const long long slots = (long long)ctx->sm_count * 24;
-    if (items > 0 && items * ((ng + gpb - 1) / gpb) < 2 * slots) {
-      long long want = (2 * slots + items - 1) / items;
-      if (want > ng) want = ng;
-      gpb = (int)((ng + want - 1) / want);
-    }
+    if (items > 0 && items * ((ng + gcan - 1) / gcan) < 2 * slots) { gpb = 1; bpg = gcan; }
+  } else {
+    gpb = ng > 0 ? ng : 1; // fused kernel (for more than 12 gases its product order differs from the canonical one)
   }
-  if (const char *e = getenv("JRB_EGA_GAS_BLOCK")) { const int v = atoi(e); if (v >= 1 && v <= ng) gpb = v; } // experiments
+  if (const char *e = getenv("JRB_EGA_GAS_BLOCK")) { const int v = atoi(e); if (v >= 1 && v <= ng) { gpb = v; bpg = 1; } } // experiments
   const int nblk = ng > 0 ? (ng + gpb - 1) / gpb : 1;
   const int cpw = choose_cpw(ctx, nblk > 1 ? gpb : ng);
   // channel-dependent (p,T) axes: the specialised kernel locates the table cell per lane (PERCH) and the records carry no cell
@@ -615,7 +619,8 @@ static int stage_locked(jrb_context *ctx, int npk, const jrb_atm_view *atm, cons
   const int n_geo = 7, n_af = 6 + ng + nw, n_src = n_geo + n_af;
   const size_t off_roff = 0, off_aoff = off_roff + (size_t)(npk + 1) * 8, off_out = off_aoff + (size_t)(npk + 1) * 8;
   const size_t off_src = off_out + (size_t)npk * sizeof(OutTab);
-  const size_t tab_bytes = align_up(off_src + (size_t)npk * n_src * 8, 256) + 256;
+  const size_t off_flag = align_up(off_src + (size_t)npk * n_src * 8, 256); // error word written by the tracer (host-mapped)
+  const size_t tab_bytes = off_flag + 256;
   CU(ctx->h_tab.ensure(tab_bytes));
   CU(ctx->d_tab.ensure(tab_bytes));
   unsigned char *HT = (unsigned char *)ctx->h_tab.p;
@@ -623,6 +628,8 @@ static int stage_locked(jrb_context *ctx, int npk, const jrb_atm_view *atm, cons
   OutTab *h_outtab = (OutTab *)(HT + off_out);
   const double **h_src = (const double **)(HT + off_src);
 
+  ctx->err_flag = (int *)(HT + off_flag);
+  *ctx->err_flag = 0;
   ctx->pk_nr.resize(npk);
   ctx->pk_ray_off.resize(npk + 1);
   {
@@ -763,6 +770,7 @@ static int stage_locked(jrb_context *ctx, int npk, const jrb_atm_view *atm, cons
   ctx->los = make_los_layout(ng, nw, use_fast && th.all_shared, th.gas_axes_same);
   ctx->n_gas_blocks = use_fast ? nblk : 1;
   ctx->gases_per_block = gpb;
+  ctx->blocks_per_group = bpg;
   // scratch per ray: the line-of-sight records, plus the per-segment block products in split mode
   const size_t part_per_ray = ctx->n_gas_blocks > 1 ? (size_t)ctx->n_gas_blocks * ((size_t)kNLOS * nd * 8 + (size_t)nd * 4) + (size_t)kNLOS * nd * 16 : 0;
   const size_t per_ray = (size_t)kNLOS * ctx->los.rec * 8 + part_per_ray;
@@ -908,6 +916,7 @@ static int run_locked(jrb_context *ctx) {
     t.ray_level0 = (int *)ctx->d_level0.p + r0;
     t.tp = ctx->o_tp + r0;
     t.tp_host = ctx->ray_out + 2 * R + r0;
+    t.error_flag = ctx->err_flag;
     t.tbl = ctx->tbl->td;
     if (pipe && c >= ctx->nbuf) CU(cudaStreamWaitEvent(st_tr, EV(c - ctx->nbuf, 3), 0)); // LOS buffer free again
     CU(cudaEventRecord(EV(c, 0), st_tr));
@@ -942,7 +951,7 @@ static int run_locked(jrb_context *ctx) {
     if (const char *s = getenv("JRB_EGA_CHUNK")) { const int v = atoi(s); if (v >= 1 && v <= 200) e.work_chunk = v; } // experiments
     if (pipe) CU(cudaStreamWaitEvent(st_e, EV(c, 1), 0));
     CU(cudaEventRecord(EV(c, 2), st_e));
-    e.n_gas_blocks = ctx->n_gas_blocks; e.gases_per_block = ctx->gases_per_block;
+    e.n_gas_blocks = ctx->n_gas_blocks; e.gases_per_block = ctx->gases_per_block; e.blocks_per_group = ctx->blocks_per_group;
     e.partial = nullptr; e.partial_len = nullptr; e.seg_pre = nullptr;
     if (ctx->use_fast && ctx->n_gas_blocks > 1) { // split mode: gas-block passes, then the combine kernel
       char *pb = (char *)ctx->d_partial.p;
@@ -993,6 +1002,10 @@ static int run_locked(jrb_context *ctx) {
   }
   CU(cudaEventRecord(ctx->events[1], ctx->stream));
   CU(cudaStreamSynchronize(ctx->stream));
+  if (ctx->err_flag && *ctx->err_flag) { // like the reference's CPU path (src/jr_common.h:693-695)
+    *ctx->err_flag = 0;
+    return ctx->fail(JRB_ERR_LIMIT, "Too many LOS points!");
+  }
   if (ctx->fov_applied) {
     int flag = 0;
     CU(cudaMemcpy(&flag, ctx->d_flag.p, 4, cudaMemcpyDeviceToHost));

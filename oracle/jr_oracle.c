@@ -398,6 +398,7 @@ int jro_formod(const jrb_ctl_view *c, const jrb_tbl_view *v, const jrb_atm_view 
   for (int ir = 0; ir < nr; ir++)
     for (int id = 0; id < nd; id++) mask[(size_t)ir * nd + id] = !isfinite(o->rad[(size_t)ir * o->row_stride + id]); /* save_mask :193-200 */
   if (c->hydz >= 0) o_hydrostatic(c, a, c->ig_h2o); /* hydrostatic1d_CPU :97-103 (idempotent, so once) */
+  int too_many = 0; /* the reference is fatal ("Too many LOS points!") when a ray needs NLOS points or more (:693-695) */
 #pragma omp parallel
   {
     o_pos *los = o_alloc_los(c->ng, c->nw);
@@ -406,6 +407,10 @@ int jro_formod(const jrb_ctl_view *c, const jrb_tbl_view *v, const jrb_atm_view 
     for (int ir = 0; ir < nr; ir++) {
       double tsurf;
       const int np = o_traceray(c, a, o, ir, los, &tsurf);
+      if (np >= O_NLOS) {
+#pragma omp atomic write
+        too_many = 1;
+      }
       double *rad = o->rad + (size_t)ir * o->row_stride, *tau = o->tau + (size_t)ir * o->row_stride;
       for (int id = 0; id < o->nd_reset; id++) { rad[id] = 0.0; tau[id] = 1.0; } /* apply_kernels_CPU :57-64 */
       for (int j = 0; j < nd * (c->ng + 1); j++) tau_path[j] = 1.0;
@@ -435,7 +440,7 @@ int jro_formod(const jrb_ctl_view *c, const jrb_tbl_view *v, const jrb_atm_view 
     o_free_los(los);
   }
   free(mask);
-  return 0;
+  return too_many ? -2 : 0;
 }
 
 /* LOS of one ray flattened like oracle/ref_hooks.c:jrref_traceray:

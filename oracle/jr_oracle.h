@@ -5,7 +5,8 @@
 #ifdef __cplusplus
 extern "C" {
 #endif
-/* complete forward model for one package; same semantics as formod_CPU (src/CPUdrivers.c:108-151). 0 on success */
+/* complete forward model for one package; same semantics as formod_CPU (src/CPUdrivers.c:108-151). 0 on success,
+ * -2 where the reference is fatal with "Too many LOS points!" (a ray of NLOS = 400 points or more, src/jr_common.h:693-695) */
 int jro_formod(const jrb_ctl_view *ctl, const jrb_tbl_view *tbl, const jrb_atm_view *atm, const jrb_obs_view *obs);
 /* ray tracer only; flattened LOS, see jr_oracle.c */
 int jro_traceray(const jrb_ctl_view *ctl, const jrb_atm_view *atm, const jrb_obs_view *obs, int ir, double *out, double *tsurf);

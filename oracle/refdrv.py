@@ -41,6 +41,8 @@ class Oracle:
     def formod(self, ctl, tbl, pkg):
         cv, tv, av, ov = ctl.view(), tbl.view(), pkg.atm_view(), pkg.obs_view()
         rc = self.lib.jro_formod(C.byref(cv), C.byref(tv), C.byref(av), C.byref(ov))
+        if rc == -2:
+            raise RuntimeError("Too many LOS points!")  # where the reference's CPU path exits (src/jr_common.h:693-695)
         if rc != 0:
             raise RuntimeError("jro_formod failed")
 

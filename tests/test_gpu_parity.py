@@ -557,3 +557,18 @@ def test_narrow_channel_groups_give_identical_results(jr, oracle, gpu_ctx_factor
         for a, b in zip(base, out):
             assert np.array_equal(a.rad, b.rad) and np.array_equal(a.tau, b.tau), cpw
     monkeypatch.delenv("JRB_EGA_CPW", raising=False)
+
+
+def test_too_many_los_points_is_an_error(jr, gpu_ctx_factory):
+    """a ray that needs NLOS = 400 points or more: the reference's CPU path is fatal ("Too many LOS points!",
+    src/jr_common.h:693-695); the CUDA path fails the call instead of returning a truncated ray.  Afterwards the context works."""
+    ctl = jr.Control(["CO2", "H2O"], [792.0, 832.0], rayds=4.0, raydz=0.2)
+    tbl = jr.synth.make_tables(ctl)
+    pkg = jr.synth.limb_package(ctl, n_profiles=1, rays_per_profile=4, z0=2.0, dz=20.0, seed=1)
+    ctx = gpu_ctx_factory()
+    ctx.set_control(ctl); ctx.set_tables(tbl)
+    with pytest.raises(jr.JrbError, match="Too many LOS points"):
+        ctx.formod_batch([copy.deepcopy(pkg)])
+    ok = jr.synth.limb_package(ctl, n_profiles=1, rays_per_profile=4, z0=30.0, dz=10.0, seed=1)
+    ctx.formod_batch([ok])
+    assert np.all(np.isfinite(ok.rad)) and ok.tau.max() <= 1.0

@@ -106,3 +106,31 @@ def test_refspec_shape_full_package(jr, oracle, gpu_ctx_factory):
     ref = run_oracle(oracle, ctl, tbl, [pkg])[0]
     assert_parity(mine, ref, "refspec 66 x 100 x 30")
     assert ref.tau.min() < 1e-3 and ref.tau.max() > 0.9  # from opaque to nearly transparent
+
+
+def test_results_do_not_depend_on_how_a_batch_is_cut(jr, gpu_ctx_factory):
+    """the order in which the gas factors are multiplied is a function of ng alone: a package alone (one gas per pass item)
+    and the same package inside a large batch (fused kernel, or one pass per group of 10 gases) give the same bits --
+    which is what makes sharding over devices bit-identical"""
+    ctx = gpu_ctx_factory()
+    # 5 gases: alone -> 5 one-gas blocks; in a batch of 8 -> fused
+    ctl = jr.synth.control_config_d()
+    tbl = jr.synth.make_tables(ctl)
+    pkgs = [jr.synth.limb_package(ctl, seed=900 + i) for i in range(8)]
+    batch = run_cuda(ctx, ctl, tbl, pkgs, 1)
+    assert ctx.stats()["ega_gas_blocks"] == 1
+    alone = run_cuda(ctx, ctl, tbl, [pkgs[5]], 1)[0]
+    assert ctx.stats()["ega_gas_blocks"] == 5
+    _same_bits(alone, batch[5], "5 gases: alone vs in a batch")
+    # 30 gases (3 product groups of 10): alone -> 30 one-gas blocks; in a batch -> one pass per group
+    gases = ["CO2", "H2O", "O3", "N2O", "CH4", "CO", "HNO3", "SO2", "F11", "CCl4"] + [f"X{i}" for i in range(20)]
+    ctl = jr.Control(gases, 2150.0 + np.arange(32))
+    tbl = jr.synth.make_tables(ctl)
+    pkgs = [jr.synth.limb_package(ctl, seed=950 + i) for i in range(8)]
+    for p in pkgs:
+        p.q[10:, :] = 1e-9 * (1 + np.arange(20))[:, None]
+    batch = run_cuda(ctx, ctl, tbl, pkgs, 1)
+    assert ctx.stats()["ega_gas_blocks"] == 3
+    alone = run_cuda(ctx, ctl, tbl, [pkgs[2]], 1)[0]
+    assert ctx.stats()["ega_gas_blocks"] == 30
+    _same_bits(alone, batch[2], "30 gases: alone vs in a batch")

@@ -224,3 +224,33 @@ def test_oracle_fov_needs_two_rays_per_scan(jr, oracle):
     ctl = jr.synth.control_limb_example()
     pkg = jr.synth.limb_package(ctl, n_profiles=2, rays_per_profile=1, seed=5)
     assert not oracle.formod_fov(pkg, [0.0], [1.0])
+
+
+_TOO_LONG = """
+import sys, importlib
+sys.path.insert(0, {root!r}); sys.path.insert(0, {root!r} + '/oracle')
+jr = importlib.import_module('jurassic-gpu_b200'); import refdrv
+ctl = jr.Control(['CO2', 'H2O'], [792.0, 832.0], rayds=4.0, raydz=0.2)
+tbl = jr.synth.make_tables(ctl)
+pkg = jr.synth.limb_package(ctl, n_profiles=1, rays_per_profile=4, z0=2.0, dz=20.0, seed=1)
+ref = refdrv.Reference(2, 5)
+tp = ref.make_tbl(tbl)
+ref.formod_tbl(ref.make_ctl(ctl), ref.make_atm(pkg), ref.make_obs(pkg), tp)
+print('SURVIVED')
+"""
+
+
+def test_too_many_los_points_is_fatal_in_the_reference_and_an_error_in_the_oracle(jr, oracle, refdrv):
+    """a ray of NLOS = 400 points or more: the reference's CPU path exits with "Too many LOS points!"
+    (src/jr_common.h:693-695); the restatement reports it, and so does the CUDA path (tests/test_gpu_parity.py)"""
+    import subprocess
+    import sys
+    ctl = jr.Control(["CO2", "H2O"], [792.0, 832.0], rayds=4.0, raydz=0.2)
+    tbl = jr.synth.make_tables(ctl)
+    pkg = jr.synth.limb_package(ctl, n_profiles=1, rays_per_profile=4, z0=2.0, dz=20.0, seed=1)
+    with pytest.raises(RuntimeError, match="Too many LOS points"):
+        oracle.formod(ctl, tbl, pkg)
+    _need(refdrv, 2, 5)
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    r = subprocess.run([sys.executable, "-c", _TOO_LONG.format(root=root)], capture_output=True, text=True, timeout=300)
+    assert r.returncode != 0 and "Too many LOS points!" in r.stdout and "SURVIVED" not in r.stdout
