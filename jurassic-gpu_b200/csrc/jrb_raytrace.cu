@@ -16,6 +16,7 @@
 //                        channel -- the table cell and interpolation weights per gas, so that the EGA kernel does
 //                        not search axes per channel.
 #include "jrb_internal.h"
+#include <cstdlib>
 
 namespace jrb {
 
@@ -90,8 +91,18 @@ __global__ void atm_slopes_kernel(const double *__restrict__ z, const double *__
   tslope[i] = st;
 }
 
+// LPR = lanes per ray.  1: one thread walks one ray (throughput form, large batches).  8: a group of 8 lanes walks one
+// ray together -- the five (p,T) evaluations of a step (the point itself and the four probe points of the refractivity
+// gradient) are independent and run on five lanes side by side, everything else is computed redundantly by all lanes of
+// the group; the per-step instruction count drops ~3x and a batch has 8x more warps.  That is what a small batch needs
+// (a single 1088-ray package is 34 warps in the throughput form: one warp per scheduler on 9 SMs, every dependent FP64
+// instruction exposed).  Every evaluation uses the same expressions in both forms: bit-identical results.
+template <int LPR>
 __global__ void __launch_bounds__(128) ray_step_kernel(TraceArgs a) {
-  const long long r = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  const long long gtid = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  const long long r = gtid / LPR;
+  const int role = LPR > 1 ? (int)(threadIdx.x & (LPR - 1)) : 0;                                   // lane within the ray's group
+  const unsigned gmask = LPR > 1 ? ((LPR >= 32 ? 0xffffffffu : ((1u << LPR) - 1u)) << ((threadIdx.x & 31) & ~(LPR - 1))) : 0u; // the group's lanes
   if (r >= a.n_rays) return;
 
   const LosLayout L = a.los;
@@ -181,27 +192,55 @@ __global__ void __launch_bounds__(128) ray_step_kernel(TraceArgs a) {
         const double frac = (zfrac - zprev) / (z - zprev);
         for (int i = 0; i < 3; i++) x[i] = xprev[i] + frac * (x[i] - xprev[i]);
         z = norm3(x) - kRE;
-        rec0[(size_t)(np - 1) * L.rec + L.z0 + LT_DSRAW] = ds * frac;
+        if (role == 0) rec0[(size_t)(np - 1) * L.rec + L.z0 + LT_DSRAW] = ds * frac;
         ds = 0.0;
       }
-      P.pt(z, level, &p, &t);
-      double *__restrict__ rec = rec0 + (size_t)np * L.rec;
-      rec[0] = p; rec[1] = t;
-      double *__restrict__ tail = rec + L.z0;
-      tail[LT_Z] = z; tail[LT_DSRAW] = ds; tail[LT_LEVEL] = (double)level;
-      tail[LT_X] = x[0]; tail[LT_X + 1] = x[1]; tail[LT_X + 2] = x[2];
+      double nref = 1.0, ngr[3] = {0.0, 0.0, 0.0};
+      const double h = 0.02;
+      if (LPR == 1) {
+        P.pt(z, level, &p, &t);
+      } else {
+        // lane 0 of the group: the point itself; lane 1: the half-step point; lanes 2..4: half step + h along each axis.
+        // (the probe points are only needed below 60 km with refraction on and not at the last point; evaluating them
+        //  anyway costs nothing -- the lanes would idle -- and keeps the group convergent)
+        double zj = z;
+        if (role >= 1 && role <= 4) {
+          double xh[3];
+          for (int i = 0; i < 3; i++) xh[i] = x[i] + 0.5 * ds * ex0[i];
+          const double r2 = xh[0] * xh[0] + xh[1] * xh[1] + xh[2] * xh[2];
+          const double xi = role == 2 ? xh[0] : (role == 3 ? xh[1] : xh[2]);
+          zj = (role == 1 ? sqrt(r2) : sqrt(fma(h, fma(2.0, xi, h), r2))) - kRE;
+        }
+        const int lvj = P.locate(zj, level);
+        double pj, tj;
+        P.eval(zj, lvj, &pj, &tj);
+        const double nj = refractivity(pj, tj);
+        p = __shfl_sync(gmask, pj, 0, LPR); t = __shfl_sync(gmask, tj, 0, LPR);
+        level = __shfl_sync(gmask, lvj, 0, LPR);
+        const double n2 = __shfl_sync(gmask, nj, 1, LPR);
+        const double g0 = __shfl_sync(gmask, nj, 2, LPR), g1 = __shfl_sync(gmask, nj, 3, LPR), g2 = __shfl_sync(gmask, nj, 4, LPR);
+        if (a.refrac && z <= 60.0) {
+          nref += refractivity(p, t);
+          ngr[0] = (g0 - n2) * (1.0 / h); ngr[1] = (g1 - n2) * (1.0 / h); ngr[2] = (g2 - n2) * (1.0 / h);
+        }
+      }
+      if (role == 0) {
+        double *__restrict__ rec = rec0 + (size_t)np * L.rec;
+        rec[0] = p; rec[1] = t;
+        double *__restrict__ tail = rec + L.z0;
+        tail[LT_Z] = z; tail[LT_DSRAW] = ds; tail[LT_LEVEL] = (double)level;
+        tail[LT_X] = x[0]; tail[LT_X + 1] = x[1]; tail[LT_X + 2] = x[2];
+      }
       for (int i = 0; i < 3; i++) xprev[i] = x[i];
       zprev = z;
       if (z < z_low) { z_low = z; z_low_idx = np; }
 
       if (stop) { tsurf = (stop == 2 ? t : -999.0); break; }
 
-      double nref = 1.0, ngr[3] = {0.0, 0.0, 0.0};
-      if (a.refrac && z <= 60.0) { // refractivity gradient by finite differences at the half step (:664-681)
+      if (LPR == 1 && a.refrac && z <= 60.0) { // refractivity gradient by finite differences at the half step (:664-681)
         nref += refractivity(p, t);
         // the four probe points (half step, and half step + h along each axis) are independent: altitudes, level
         // searches and the exponentials are evaluated side by side
-        const double h = 0.02;
         double xh[3], zz[4], ph[4], th[4];
         int lv[4];
         for (int i = 0; i < 3; i++) xh[i] = x[i] + 0.5 * ds * ex0[i];
@@ -233,6 +272,7 @@ __global__ void __launch_bounds__(128) ray_step_kernel(TraceArgs a) {
     if (np > kNLOS) np = kNLOS;
   }
 
+  if (role != 0) return; // the rest is done by the first lane of the group (it wrote the records it reads back here)
   // ---- tangent point (from the raw step lengths; :502-539) ----
   if (np > 0) {
     const int ip = z_low_idx;
@@ -347,7 +387,10 @@ cudaError_t launch_raytrace(const TraceArgs &a, cudaStream_t stream, int *launch
   // pipelined chunks run beside the persistent EGA CTAs of the previous chunk, which leave ~4 K registers per SM:
   // one-warp ray CTAs (104 regs x 32) and two-warp finalisation CTAs (48 regs x 64) fit into that remainder
   const int bs = a.small_blocks ? 32 : 128, bf = a.small_blocks ? 64 : 256;
-  ray_step_kernel<<<(unsigned)((a.n_rays + bs - 1) / bs), bs, 0, stream>>>(a);
+  // small batches: 8 lanes per ray (see ray_step_kernel); from ~16 k rays on the throughput form fills the schedulers
+  const bool coop = !a.small_blocks && a.n_rays <= 16384 && !getenv("JRB_NO_COOP_TRACER");
+  if (coop) ray_step_kernel<8><<<(unsigned)((a.n_rays * 8 + 127) / 128), 128, 0, stream>>>(a);
+  else ray_step_kernel<1><<<(unsigned)((a.n_rays + bs - 1) / bs), bs, 0, stream>>>(a);
   const long long n = a.n_rays * kNLOS;
   los_finalize_kernel<<<(unsigned)((n + bf - 1) / bf), bf, 0, stream>>>(a);
   if (launches) *launches += 2;

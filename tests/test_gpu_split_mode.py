@@ -134,3 +134,34 @@ def test_results_do_not_depend_on_how_a_batch_is_cut(jr, gpu_ctx_factory):
     alone = run_cuda(ctx, ctl, tbl, [pkgs[2]], 1)[0]
     assert ctx.stats()["ega_gas_blocks"] == 30
     _same_bits(alone, batch[2], "30 gases: alone vs in a batch")
+
+
+def test_cooperative_tracer_is_bit_identical_to_thread_per_ray(jr, gpu_ctx_factory):
+    """small batches walk a ray with a group of 8 lanes (the five (p,T) evaluations of a step side by side); same expressions,
+    same bits: radiances, tangent points and every line-of-sight record; limb with refraction, observer inside the
+    atmosphere, rejected rays, nadir (ground hit), refraction off"""
+    ctx = gpu_ctx_factory()
+    cases = []
+    ctl = jr.synth.control_config_d()
+    pkg = jr.synth.limb_package(ctl, n_profiles=3, rays_per_profile=21, dz=3.1, seed=31)
+    pkg.obsz[3] = 40.0; pkg.vpz[3] = 10.0; pkg.vplat[3] = 3.0     # observer inside the atmosphere
+    pkg.obsz[4] = -1.0                                             # rejected
+    pkg.vpz[5] = 95.0                                              # view point above the atmosphere
+    pkg.vpz[6] = -50.0; pkg.vplat[6] = 1.0                         # ground hit
+    cases.append((ctl, pkg))
+    ctl_e = jr.synth.control_config_e()
+    cases.append((ctl_e, jr.synth.nadir_package(ctl_e, n_profiles=2, rays_per_profile=9, dlat=0.9, seed=32)))
+    ctl_n = jr.Control(["CO2", "H2O"], [792.0, 832.0], refrac=0, rayds=5.0, raydz=1.0)
+    cases.append((ctl_n, jr.synth.limb_package(ctl_n, n_profiles=1, rays_per_profile=10, dz=6.0, seed=33)))
+    for ctl, pkg in cases:
+        tbl = jr.synth.make_tables(ctl)
+        coop = run_cuda(ctx, ctl, tbl, [pkg], 1)[0]
+        los_c = [ctx.debug_los(r) for r in range(pkg.n_rays)]
+        with env(JRB_NO_COOP_TRACER=1):
+            plain = run_cuda(ctx, ctl, tbl, [pkg], 1)[0]
+            los_p = [ctx.debug_los(r) for r in range(pkg.n_rays)]
+        _same_bits(coop, plain, "cooperative tracer")
+        for name in ("tpz", "tplon", "tplat"):
+            assert np.array_equal(getattr(coop, name), getattr(plain, name)), name
+        for (a, ta), (b, tb) in zip(los_c, los_p):
+            assert a.shape == b.shape and np.array_equal(a, b) and ta == tb
