@@ -164,4 +164,4 @@ def test_cooperative_tracer_is_bit_identical_to_thread_per_ray(jr, gpu_ctx_facto
         for name in ("tpz", "tplon", "tplat"):
             assert np.array_equal(getattr(coop, name), getattr(plain, name)), name
         for (a, ta), (b, tb) in zip(los_c, los_p):
-            assert a.shape == b.shape and np.array_equal(a, b) and ta == tb
+            assert a.shape == b.shape and np.array_equal(a, b, equal_nan=True) and ta == tb  # (a record may hold an unwritten padding word)

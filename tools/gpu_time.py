@@ -7,7 +7,7 @@ jr = importlib.import_module("jurassic-gpu_b200")
 synth = jr.synth
 
 def timing(name, ctl, tbl, pkgs, reps=3):
-    ctx = jr.Context(0); ctx.set_control(ctl); ctx.set_tables(tbl); ctx.set_kernel_variant(1)
+    ctx = jr.Context(0); ctx.set_control(ctl); ctx.set_tables(tbl); ctx.set_kernel_variant(0 if os.environ.get('GENERIC', '0') == '1' else 1)
     if os.environ.get("FOV", "0") == "1":  # field-of-view epilogue with the 13-point test shape
         import numpy as np
         shape = np.loadtxt(os.path.join(ROOT, "tests", "golden", "fov_shape.tab"))
@@ -22,8 +22,8 @@ def timing(name, ctl, tbl, pkgs, reps=3):
           f"-> total {rc/best['ms_total_device']/1e3:.2f} M/s, ega-only {rc/best['ms_ega']/1e3:.2f} M/s", flush=True)
     ctx.close()
 
-ctl = synth.control_config_d(); tbl = synth.make_tables(ctl)
-timing("D", ctl, tbl, [synth.limb_package(ctl, seed=20240517 + i) for i in range(int(os.environ.get("NPK", "32")))])
+ctl = synth.control_config_d(); tbl = synth.make_tables(ctl, axis_jitter=os.environ.get("JITTER", "0") == "1")
+timing("D" + (" jitter" if os.environ.get("JITTER", "0") == "1" else ""), ctl, tbl, [synth.limb_package(ctl, seed=20240517 + i) for i in range(int(os.environ.get("NPK", "32")))])
 if os.environ.get("WITH_E", "1") == "1":
     ctl = synth.control_config_e(); tbl = synth.make_tables(ctl)
     timing("E", ctl, tbl, [synth.nadir_package(ctl, seed=20240518 + i) for i in range(int(os.environ.get("NPK_E", "8")))])
@@ -45,3 +45,12 @@ if os.environ.get("WITH_A", "0") == "1":
     ctl = synth.control_limb_example(); tbl = synth.make_tables(ctl)
     timing("A-like nd=2", ctl, tbl, [synth.limb_package(ctl, seed=20240517 + i) for i in range(32)])
 
+if os.environ.get("WITH_R", "0") == "1":  # refspec shape at full width: 30 gases x 100 channels, 66-ray packages
+    gases = ["CO2", "H2O", "O3", "N2O", "CH4", "CO", "HNO3", "SO2", "F11", "CCl4"] + [f"X{i}" for i in range(20)]
+    ctl = jr.Control(gases, 2150.0 + synth.np.arange(100)); tbl = synth.make_tables(ctl)
+    pk = [synth.limb_package(ctl, n_profiles=1, rays_per_profile=66, z0=3.0, dz=1.0, seed=20240517 + i) for i in range(int(os.environ.get("NPK_R", "64")))]
+    for p in pk:
+        for ig in range(10, 30): p.q[ig, :] = p.q[ig % 10, :] * (0.2 + 0.05 * ig)
+    timing("refspec 30 gases x 100 channels", ctl, tbl, pk)
+    os.environ["JRB_NO_SPLIT"] = "1"
+    timing("refspec 30 gases x 100 channels, fused", ctl, tbl, pk)
