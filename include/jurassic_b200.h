@@ -105,6 +105,7 @@ typedef struct {
   long long cum_runs, cum_launches, cum_ega_launches;
   double cum_ms_ega, cum_ms_raytrace, cum_ms_device;
   int ega_per_channel_axes; /* 1: the (p,T) axes of the tables depend on the channel; the specialised kernel located the cells per lane */
+  int ega_tiled;           /* 1: the segment-tiled form of the specialised kernel ran (large batches) */
   int ega_gas_blocks;      /* > 1: split mode -- gas-block passes + combine kernel (many gases, or a batch too small to fill the GPU) */
 } jrb_stats;
 

@@ -93,7 +93,7 @@ class Stats(C.Structure):
                 ("n_chunks", C.c_int), ("pipelined", C.c_int), ("ega_phase_lock", C.c_int), ("ega_channels_per_warp", C.c_int),
                 ("io_direct", C.c_int), ("host_ms_stage", C.c_float), ("cum_runs", C.c_longlong), ("cum_launches", C.c_longlong),
                 ("cum_ega_launches", C.c_longlong), ("cum_ms_ega", C.c_double), ("cum_ms_raytrace", C.c_double),
-                ("cum_ms_device", C.c_double), ("ega_per_channel_axes", C.c_int), ("ega_gas_blocks", C.c_int)]
+                ("cum_ms_device", C.c_double), ("ega_per_channel_axes", C.c_int), ("ega_tiled", C.c_int), ("ega_gas_blocks", C.c_int)]
 
 
 class GroupStats(C.Structure):

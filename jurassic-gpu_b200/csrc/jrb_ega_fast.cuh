@@ -129,10 +129,11 @@ __device__ __forceinline__ void relocate(const float4 *__restrict__ brk, const u
 // The four table columns of an EGA step, starting from the prefetched brackets (k, b): per column u* = u(eps) (get_u, may
 // extrapolate), then eps(u* + u_seg) clamped to [0,1] (get_eps + c01, src/jr_common.h:249-257).  Written stage by stage
 // over the four columns so that their independent FP64 chains interleave (D -0.5 %, E -1.7 % against column after column).
+// (k, b) are updated in place: on return b is the bracket at k, where the column-density lookup ended.
 __device__ __forceinline__ void column_finish4(const float4 *__restrict__ brk, const unsigned f0, const unsigned f1, const unsigned f2,
                                                const unsigned f3, const int n0, const int n1, const int n2, const int n3, const double eps,
-                                               const float epsd, const double useg, int &k0, int &k1, int &k2, int &k3, float4 b0, float4 b1,
-                                               float4 b2, float4 b3, double &r0, double &r1, double &r2, double &r3) {
+                                               const float epsd, const double useg, int &k0, int &k1, int &k2, int &k3, float4 &b0, float4 &b1,
+                                               float4 &b2, float4 &b3, double &r0, double &r1, double &r2, double &r3) {
   relocate<true>(brk, f0, n0, epsd, k0, b0);
   relocate<true>(brk, f1, n1, epsd, k1, b1);
   relocate<true>(brk, f2, n2, epsd, k2, b2);
@@ -516,8 +517,8 @@ __global__ void __launch_bounds__(kEgaBlock, JRB_EGA_MINBLOCKS) ega_fast_kernel(
             double e00, e01, e10, e11;
             if (!ROBUST || !unsorted) {
               // the four hinted brackets are requested back to back: their latencies overlap
-              const float4 b00 = brk[c00.x + (unsigned)k00], b01 = brk[c01.x + (unsigned)k01], b10 = brk[c10.x + (unsigned)k10],
-                           b11 = brk[c11.x + (unsigned)k11];
+              float4 b00 = brk[c00.x + (unsigned)k00], b01 = brk[c01.x + (unsigned)k01], b10 = brk[c10.x + (unsigned)k10],
+                     b11 = brk[c11.x + (unsigned)k11];
               const float epsd = fast::round_down(eps);
               fast::column_finish4(brk, c00.x, c01.x, c10.x, c11.x, (int)n00u, (int)n01u, (int)n10u, (int)n11u, eps, epsd, useg, k00, k01, k10, k11,
                                    b00, b01, b10, b11, e00, e01, e10, e11);
@@ -665,5 +666,7 @@ cudaError_t launch_ega_split(const EgaArgs &a, cudaStream_t stream, int sm_count
 // one translation unit per MASK
 template <int MASK>
 cudaError_t launch_ega_fast_mask(const EgaArgs &a, cudaStream_t stream, int sm_count, int *ngb_out);
+template <int MASK>
+cudaError_t launch_ega_tiled_mask(const EgaArgs &a, cudaStream_t stream, int sm_count); // segment-tiled form (jrb_ega_tiled.cuh)
 
 } // namespace jrb

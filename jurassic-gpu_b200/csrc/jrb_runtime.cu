@@ -962,8 +962,15 @@ static int run_locked(jrb_context *ctx) {
       CU(launch_ega_split_passes(e, st_e));
       CU(launch_ega_combine(e, st_e));
       launches += 2;
-    } else if (ctx->use_fast) CU(launch_ega_fast(e, st_e, &ngb));
-    else CU(launch_ega_generic(e, st_e));
+    } else if (ctx->use_fast) {
+      // segment-tiled form: large batches, one ray x 32 channels per warp, rays of different length (free-running CTAs)
+      bool tiled = false;
+      if (const char *s = getenv("JRB_EGA_TILED")) tiled = atoi(s) != 0;
+      tiled = tiled && e.cpw == 32 && !e.per_channel_axes && e.n_rays * ((nd + 31) / 32) >= 16ll * ctx->sm_count * 24 &&
+              ega_tiled_fits(ng, ctx->los.rec, (size_t)ctx->smem_optin);
+      if (tiled) { CU(launch_ega_tiled(e, st_e)); ctx->stats.ega_tiled = 1; }
+      else { CU(launch_ega_fast(e, st_e, &ngb)); ctx->stats.ega_tiled = 0; }
+    } else CU(launch_ega_generic(e, st_e));
     launches += (ctx->use_fast && e.phase_lock_mode < 0 && e.n_rays > 0) ? 2 : 1; // + chunk_balance_kernel
     CU(cudaEventRecord(EV(c, 3), st_e));
   }

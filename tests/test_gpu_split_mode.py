@@ -165,3 +165,26 @@ def test_cooperative_tracer_is_bit_identical_to_thread_per_ray(jr, gpu_ctx_facto
             assert np.array_equal(getattr(coop, name), getattr(plain, name)), name
         for (a, ta), (b, tb) in zip(los_c, los_p):
             assert a.shape == b.shape and np.array_equal(a, b, equal_nan=True) and ta == tb  # (a record may hold an unwritten padding word)
+
+
+def test_segment_tiled_kernel_is_bit_identical(jr, gpu_ctx_factory):
+    """the segment-tiled form of the specialised kernel (jrb_ega_tiled.cuh: brackets and descriptors stay in registers across
+    the segments of a tile) against the segment-by-segment kernel on a batch large enough to select it: Config D
+    (opaque rays, rays of different length), a table set with missing pairs and unsorted columns, and a NaN-masked entry"""
+    ctx = gpu_ctx_factory()
+    ctl = jr.synth.control_config_d()
+    for kind in ("plain", "holes"):
+        tbl = jr.synth.make_tables(ctl, skip_pairs=[(3, 5), (4, 31), (1, 0)] if kind == "holes" else ())
+        if kind == "holes":  # one column out of order in u: flagged at pack time, evaluated by plain bisection
+            tbl.u[2, 7, 3, 10, 4], tbl.u[2, 7, 3, 11, 4] = tbl.u[2, 7, 3, 11, 4], tbl.u[2, 7, 3, 10, 4]
+        pkgs = [jr.synth.limb_package(ctl, seed=1200 + i) for i in range(56)]  # 60 928 rays >= 16 rounds of 24 warps on 148 SMs
+        pkgs[3].rad[40, 9] = np.nan
+        with env(JRB_EGA_TILED=0):
+            ref = run_cuda(ctx, ctl, tbl, pkgs, 1)
+            assert ctx.stats()["ega_tiled"] == 0
+        with env(JRB_EGA_TILED=1):
+            til = run_cuda(ctx, ctl, tbl, pkgs, 1)
+            assert ctx.stats()["ega_tiled"] == 1
+        for a, b in zip(til, ref):
+            _same_bits(a, b, f"tiled vs segment-by-segment ({kind})")
+        assert min(p.tau.min() for p in ref) < 1e-6
