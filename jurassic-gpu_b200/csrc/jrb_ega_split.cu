@@ -15,10 +15,13 @@ namespace jrb {
 
 namespace {
 
-// Gas-independent part of a segment, fully parallel: thread per (ray, segment, channel) computes what the fused kernel
-// computes once per (segment, channel) -- exp(-beta_ds) of the continua / extinction (continua_core_bbbb) and the band
-// Planck source (src_planck_core) -- into a.seg_pre[ray][segment][channel] = {exp(-beta_ds), src}.  This takes the
-// transcendentals out of the sequential along-ray loop of the combine kernel.
+// Everything of a segment except the along-ray recurrence, fully parallel: thread per (ray, segment, channel).
+//   tau_gas = product of the block products in the canonical order (groups in order, inside a group in gas order; a block
+//             whose gas went opaque at an earlier segment contributes 0)
+//   continua / extinction (continua_core_bbbb), band Planck source (src_planck_core), and the two terms of new_obs_core:
+//   a.seg_pre[ray][segment][channel] = {src * eps, 1 - eps}  with eps = 1 - tau_gas exp(-beta_ds), or {0, 1} where the
+//   reference skips the segment (tau_gas <= 1e-50, src/jr_common.h:295).
+// This takes all loads of block products and all transcendentals out of the sequential loop of the combine kernel.
 __global__ void __launch_bounds__(256) ega_segment_kernel(const EgaArgs a) {
   const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   const int nd = a.nd;
@@ -27,46 +30,54 @@ __global__ void __launch_bounds__(256) ega_segment_kernel(const EgaArgs a) {
   const long long ir = seg / kNLOS;
   const int ip = (int)(seg - ir * kNLOS);
   if (ir >= a.n_rays || ip >= a.ray_np[ir]) return;
-  const LosLayout L = a.los;
-  const double *__restrict__ rec = a.los_data + ((size_t)ir * kNLOS + ip) * L.rec;
-  const double p = rec[0], t = rec[1], ds = rec[2];
-  const double u_co2 = (a.ctm_mask & 8) ? rec[L.u0 + a.ig_co2] : 0.0;
-  const double u_h2o = (a.ctm_mask & 4) ? rec[L.u0 + a.ig_h2o] : 0.0;
-  const double beta_ds = continuum_beta_ds(a.ctm_mask, a.chan, nd, id, p, t, ds, a.nw > 0 ? rec[4 + a.window[id]] : 0.0, u_co2, u_h2o, rec[3]);
-  a.seg_pre[idx] = make_double2(exp(-beta_ds), planck_source(a.tbl.sr, nd, id, t));
+  const int nb = a.n_gas_blocks, bpg = max(a.blocks_per_group, 1);
+  const size_t bstride = (size_t)a.n_rays * kNLOS * nd, lstride = (size_t)a.n_rays * nd;
+  const double *__restrict__ part = a.partial + idx;
+  const int *__restrict__ plen = a.partial_len + (size_t)ir * nd + id;
+  double tau_gas = 1.0;
+  for (int b0 = 0; b0 < nb; b0 += bpg) {
+    double pg = 1.0;
+    for (int b = b0; b < min(b0 + bpg, nb); b++) pg *= (ip < plen[(size_t)b * lstride]) ? part[(size_t)b * bstride] : 0.0;
+    tau_gas *= pg;
+  }
+  double2 out = make_double2(0.0, 1.0);
+  if (tau_gas > 1e-50) { // new_obs_core (src/jr_common.h:293-300)
+    const LosLayout L = a.los;
+    const double *__restrict__ rec = a.los_data + ((size_t)ir * kNLOS + ip) * L.rec;
+    const double p = rec[0], t = rec[1], ds = rec[2];
+    const double u_co2 = (a.ctm_mask & 8) ? rec[L.u0 + a.ig_co2] : 0.0;
+    const double u_h2o = (a.ctm_mask & 4) ? rec[L.u0 + a.ig_h2o] : 0.0;
+    const double beta_ds = continuum_beta_ds(a.ctm_mask, a.chan, nd, id, p, t, ds, a.nw > 0 ? rec[4 + a.window[id]] : 0.0, u_co2, u_h2o, rec[3]);
+    const double src = planck_source(a.tbl.sr, nd, id, t);
+    const double eps = 1. - tau_gas * exp(-beta_ds);
+    out = make_double2(src * eps, 1. - eps);
+  }
+  a.seg_pre[idx] = out;
 }
 
-// thread per (ray, channel): tau_gas = product of the block products in gas order, then the radiance update of the fused
-// kernel (new_obs_core) and its per-ray epilogues (add_surface_core, brightness_core).  Nothing in the loop but loads that
-// do not depend on the recurrence (unrolled: several segments in flight) and three multiply-adds.
+// thread per (ray, channel): the recurrence rad += (src eps) tau; tau *= (1 - eps) over the segments (same operations in the
+// same order as the fused kernel), then the per-ray epilogues (add_surface_core, brightness_core).  One 16-byte load per
+// segment that does not depend on the recurrence: unrolled, eight segments in flight.
 __global__ void __launch_bounds__(128) ega_combine_kernel(const EgaArgs a) {
   const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (idx >= a.n_rays * a.nd) return;
   const long long ir = idx / a.nd;
   const int id = (int)(idx - ir * a.nd), nd = a.nd;
   const int np = a.ray_np[ir];
-  const int nb = a.n_gas_blocks, bpg = max(a.blocks_per_group, 1);
-  // segments every block has a product for; beyond it some block's factor is 0 and nothing is accumulated any more
-  int n_live = np;
-  for (int b = 0; b < nb; b++) n_live = min(n_live, a.partial_len[((size_t)b * a.n_rays + ir) * nd + id]);
-  const size_t bstride = (size_t)a.n_rays * kNLOS * nd;
-  const double *__restrict__ part = a.partial + ((size_t)ir * kNLOS) * nd + id;
   const double2 *__restrict__ pre = a.seg_pre + ((size_t)ir * kNLOS) * nd + id;
   double rad = 0.0, tau = 1.0;
-#pragma unroll 4
-  for (int ip = 0; ip < n_live; ++ip) {
-    double tau_gas = 1.0;
-    for (int b0 = 0; b0 < nb; b0 += bpg) { // product groups in order; inside a group a running product in gas order
-      double pg = 1.0;
-      for (int b = b0; b < min(b0 + bpg, nb); b++) pg *= part[(size_t)b * bstride + (size_t)ip * nd];
-      tau_gas *= pg;
-    }
-    const double2 es = pre[(size_t)ip * nd];
-    if (tau_gas > 1e-50) { // new_obs_core (src/jr_common.h:293-300)
-      const double eps = 1. - tau_gas * es.x;
-      rad += es.y * eps * tau;
-      tau *= (1. - eps);
-    }
+  int ip = 0;
+  for (; ip + 8 <= np; ip += 8) {
+    double2 e[8];
+#pragma unroll
+    for (int j = 0; j < 8; j++) e[j] = pre[(size_t)(ip + j) * nd];
+#pragma unroll
+    for (int j = 0; j < 8; j++) { rad += e[j].x * tau; tau *= e[j].y; }
+  }
+  for (; ip < np; ++ip) {
+    const double2 e = pre[(size_t)ip * nd];
+    rad += e.x * tau;
+    tau *= e.y;
   }
   epilogue(rad, tau, a.ray_tsurf[ir], a.tbl.sr, nd, id, a.write_bbt, a.chan[CH_NU * nd + id]);
   a.rad[idx] = rad;

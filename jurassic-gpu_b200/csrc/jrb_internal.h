@@ -67,7 +67,7 @@ struct EgaArgs {
   int blocks_per_group;             // combine: the products of this many consecutive blocks are multiplied first (canonical order)
   double *partial;                  // [n_gas_blocks][n_rays][NLOS][nd] per-segment product of the block's gas factors
   int *partial_len;                 // [n_gas_blocks][n_rays][nd] segments that carry a product (a gas went opaque at len-1 if < np)
-  double2 *seg_pre;                 // [n_rays][NLOS][nd] {exp(-beta_ds), Planck source} per segment and channel (ega_segment_kernel)
+  double2 *seg_pre;                 // [n_rays][NLOS][nd] {src * eps, 1 - eps} per segment and channel (ega_segment_kernel)
 };
 
 struct FovArgs { // optional epilogue: field-of-view convolution (formod_fov, src/jurassic.c:214-258)
@@ -115,7 +115,7 @@ cudaError_t launch_ega_fast(const EgaArgs &a, cudaStream_t stream, int *ngb_out)
 // split mode: gas-block passes of the specialised kernel (a.partial / a.partial_len filled), then the combine kernel that
 // multiplies the block products per segment and does continuum, Planck source, accumulation and the epilogues
 cudaError_t launch_ega_split_passes(const EgaArgs &a, cudaStream_t stream);
-cudaError_t launch_ega_segments(const EgaArgs &a, cudaStream_t stream); // gas-independent part per (segment, channel), fully parallel
+cudaError_t launch_ega_segments(const EgaArgs &a, cudaStream_t stream); // everything but the recurrence, per (segment, channel), fully parallel
 cudaError_t launch_ega_combine(const EgaArgs &a, cudaStream_t stream);
 cudaError_t launch_ega_tiled(const EgaArgs &a, cudaStream_t stream); // segment-tiled form (jrb_ega_tiled.cuh)
 bool ega_tiled_fits(int ng, int los_rec, size_t smem_max);

@@ -958,8 +958,8 @@ static int run_locked(jrb_context *ctx) {
       e.seg_pre = (double2 *)pb; pb += (size_t)e.n_rays * kNLOS * nd * 16;
       e.partial = (double *)pb; pb += (size_t)ctx->n_gas_blocks * (size_t)e.n_rays * kNLOS * nd * 8;
       e.partial_len = (int *)pb;
-      CU(launch_ega_segments(e, st_e));
       CU(launch_ega_split_passes(e, st_e));
+      CU(launch_ega_segments(e, st_e));
       CU(launch_ega_combine(e, st_e));
       launches += 2;
     } else if (ctx->use_fast) {

@@ -180,7 +180,7 @@ def test_gas_dependent_axes_use_per_gas_cells(jr, oracle, gpu_ctx_factory):
 
 
 def test_no_refraction_and_extinction_windows(jr, oracle, gpu_ctx_factory):
-    ctl = jr.Control(["CO2", "H2O"], [792.0, 832.0], refrac=0, rayds=5.0, raydz=1.0)
+    ctl = jr.Control(["CO2", "H2O"], [792.0, 832.0], refrac=0, rayds=8.0, raydz=1.0)  # (rayds 5 would need > 400 points: fatal)
     pkg = jr.synth.limb_package(ctl, n_profiles=1, rays_per_profile=10, dz=6.0, seed=11)
     pkg.k[0, :] = 3e-4 * np.exp(-pkg.z / 6.0)
     _both(gpu_ctx_factory, oracle, ctl, jr.synth.make_tables(ctl), [pkg], "norefrac")
@@ -569,6 +569,6 @@ def test_too_many_los_points_is_an_error(jr, gpu_ctx_factory):
     ctx.set_control(ctl); ctx.set_tables(tbl)
     with pytest.raises(jr.JrbError, match="Too many LOS points"):
         ctx.formod_batch([copy.deepcopy(pkg)])
-    ok = jr.synth.limb_package(ctl, n_profiles=1, rays_per_profile=4, z0=30.0, dz=10.0, seed=1)
+    ok = jr.synth.limb_package(ctl, n_profiles=1, rays_per_profile=4, z0=80.0, dz=2.0, seed=1)  # short paths: ~200 points
     ctx.formod_batch([ok])
     assert np.all(np.isfinite(ok.rad)) and ok.tau.max() <= 1.0

@@ -151,7 +151,7 @@ def test_cooperative_tracer_is_bit_identical_to_thread_per_ray(jr, gpu_ctx_facto
     cases.append((ctl, pkg))
     ctl_e = jr.synth.control_config_e()
     cases.append((ctl_e, jr.synth.nadir_package(ctl_e, n_profiles=2, rays_per_profile=9, dlat=0.9, seed=32)))
-    ctl_n = jr.Control(["CO2", "H2O"], [792.0, 832.0], refrac=0, rayds=5.0, raydz=1.0)
+    ctl_n = jr.Control(["CO2", "H2O"], [792.0, 832.0], refrac=0, rayds=8.0, raydz=1.0)
     cases.append((ctl_n, jr.synth.limb_package(ctl_n, n_profiles=1, rays_per_profile=10, dz=6.0, seed=33)))
     for ctl, pkg in cases:
         tbl = jr.synth.make_tables(ctl)
