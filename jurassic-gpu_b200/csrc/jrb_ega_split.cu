@@ -10,6 +10,8 @@
 // The price is the scratch traffic of the block products: 8 B per (block, segment, channel) written and read once, against
 // 176 B of table gathers per (gas, segment, channel).
 #include "jrb_ega_fast.cuh"
+#include "jrb_ega_tiled.cuh"
+#include <cstdlib>
 
 namespace jrb {
 
@@ -92,6 +94,8 @@ __global__ void __launch_bounds__(128) ega_combine_kernel(const EgaArgs a) {
 
 cudaError_t launch_ega_split(const EgaArgs &a, cudaStream_t stream, int sm_count) {
   const bool multi = a.cpw < 32;
+  if (a.use_tiled && !multi && !a.per_channel_axes) // segment-tiled pass: brackets stay in registers across the segments of a tile
+    return a.unsorted_columns ? launch_ega_tiled_tm<0, true, true>(a, stream, sm_count) : launch_ega_tiled_tm<0, false, true>(a, stream, sm_count);
   if (a.per_channel_axes)
     return multi ? launch_ega_fast_tm<0, true, true, true, true>(a, stream, sm_count) : launch_ega_fast_tm<0, false, true, true, true>(a, stream, sm_count);
   if (a.unsorted_columns)

@@ -14,7 +14,8 @@
 //       for segment of the tile:  continuum, Planck source, radiance update with prod[segment]
 //
 // The product of the gas factors of a segment is formed in gas order, the segments are accumulated in order: results are
-// bit-identical to ega_fast_kernel.  Used for large batches of rays with at most 12 gases and >= 32-channel groups.
+// bit-identical to ega_fast_kernel.  Used whenever a warp handles one ray x 32 channels and the (p,T) axes are shared by the
+// channels; also as the gas-block pass of the split mode (SPLIT).
 #pragma once
 #include "jrb_ega_fast.cuh"
 
@@ -33,7 +34,9 @@ __host__ __device__ inline size_t ega_tiled_smem_bytes(int ng, int rec, int thre
          + (size_t)kEgaTile * threads * 8;           // per-segment products of the gas factors
 }
 
-template <int MASK, bool ROBUST>
+// SPLIT = true: gas-block pass of the split mode (see ega_fast_kernel): an item is (gas block, channel group, ray), the
+// products of the block's factors go to a.partial instead of into the radiance update (MASK plays no role then).
+template <int MASK, bool ROBUST, bool SPLIT = false>
 __global__ void __launch_bounds__(kEgaBlock, JRB_EGA_MINBLOCKS) ega_tiled_kernel(const EgaArgs a) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   constexpr int T = kEgaTile;
@@ -41,14 +44,15 @@ __global__ void __launch_bounds__(kEgaBlock, JRB_EGA_MINBLOCKS) ega_tiled_kernel
   const LosLayout L = a.los;
   const TblDev &Tb = a.tbl;
   const int nd = a.nd, ng = a.ng;
+  const int ngs = SPLIT ? a.gases_per_block : ng; // gases whose state a thread holds
   const int sstride = blockDim.x;
 
   unsigned long long *chunk_state = reinterpret_cast<unsigned long long *>(smem_raw);
   unsigned long long *bars = reinterpret_cast<unsigned long long *>(smem_raw + 16) + warp * 2;
   double *recbuf = reinterpret_cast<double *>(smem_raw + 16 + (size_t)nwarps * 16) + (size_t)warp * 2 * T * L.rec;
   double *tau_s = reinterpret_cast<double *>(smem_raw + 16 + (size_t)nwarps * 16 + (size_t)nwarps * 2 * T * L.rec * 8) + tid;
-  unsigned long long *hint_s = reinterpret_cast<unsigned long long *>(tau_s - tid + (size_t)ng * sstride) + tid;
-  double *prod_s = reinterpret_cast<double *>(hint_s - tid + (size_t)ng * sstride) + tid;
+  unsigned long long *hint_s = reinterpret_cast<unsigned long long *>(tau_s - tid + (size_t)ngs * sstride) + tid;
+  double *prod_s = reinterpret_cast<double *>(hint_s - tid + (size_t)ngs * sstride) + tid;
 
   if (lane == 0) { fast::mbar_init(&bars[0], 1); fast::mbar_init(&bars[1], 1); }
   if (tid == 0) *chunk_state = fast::kChunkEmpty;
@@ -57,13 +61,21 @@ __global__ void __launch_bounds__(kEgaBlock, JRB_EGA_MINBLOCKS) ega_tiled_kernel
   unsigned parity0 = 0, parity1 = 0;
 
   const int ngroups = (nd + 31) / 32;
-  const unsigned long long n_items = (unsigned long long)a.n_rays * ngroups; // channel-group major
+  const unsigned long long n_items_blk = (unsigned long long)a.n_rays * ngroups; // channel-group major
+  const unsigned long long n_items = SPLIT ? n_items_blk * (unsigned long long)a.n_gas_blocks : n_items_blk; // gas-block major
 
   for (;;) {
     unsigned long long item = 0;
     if (lane == 0) item = fast::next_item(chunk_state, a.work_counter, (unsigned)a.work_chunk);
     item = __shfl_sync(0xffffffffu, item, 0);
     if (item >= n_items) break;
+    int g0 = 0, g1 = ng, gblk = 0; // gases of this item
+    if (SPLIT) {
+      gblk = (int)(item / n_items_blk);
+      item -= (unsigned long long)gblk * n_items_blk;
+      g0 = gblk * a.gases_per_block;
+      g1 = min(ng, g0 + a.gases_per_block);
+    }
     const int grp = (int)(item / (unsigned long long)a.n_rays);
     const long long ir = (long long)(item - (unsigned long long)grp * (unsigned long long)a.n_rays);
     const int id_raw = grp * 32 + lane;
@@ -73,12 +85,15 @@ __global__ void __launch_bounds__(kEgaBlock, JRB_EGA_MINBLOCKS) ega_tiled_kernel
     const double *__restrict__ rec_g = a.los_data + (size_t)ir * kNLOS * L.rec;
     const int np = a.ray_np[ir];
     const int win = a.window[id];
-    for (int ig = 0; ig < ng; ig++) {
-      tau_s[ig * sstride] = 1.0;
-      hint_s[ig * sstride] = (Tb.np[ig * nd + id] >= 2) ? 0ull : ~0ull; // no table: factor 1 (src/jr_common.h:240)
+    for (int ig = g0; ig < g1; ig++) {
+      tau_s[(ig - g0) * sstride] = 1.0;
+      hint_s[(ig - g0) * sstride] = (Tb.np[ig * nd + id] >= 2) ? 0ull : ~0ull; // no table: factor 1 (src/jr_common.h:240)
     }
     double rad = 0.0, tau = 1.0;
     bool dead = false; // a gas went opaque: the remaining segments change nothing (src/jr_common.h:239,295)
+    int n_done = 0;    // SPLIT: segments for which this lane stored a block product
+    double *__restrict__ part = nullptr;
+    if (SPLIT) part = a.partial + (((size_t)gblk * (size_t)a.n_rays + (size_t)ir) * kNLOS) * (size_t)nd + id;
     const int ntiles = (np + T - 1) / T;
 
     __syncwarp();
@@ -106,10 +121,10 @@ __global__ void __launch_bounds__(kEgaBlock, JRB_EGA_MINBLOCKS) ega_tiled_kernel
       bool any_opaque = false;
 
 #pragma unroll 1
-      for (int ig = 0; ig < ng; ig++) {
-        unsigned long long h = hint_s[ig * sstride];
+      for (int ig = g0; ig < g1; ig++) {
+        unsigned long long h = hint_s[(ig - g0) * sstride];
         if (h == ~0ull) continue; // this (gas, channel) pair has no table: factor 1 in every segment
-        double tp = tau_s[ig * sstride];
+        double tp = tau_s[(ig - g0) * sstride];
         unsigned ccell = (unsigned)(h >> 40);      // cell the bracket indices in h belong to
         bool loaded = false;                       // descriptors / brackets in registers are valid for ccell
         uint2 c00 = make_uint2(0, 0), c01 = c00, c10 = c00, c11 = c00;
@@ -176,68 +191,79 @@ __global__ void __launch_bounds__(kEgaBlock, JRB_EGA_MINBLOCKS) ega_tiled_kernel
           }
           prod_s[s * sstride] *= f;
         }
-        tau_s[ig * sstride] = tp;
+        tau_s[(ig - g0) * sstride] = tp;
         if (loaded)
-          hint_s[ig * sstride] = (unsigned long long)k00 | ((unsigned long long)k01 << 10) | ((unsigned long long)k10 << 20) |
+          hint_s[(ig - g0) * sstride] = (unsigned long long)k00 | ((unsigned long long)k01 << 10) | ((unsigned long long)k10 << 20) |
                                  ((unsigned long long)k11 << 30) | ((unsigned long long)ccell << 40);
       }
 
-      // radiance update of the tile (continua_core_bbbb, src_planck_core, new_obs_core)
+      if constexpr (SPLIT) { // the block's products of this tile (exact zeros from the segment on where a gas went opaque)
+        if (lane_on)
+          for (int s = 0; s < nseg; s++) part[(size_t)(ip0 + s) * nd] = prod_s[s * sstride];
+        n_done = ip0 + nseg;
+      } else { // radiance update of the tile (continua_core_bbbb, src_planck_core, new_obs_core)
 #pragma unroll 1
-      for (int s = 0; s < nseg; s++) {
-        const double *__restrict__ R = RT + (size_t)s * L.rec;
-        const double p = R[0], t = R[1], ds = R[2];
-        const double u_co2 = (MASK & 8) ? R[L.u0 + a.ig_co2] : 0.0;
-        const double u_h2o = (MASK & 4) ? R[L.u0 + a.ig_h2o] : 0.0;
-        const double beta_ds = continuum_beta_ds(MASK, a.chan, nd, id, p, t, ds, a.nw > 0 ? R[4 + win] : 0.0, u_co2, u_h2o, R[3]);
-        const double tau_gas = prod_s[s * sstride];
-        const double src = planck_source(Tb.sr, nd, id, t);
-        accumulate(rad, tau, beta_ds, src, tau_gas);
+        for (int s = 0; s < nseg; s++) {
+          const double *__restrict__ R = RT + (size_t)s * L.rec;
+          const double p = R[0], t = R[1], ds = R[2];
+          const double u_co2 = (MASK & 8) ? R[L.u0 + a.ig_co2] : 0.0;
+          const double u_h2o = (MASK & 4) ? R[L.u0 + a.ig_h2o] : 0.0;
+          const double beta_ds = continuum_beta_ds(MASK, a.chan, nd, id, p, t, ds, a.nw > 0 ? R[4 + win] : 0.0, u_co2, u_h2o, R[3]);
+          const double tau_gas = prod_s[s * sstride];
+          const double src = planck_source(Tb.sr, nd, id, t);
+          accumulate(rad, tau, beta_ds, src, tau_gas);
+        }
       }
       // an opaque gas keeps its factor 0: every later product is 0 and nothing is accumulated any more
       if (any_opaque && prod_s[(nseg - 1) * sstride] == 0.0) dead = true;
     }
-    epilogue(rad, tau, a.ray_tsurf[ir], Tb.sr, nd, id, a.write_bbt, a.chan[CH_NU * nd + id]);
-    if (lane_on) {
-      a.rad[(size_t)ir * nd + id] = rad;
-      a.tau[(size_t)ir * nd + id] = tau;
-      if (a.rad_host) {
-        a.rad_host[ir][id] = rad;
-        a.tau_host[ir][id] = tau;
+    if constexpr (SPLIT) {
+      if (lane_on) a.partial_len[((size_t)gblk * (size_t)a.n_rays + (size_t)ir) * nd + id] = n_done;
+    } else {
+      epilogue(rad, tau, a.ray_tsurf[ir], Tb.sr, nd, id, a.write_bbt, a.chan[CH_NU * nd + id]);
+      if (lane_on) {
+        a.rad[(size_t)ir * nd + id] = rad;
+        a.tau[(size_t)ir * nd + id] = tau;
+        if (a.rad_host) {
+          a.rad_host[ir][id] = rad;
+          a.tau_host[ir][id] = tau;
+        }
       }
     }
   }
 }
 
-template <int MASK, bool ROBUST>
+template <int MASK, bool ROBUST, bool SPLIT = false>
 cudaError_t launch_ega_tiled_tm(const EgaArgs &a, cudaStream_t stream, int sm_count) {
+  const int ng_state = SPLIT ? a.gases_per_block : a.ng;
+  const long long n_items = a.n_rays * ((a.nd + 31) / 32) * (SPLIT ? a.n_gas_blocks : 1);
   int dev = 0, smem_max = 0;
   cudaGetDevice(&dev);
   cudaDeviceGetAttribute(&smem_max, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev);
   int block = kEgaBlock;
   if (const char *s = getenv("JRB_EGA_THREADS")) { const int v = atoi(s); if (v >= 32 && v <= kEgaBlock && v % 32 == 0) block = v; } // experiments
-  while (block > 32 && ega_tiled_smem_bytes(a.ng, a.los.rec, block) > (size_t)smem_max) block -= 32;
-  const size_t smem = ega_tiled_smem_bytes(a.ng, a.los.rec, block);
+  else if (n_items < 16ll * sm_count * (kEgaBlock / 32)) block = kEgaSmallBlock; // small batches: finer tail (as in launch_ega_fast_tm)
+  while (block > 32 && ega_tiled_smem_bytes(ng_state, a.los.rec, block) > (size_t)smem_max) block -= 32;
+  const size_t smem = ega_tiled_smem_bytes(ng_state, a.los.rec, block);
   if (smem > (size_t)smem_max) return cudaErrorInvalidConfiguration;
   static std::atomic<unsigned long long> attr_done{0};
   cudaError_t e = cudaSuccess;
   if (!((attr_done.load(std::memory_order_acquire) >> (dev & 63)) & 1ull)) {
-    e = cudaFuncSetAttribute(ega_tiled_kernel<MASK, ROBUST>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_max);
+    e = cudaFuncSetAttribute(ega_tiled_kernel<MASK, ROBUST, SPLIT>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_max);
     if (e != cudaSuccess) return e;
     attr_done.fetch_or(1ull << (dev & 63), std::memory_order_release);
   }
   int blocks_per_sm = 0;
-  e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&blocks_per_sm, ega_tiled_kernel<MASK, ROBUST>, block, smem);
+  e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&blocks_per_sm, ega_tiled_kernel<MASK, ROBUST, SPLIT>, block, smem);
   if (e != cudaSuccess) return e;
   if (blocks_per_sm < 1) return cudaErrorInvalidConfiguration;
   EgaArgs args = a;
   if (args.work_chunk <= 0) args.work_chunk = block / 32;
-  const long long n_items = a.n_rays * ((a.nd + 31) / 32);
   long long grid = (long long)sm_count * blocks_per_sm;
   const long long need = (n_items + block / 32 - 1) / (block / 32);
   if (grid > need) grid = need;
   if (grid < 1) grid = 1;
-  ega_tiled_kernel<MASK, ROBUST><<<(unsigned)grid, block, smem, stream>>>(args);
+  ega_tiled_kernel<MASK, ROBUST, SPLIT><<<(unsigned)grid, block, smem, stream>>>(args);
   return cudaGetLastError();
 }
 

@@ -951,6 +951,12 @@ static int run_locked(jrb_context *ctx) {
     if (const char *s = getenv("JRB_EGA_CHUNK")) { const int v = atoi(s); if (v >= 1 && v <= 200) e.work_chunk = v; } // experiments
     if (pipe) CU(cudaStreamWaitEvent(st_e, EV(c, 1), 0));
     CU(cudaEventRecord(EV(c, 2), st_e));
+    // segment-tiled form (jrb_ega_tiled.cuh): a warp handles one ray x 32 channels, shared (p,T) axes, free-running CTAs
+    // (chunks of equally long rays -- nadir swaths -- keep the lock-step kernel, whose warps share brackets through L1)
+    e.use_tiled = 1;
+    if (const char *s = getenv("JRB_EGA_TILED")) e.use_tiled = atoi(s) != 0;
+    e.use_tiled = e.use_tiled && ctx->use_fast && e.cpw == 32 && !e.per_channel_axes &&
+                  ega_tiled_fits(ctx->n_gas_blocks > 1 ? ctx->gases_per_block : ng, ctx->los.rec, (size_t)ctx->smem_optin);
     e.n_gas_blocks = ctx->n_gas_blocks; e.gases_per_block = ctx->gases_per_block; e.blocks_per_group = ctx->blocks_per_group;
     e.partial = nullptr; e.partial_len = nullptr; e.seg_pre = nullptr;
     if (ctx->use_fast && ctx->n_gas_blocks > 1) { // split mode: gas-block passes, then the combine kernel
@@ -959,16 +965,12 @@ static int run_locked(jrb_context *ctx) {
       e.partial = (double *)pb; pb += (size_t)ctx->n_gas_blocks * (size_t)e.n_rays * kNLOS * nd * 8;
       e.partial_len = (int *)pb;
       CU(launch_ega_split_passes(e, st_e));
+      ctx->stats.ega_tiled = e.use_tiled;
       CU(launch_ega_segments(e, st_e));
       CU(launch_ega_combine(e, st_e));
       launches += 2;
     } else if (ctx->use_fast) {
-      // segment-tiled form: large batches, one ray x 32 channels per warp, rays of different length (free-running CTAs)
-      bool tiled = false;
-      if (const char *s = getenv("JRB_EGA_TILED")) tiled = atoi(s) != 0;
-      tiled = tiled && e.cpw == 32 && !e.per_channel_axes && e.n_rays * ((nd + 31) / 32) >= 16ll * ctx->sm_count * 24 &&
-              ega_tiled_fits(ng, ctx->los.rec, (size_t)ctx->smem_optin);
-      if (tiled) { CU(launch_ega_tiled(e, st_e)); ctx->stats.ega_tiled = 1; }
+      if (e.use_tiled) { CU(launch_ega_tiled(e, st_e)); ctx->stats.ega_tiled = 1; }
       else { CU(launch_ega_fast(e, st_e, &ngb)); ctx->stats.ega_tiled = 0; }
     } else CU(launch_ega_generic(e, st_e));
     launches += (ctx->use_fast && e.phase_lock_mode < 0 && e.n_rays > 0) ? 2 : 1; // + chunk_balance_kernel

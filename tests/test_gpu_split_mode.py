@@ -188,3 +188,21 @@ def test_segment_tiled_kernel_is_bit_identical(jr, gpu_ctx_factory):
         for a, b in zip(til, ref):
             _same_bits(a, b, f"tiled vs segment-by-segment ({kind})")
         assert min(p.tau.min() for p in ref) < 1e-6
+
+
+def test_tiled_gas_block_pass_is_bit_identical(jr, gpu_ctx_factory):
+    """latency mode with the segment-tiled pass kernel (default) against the segment-by-segment pass kernel and the fused one"""
+    ctl = jr.synth.control_config_d()
+    tbl = jr.synth.make_tables(ctl, skip_pairs=[(2, 3)])
+    pkg = jr.synth.limb_package(ctl, seed=77)
+    ctx = gpu_ctx_factory()
+    tiled = run_cuda(ctx, ctl, tbl, [pkg], 1)[0]
+    st = ctx.stats()
+    assert st["ega_gas_blocks"] == 5 and st["ega_tiled"] == 1
+    with env(JRB_EGA_TILED=0):
+        plain = run_cuda(ctx, ctl, tbl, [pkg], 1)[0]
+        assert ctx.stats()["ega_tiled"] == 0
+    with env(JRB_NO_SPLIT=1, JRB_EGA_TILED=0):
+        fused = run_cuda(ctx, ctl, tbl, [pkg], 1)[0]
+    _same_bits(tiled, plain, "tiled pass vs plain pass")
+    _same_bits(tiled, fused, "tiled pass vs fused")
