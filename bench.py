@@ -433,8 +433,13 @@ def run_workload(args, jr, D, workload, steps, warmup, cpu_seconds, with_gather_
     ega = st["cum_ms_ega"] / n_launch                       # average duration of one launch
     rc_per_launch = my_rc * st["cum_runs"] / n_launch       # ray-channels one launch processes
     achieved = rc_per_launch * bytes_rc / (ega / 1e3) / 1e9
-    kernel = (f"ega_fast_kernel<mask={st['ega_ctm_mask']}> ({st['ega_ngb']} gases, {st['ega_channels_per_warp']} channels per warp, "
-              f"{'lock-step' if st['ega_phase_lock'] else 'free-running'} CTAs)") if st["ega_kernel_variant"] else "ega_generic_kernel"
+    if not st["ega_kernel_variant"]:
+        kernel = "ega_generic_kernel"
+    elif st["ega_tiled"]:
+        kernel = f"ega_tiled_kernel<mask={st['ega_ctm_mask']}> ({st['ega_ngb']} gases, 32 channels per warp, tiles of 8 segments, free-running CTAs)"
+    else:
+        kernel = (f"ega_fast_kernel<mask={st['ega_ctm_mask']}> ({st['ega_ngb']} gases, {st['ega_channels_per_warp']} channels per warp, "
+                  f"{'lock-step' if st['ega_phase_lock'] else 'free-running'} CTAs)")
     traffic, traffic_src, secondary = load_traffic(workload, count // max(st["n_chunks"], 1), kernel)
     roofline = {"bound": "hbm", "kernel": kernel, "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                 "traffic": traffic, "traffic_source": traffic_src, "secondary": secondary,
@@ -534,7 +539,33 @@ def run_workload(args, jr, D, workload, steps, warmup, cpu_seconds, with_gather_
                 parity["ok"] = bool(parity["ok"] and same)
             del priv
 
-    out = {"value": value, "ms_per_step": ms_per_step, "e2e": e2e, "roofline": roofline, "cpu_baseline": cpu, "parity": parity,
+    # ---- the reference's own symbol: formod_GPU(ctl, atm, obs) on ONE package (what every unmodified JURASSIC caller does,
+    # src/formod.c:65,100): latency mode of the library (one-gas passes + cooperative tracer), bit-identical to the batch ----
+    single = None
+    if rank == 0 and workload == "d":
+        lib.formod_GPU.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p]
+        lib.formod_GPU.restype = None
+        o1 = obs_t()
+        C.memmove(C.addressof(o1), C.addressof(obss[0]), C.sizeof(obs_t))
+        a1p, o1p = (C.c_void_p * 1)(C.addressof(atms[0])), (C.c_void_p * 1)(C.addressof(o1))
+        lib.jr_b200_pin_packages(a1p, o1p, 1)
+        for _ in range(3):
+            lib.formod_GPU(C.addressof(c), C.addressof(atms[0]), C.addressof(o1))
+        t0 = time.perf_counter()
+        for _ in range(20):
+            lib.formod_GPU(C.addressof(c), C.addressof(atms[0]), C.addressof(o1))
+        wall = (time.perf_counter() - t0) / 20 * 1e3
+        s1 = ctx.stats()
+        same = bool(np.array_equal(np.ctypeslib.as_array(o1.rad), np.ctypeslib.as_array(obss[0].rad), equal_nan=True) and
+                    np.array_equal(np.ctypeslib.as_array(o1.tau), np.ctypeslib.as_array(obss[0].tau)))
+        single = {"what": "formod_GPU(ctl_t*, atm_t*, obs_t*) on one package: 1088 rays x %d channels x %d gases" % (ctl.nd, ctl.ng),
+                  "ms_wall_per_call": wall, "ms_device": s1["ms_total_device"], "ms_raytrace": s1["ms_raytrace"], "ms_ega": s1["ms_ega"],
+                  "gas_blocks": s1["ega_gas_blocks"], "ray_channels_per_s": 1088 * ctl.nd / (wall / 1e3),
+                  "bit_identical_to_batch": same}
+        if not same:
+            raise SystemExit("bench: formod_GPU on one package differs from the same package inside the batch")
+
+    out = {"value": value, "ms_per_step": ms_per_step, "e2e": e2e, "roofline": roofline, "cpu_baseline": cpu, "parity": parity, "single_package": single,
            "gpu_launches": launches, "clocks": clocks, "config": cfg, "gather": gather,
            "tables": {"seconds_incl_generation": t_tables, "blob_bytes": int(st["table_blob_bytes"]), "nccl_nranks": int(gst.nccl_nranks)},
            "rays_per_gpu": int(my_rays), "los_chunks_per_step": int(st["n_chunks"])}
@@ -606,7 +637,7 @@ def main():
                "ms_per_step": res["ms_per_step"], "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f64",
                "data": "synthetic", "config": res["config"], "clocks": res["clocks"], "e2e": res["e2e"], "gpu_launches": res["gpu_launches"],
                "roofline": res["roofline"], "cpu_baseline": res["cpu_baseline"], "parity": res["parity"],
-               "extra": dict(extra, gather=res["gather"], tables=res["tables"], rays_per_gpu=res["rays_per_gpu"],
+               "extra": dict(extra, single_package=res["single_package"], gather=res["gather"], tables=res["tables"], rays_per_gpu=res["rays_per_gpu"],
                              los_chunks_per_step=res["los_chunks_per_step"])}
         if out["cpu_baseline"] is not None and res["parity"] is not None:
             out["cpu_baseline"]["parity"] = res["parity"]

@@ -59,6 +59,8 @@ __global__ void __launch_bounds__(kEgaBlock, JRB_EGA_MINBLOCKS) ega_tiled_kernel
   asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   __syncthreads();
   unsigned parity0 = 0, parity1 = 0;
+  // lock step (see ega_fast_kernel): the warps of a CTA start their rays together when the rays of a chunk are equally long
+  const bool phase_lock = a.phase_lock_mode == 1 || (a.phase_lock_mode < 0 && a.balance != nullptr && a.balance[0] * 32ull < a.balance[1]);
 
   const int ngroups = (nd + 31) / 32;
   const unsigned long long n_items_blk = (unsigned long long)a.n_rays * ngroups; // channel-group major
@@ -66,9 +68,19 @@ __global__ void __launch_bounds__(kEgaBlock, JRB_EGA_MINBLOCKS) ega_tiled_kernel
 
   for (;;) {
     unsigned long long item = 0;
-    if (lane == 0) item = fast::next_item(chunk_state, a.work_counter, (unsigned)a.work_chunk);
-    item = __shfl_sync(0xffffffffu, item, 0);
-    if (item >= n_items) break;
+    if (phase_lock) {
+      __syncthreads();
+      if (tid == 0) *chunk_state = atomicAdd(a.work_counter, (unsigned long long)nwarps);
+      __syncthreads();
+      const unsigned long long base = *chunk_state;
+      if (base >= n_items) break;
+      item = base + warp;
+      if (item >= n_items) continue;
+    } else {
+      if (lane == 0) item = fast::next_item(chunk_state, a.work_counter, (unsigned)a.work_chunk);
+      item = __shfl_sync(0xffffffffu, item, 0);
+      if (item >= n_items) break;
+    }
     int g0 = 0, g1 = ng, gblk = 0; // gases of this item
     if (SPLIT) {
       gblk = (int)(item / n_items_blk);
@@ -259,6 +271,10 @@ cudaError_t launch_ega_tiled_tm(const EgaArgs &a, cudaStream_t stream, int sm_co
   if (blocks_per_sm < 1) return cudaErrorInvalidConfiguration;
   EgaArgs args = a;
   if (args.work_chunk <= 0) args.work_chunk = block / 32;
+  if (args.phase_lock_mode < 0 && args.balance != nullptr && a.n_rays > 0) { // let the device decide: equal-length chunks -> lock step
+    const long long n_chunks = (n_items + block / 32 - 1) / (block / 32);
+    chunk_balance_kernel<<<(unsigned)((n_chunks + 127) / 128), 128, 0, stream>>>(a.ray_np, a.n_rays, 1, block / 32, args.balance);
+  }
   long long grid = (long long)sm_count * blocks_per_sm;
   const long long need = (n_items + block / 32 - 1) / (block / 32);
   if (grid > need) grid = need;
