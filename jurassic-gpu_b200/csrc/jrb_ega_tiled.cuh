@@ -94,8 +94,20 @@ __global__ void __launch_bounds__(kEgaBlock, JRB_EGA_MINBLOCKS) ega_tiled_kernel
     const bool lane_on = id_raw < nd;
     const int id = lane_on ? id_raw : nd - 1;
 
+    if (a.rays_ready) { // the tracer runs beside this kernel on another stream: wait until this ray's records are final
+      if (lane == 0) {
+        unsigned long long ready;
+        for (unsigned spins = 0;; ++spins) {
+          asm volatile("ld.acquire.gpu.global.u64 %0, [%1];" : "=l"(ready) : "l"(a.rays_ready) : "memory");
+          if (ready > (unsigned long long)ir) break;
+          if (spins > (1u << 22)) { if (a.error_flag) *a.error_flag = 2; break; } // > 4 s: report instead of hanging the device
+          __nanosleep(1000);
+        }
+      }
+      __syncwarp();
+    }
     const double *__restrict__ rec_g = a.los_data + (size_t)ir * kNLOS * L.rec;
-    const int np = a.ray_np[ir];
+    const int np = __ldcg(&a.ray_np[ir]); // (L2: the tracer may have written it while this kernel was running)
     const int win = a.window[id];
     for (int ig = g0; ig < g1; ig++) {
       tau_s[(ig - g0) * sstride] = 1.0;
@@ -232,7 +244,7 @@ __global__ void __launch_bounds__(kEgaBlock, JRB_EGA_MINBLOCKS) ega_tiled_kernel
     if constexpr (SPLIT) {
       if (lane_on) a.partial_len[((size_t)gblk * (size_t)a.n_rays + (size_t)ir) * nd + id] = n_done;
     } else {
-      epilogue(rad, tau, a.ray_tsurf[ir], Tb.sr, nd, id, a.write_bbt, a.chan[CH_NU * nd + id]);
+      epilogue(rad, tau, __ldcg(&a.ray_tsurf[ir]), Tb.sr, nd, id, a.write_bbt, a.chan[CH_NU * nd + id]);
       if (lane_on) {
         a.rad[(size_t)ir * nd + id] = rad;
         a.tau[(size_t)ir * nd + id] = tau;
