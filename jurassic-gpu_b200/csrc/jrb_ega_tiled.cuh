@@ -100,7 +100,8 @@ __global__ void __launch_bounds__(kEgaBlock, JRB_EGA_MINBLOCKS) ega_tiled_kernel
         for (unsigned spins = 0;; ++spins) {
           asm volatile("ld.acquire.gpu.global.u64 %0, [%1];" : "=l"(ready) : "l"(a.rays_ready) : "memory");
           if (ready > (unsigned long long)ir) break;
-          if (spins > (1u << 22)) { if (a.error_flag) *a.error_flag = 2; break; } // > 4 s: report instead of hanging the device
+          // never seen with a tracer that can run beside this kernel; if it cannot, report instead of hanging the device
+          if (spins > (1u << 18) || (a.error_flag && *(volatile int *)a.error_flag == 2)) { if (a.error_flag) *a.error_flag = 2; break; }
           __nanosleep(1000);
         }
       }
@@ -267,6 +268,7 @@ cudaError_t launch_ega_tiled_tm(const EgaArgs &a, cudaStream_t stream, int sm_co
   int block = kEgaBlock;
   if (const char *s = getenv("JRB_EGA_THREADS")) { const int v = atoi(s); if (v >= 32 && v <= kEgaBlock && v % 32 == 0) block = v; } // experiments
   else if (n_items < 16ll * sm_count * (kEgaBlock / 32)) block = kEgaSmallBlock; // small batches: finer tail (as in launch_ega_fast_tm)
+  if (a.block_threads >= 32 && a.block_threads < block) block = a.block_threads / 32 * 32;
   while (block > 32 && ega_tiled_smem_bytes(ng_state, a.los.rec, block) > (size_t)smem_max) block -= 32;
   const size_t smem = ega_tiled_smem_bytes(ng_state, a.los.rec, block);
   if (smem > (size_t)smem_max) return cudaErrorInvalidConfiguration;

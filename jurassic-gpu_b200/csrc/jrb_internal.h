@@ -43,6 +43,7 @@ struct EgaArgs {
   int ig_co2, ig_h2o;
   int write_bbt;
   int unsorted_columns; // the table set has columns flagged kColNonMonotone -> ROBUST kernel instantiation
+  int block_threads;    // 0: the launcher chooses the CTA size; else an upper limit (tracer overlap leaves one sub-partition a warp short)
   int use_tiled;        // segment-tiled form of the specialised kernel (jrb_ega_tiled.cuh) where it applies
   int los_evict_first;  // line-of-sight record copies carry the L2 evict_first hint (they are streamed, the tables are reused)
   int per_channel_axes; // the (p,T) axes depend on the channel -> PERCH instantiation (lanes locate their own table cells)

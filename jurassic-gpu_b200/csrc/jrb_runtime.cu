@@ -922,10 +922,12 @@ static int run_locked(jrb_context *ctx) {
     t.error_flag = ctx->err_flag;
     t.tbl = ctx->tbl->td;
     if (pipe && c >= ctx->nbuf) CU(cudaStreamWaitEvent(st_tr, EV(c - ctx->nbuf, 3), 0)); // LOS buffer free again
-    // Tracer beside the EGA kernel.  For a large batch handled by the free-running tiled kernel the rays are traced in
-    // sub-ranges on a second stream: the EGA kernel starts after the first sub-range and a warp waits at a watermark word
-    // (rays whose records are final) before it starts a ray.  The later sub-ranges run in the registers the persistent EGA
-    // CTAs leave free (one 32-thread tracer CTA per SM: 4096 of 65536 registers), ~3x faster than the EGA kernel consumes rays.
+    // Tracer beside the EGA kernel (JRB_OVERLAP_TRACER=1, off by default -- see profiles/README.md).  For a large batch handled
+    // by the free-running tiled kernel the rays are traced in sub-ranges on a second stream: the EGA kernel starts after the
+    // first sub-range and a warp waits at a watermark word (rays whose records are final) before it starts a ray.  The later
+    // sub-ranges need registers beside the persistent EGA CTAs.  Registers are per sub-partition (16384 each): a 24-warp CTA
+    // of 80 registers leaves 1024 in each, which no tracer warp (104 x 32) fits -- with that shape the tracer never runs and
+    // the kernel waits forever.  The EGA CTA therefore gets 23 warps in this mode: one sub-partition keeps 3584 registers free.
     const long long sub_rays = 8192; // multiple of 32: a cache line of per-ray data belongs to one sub-range
     // segment-tiled form (jrb_ega_tiled.cuh): a warp handles one ray x 32 channels, shared (p,T) axes
     int use_tiled = 1;
@@ -933,11 +935,12 @@ static int run_locked(jrb_context *ctx) {
     use_tiled = use_tiled && ctx->use_fast && ctx->cpw == 32 && th.all_shared &&
                 ega_tiled_fits(ctx->n_gas_blocks > 1 ? ctx->gases_per_block : ng, ctx->los.rec, (size_t)ctx->smem_optin);
     bool overlap = use_tiled && ctx->n_gas_blocks == 1 && !pipe && !fov && (r1 - r0) >= 4 * sub_rays; // (only the tiled kernel waits at the watermark)
-    if (const char *s = getenv("JRB_OVERLAP_TRACER")) overlap = overlap && atoi(s) != 0;
     {
+      const char *s = getenv("JRB_OVERLAP_TRACER");
+      overlap = overlap && s && atoi(s) != 0;
       int regs_sm = 0;
       cudaDeviceGetAttribute(&regs_sm, cudaDevAttrMaxRegistersPerMultiprocessor, ctx->device);
-      if (regs_sm - 768 * 80 < 104 * 32 + 255) overlap = false; // the tracer CTA must fit beside the persistent EGA CTA
+      if (regs_sm / 4 - 5 * 80 * 32 < 104 * 32) overlap = false; // a tracer warp must fit the sub-partition that holds 5 EGA warps
     }
     unsigned long long *watermark = (unsigned long long *)ctx->d_counter.p + 4 * c + 3;
     CU(cudaEventRecord(EV(c, 0), st_tr));
@@ -998,6 +1001,7 @@ static int run_locked(jrb_context *ctx) {
     CU(cudaEventRecord(EV(c, 2), st_e));
     e.use_tiled = use_tiled;
     e.rays_ready = overlap ? watermark : nullptr;
+    e.block_threads = overlap ? 736 : 0;
     e.error_flag = ctx->err_flag;
     if (overlap) e.phase_lock_mode = 0; // ray lengths are not known yet when the kernel starts: free-running CTAs
     e.n_gas_blocks = ctx->n_gas_blocks; e.gases_per_block = ctx->gases_per_block; e.blocks_per_group = ctx->blocks_per_group;

@@ -182,14 +182,14 @@ def test_segment_tiled_kernel_is_bit_identical(jr, gpu_ctx_factory):
         with env(JRB_EGA_TILED=0):
             ref = run_cuda(ctx, ctl, tbl, pkgs, 1)
             assert ctx.stats()["ega_tiled"] == 0
-        with env(JRB_EGA_TILED=1, JRB_OVERLAP_TRACER=0):
+        with env(JRB_EGA_TILED=1):
             til = run_cuda(ctx, ctl, tbl, pkgs, 1)
             st = ctx.stats()
             assert st["ega_tiled"] == 1 and st["pipelined"] == 0
         for a, b in zip(til, ref):
             _same_bits(a, b, f"tiled vs segment-by-segment ({kind})")
-        # default: the tracer runs beside the tiled kernel in sub-ranges behind a watermark (rays are started as they get ready)
-        with env(JRB_EGA_TILED=None, JRB_OVERLAP_TRACER=None):
+        # opt-in: the tracer runs beside the tiled kernel in sub-ranges behind a watermark (rays are started as they get ready)
+        with env(JRB_EGA_TILED=None, JRB_OVERLAP_TRACER=1):
             ovl = run_cuda(ctx, ctl, tbl, pkgs, 1)
             st = ctx.stats()
             assert st["ega_tiled"] == 1 and st["pipelined"] == 2
