@@ -96,8 +96,7 @@ typedef struct {
   int ega_ngb, ega_ctm_mask;                                  /* gases handled by the specialised kernel; continuum mask */
   long long table_blob_bytes;
   float host_ms_pack, host_ms_h2d, host_ms_d2h, host_ms_scatter; /* wall-clock phases of the last stage / fetch */
-  int n_chunks, pipelined; /* LOS chunks of the last run; pipelined: 1 = JRB_PIPELINE chunk pipeline, 2 = the tracer ran beside the EGA
-                              kernel in sub-ranges behind a watermark (large batches; ms_raytrace is then mostly hidden inside ms_ega) */
+  int n_chunks, pipelined; /* LOS chunks of the last run; 1 if the tracer of chunk c+1 ran beside the EGA kernel of chunk c */
   int ega_phase_lock;      /* 1 if the specialised kernel ran its CTAs in lock step (rays of equal length) */
   int ega_channels_per_warp; /* channels of a ray handled by one warp of the specialised kernel (32, or fewer = several rays per warp) */
   int io_direct;           /* 1: inputs were gathered from / results stored into the caller's page-locked structs (jrb_host_register) */

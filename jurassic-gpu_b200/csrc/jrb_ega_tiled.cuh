@@ -94,21 +94,8 @@ __global__ void __launch_bounds__(kEgaBlock, JRB_EGA_MINBLOCKS) ega_tiled_kernel
     const bool lane_on = id_raw < nd;
     const int id = lane_on ? id_raw : nd - 1;
 
-    if (a.rays_ready) { // the tracer runs beside this kernel on another stream: wait until this ray's records are final
-      if (lane == 0) {
-        unsigned long long ready;
-        for (unsigned spins = 0;; ++spins) {
-          asm volatile("ld.acquire.gpu.global.u64 %0, [%1];" : "=l"(ready) : "l"(a.rays_ready) : "memory");
-          if (ready > (unsigned long long)ir) break;
-          // never seen with a tracer that can run beside this kernel; if it cannot, report instead of hanging the device
-          if (spins > (1u << 18) || (a.error_flag && *(volatile int *)a.error_flag == 2)) { if (a.error_flag) *a.error_flag = 2; break; }
-          __nanosleep(1000);
-        }
-      }
-      __syncwarp();
-    }
     const double *__restrict__ rec_g = a.los_data + (size_t)ir * kNLOS * L.rec;
-    const int np = __ldcg(&a.ray_np[ir]); // (L2: the tracer may have written it while this kernel was running)
+    const int np = a.ray_np[ir];
     const int win = a.window[id];
     for (int ig = g0; ig < g1; ig++) {
       tau_s[(ig - g0) * sstride] = 1.0;
@@ -245,7 +232,7 @@ __global__ void __launch_bounds__(kEgaBlock, JRB_EGA_MINBLOCKS) ega_tiled_kernel
     if constexpr (SPLIT) {
       if (lane_on) a.partial_len[((size_t)gblk * (size_t)a.n_rays + (size_t)ir) * nd + id] = n_done;
     } else {
-      epilogue(rad, tau, __ldcg(&a.ray_tsurf[ir]), Tb.sr, nd, id, a.write_bbt, a.chan[CH_NU * nd + id]);
+      epilogue(rad, tau, a.ray_tsurf[ir], Tb.sr, nd, id, a.write_bbt, a.chan[CH_NU * nd + id]);
       if (lane_on) {
         a.rad[(size_t)ir * nd + id] = rad;
         a.tau[(size_t)ir * nd + id] = tau;
@@ -268,7 +255,6 @@ cudaError_t launch_ega_tiled_tm(const EgaArgs &a, cudaStream_t stream, int sm_co
   int block = kEgaBlock;
   if (const char *s = getenv("JRB_EGA_THREADS")) { const int v = atoi(s); if (v >= 32 && v <= kEgaBlock && v % 32 == 0) block = v; } // experiments
   else if (n_items < 16ll * sm_count * (kEgaBlock / 32)) block = kEgaSmallBlock; // small batches: finer tail (as in launch_ega_fast_tm)
-  if (a.block_threads >= 32 && a.block_threads < block) block = a.block_threads / 32 * 32;
   while (block > 32 && ega_tiled_smem_bytes(ng_state, a.los.rec, block) > (size_t)smem_max) block -= 32;
   const size_t smem = ega_tiled_smem_bytes(ng_state, a.los.rec, block);
   if (smem > (size_t)smem_max) return cudaErrorInvalidConfiguration;

@@ -43,7 +43,6 @@ struct EgaArgs {
   int ig_co2, ig_h2o;
   int write_bbt;
   int unsorted_columns; // the table set has columns flagged kColNonMonotone -> ROBUST kernel instantiation
-  int block_threads;    // 0: the launcher chooses the CTA size; else an upper limit (tracer overlap leaves one sub-partition a warp short)
   int use_tiled;        // segment-tiled form of the specialised kernel (jrb_ega_tiled.cuh) where it applies
   int los_evict_first;  // line-of-sight record copies carry the L2 evict_first hint (they are streamed, the tables are reused)
   int per_channel_axes; // the (p,T) axes depend on the channel -> PERCH instantiation (lanes locate their own table cells)
@@ -61,10 +60,6 @@ struct EgaArgs {
   double *const *rad_host, *const *tau_host;
   unsigned long long *work_counter; // dynamic work distribution (zeroed before launch)
   int work_chunk;                   // consecutive items a CTA draws at a time (1..200); 0 = one per warp of the CTA
-  // tracer overlap: number of leading rays of this launch whose line-of-sight records are final (written by a tiny kernel
-  // after every tracer sub-range on another stream); NULL = all rays are ready.  A warp waits here before it starts a ray.
-  const unsigned long long *rays_ready;
-  int *error_flag;                  // host-mapped word (bit 1: a warp gave up waiting at the watermark -- must never happen)
   unsigned long long *balance;      // [2] scratch (zeroed before launch): idle / total segment slots of lock-step execution
   int phase_lock_mode;              // -1 decide on the device from `balance`, 0 never, 1 always
   int cpw;                          // channels of a ray per warp: 32, or less (= several rays per warp, see jrb_ega_fast.cuh)
@@ -115,7 +110,6 @@ cudaError_t launch_nan_mask(double *rad, const long long *flat, long long n, cud
 
 // three launches: level slopes, ray stepping (thread per ray), LOS finalisation (thread per ray x segment)
 cudaError_t launch_raytrace(const TraceArgs &a, cudaStream_t stream, int *launches);
-cudaError_t launch_set_word(unsigned long long *word, unsigned long long value, cudaStream_t stream); // the watermark above
 cudaError_t launch_ega_generic(const EgaArgs &a, cudaStream_t stream);
 // fast path: returns cudaErrorInvalidValue if (ng, ctm_mask) has no instantiation
 cudaError_t launch_ega_fast(const EgaArgs &a, cudaStream_t stream, int *ngb_out);

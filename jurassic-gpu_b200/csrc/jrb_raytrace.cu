@@ -376,15 +376,6 @@ __global__ void __launch_bounds__(256) los_finalize_kernel(TraceArgs a) {
   }
 }
 
-__global__ void set_word_kernel(unsigned long long *word, unsigned long long value) {
-  *word = value;
-  __threadfence();
-}
-cudaError_t launch_set_word(unsigned long long *word, unsigned long long value, cudaStream_t stream) {
-  set_word_kernel<<<1, 1, 0, stream>>>(word, value);
-  return cudaGetLastError();
-}
-
 cudaError_t launch_raytrace(const TraceArgs &a, cudaStream_t stream, int *launches) {
   if (launches) *launches = 0;
   if (a.prepare_atm && a.n_atm > 0) {

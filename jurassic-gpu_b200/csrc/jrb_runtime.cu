@@ -152,8 +152,6 @@ struct jrb_context {
   bool l2_window_set = false;
   DevBuf d_partial;
   std::vector<cudaEvent_t> events;
-  cudaEvent_t ev_trace = nullptr;
-  cudaEvent_t ev_trace_done() { if (!ev_trace) cudaEventCreateWithFlags(&ev_trace, cudaEventDisableTiming); return ev_trace; }
   jrb_stats stats;
   bool np_fetched = false;
 
@@ -221,7 +219,6 @@ void jrb_destroy(jrb_context *ctx) {
   cudaSetDevice(ctx->device);
   cudaStreamSynchronize(ctx->stream);
   for (auto ev : ctx->events) cudaEventDestroy(ev);
-  if (ctx->ev_trace) cudaEventDestroy(ctx->ev_trace);
   ctx->d_chan.release(); ctx->d_window.release(); ctx->tbl.reset();
   ctx->d_in.release(); ctx->d_tab.release(); ctx->d_out.release(); ctx->d_rayout.release(); ctx->d_los.release();
   ctx->d_np.release(); ctx->d_tsurf.release(); ctx->d_counter.release(); ctx->d_slope.release(); ctx->d_level0.release();
@@ -893,7 +890,7 @@ static int run_locked(jrb_context *ctx) {
   auto EV = [&](long long c, int k) { return ctx->events[2 + 4 * (size_t)c + k]; };
   const size_t per_ray = (size_t)kNLOS * ctx->los.rec;
   long long launches = 0;
-  int ngb = ng, n_overlapped = 0;
+  int ngb = ng;
   cudaStream_t st_tr = pipe ? ctx->s_trace : ctx->stream;
   CU(cudaEventRecord(ctx->events[0], ctx->stream));
   if (pipe) CU(cudaStreamWaitEvent(st_tr, ctx->events[0], 0));
@@ -922,56 +919,16 @@ static int run_locked(jrb_context *ctx) {
     t.error_flag = ctx->err_flag;
     t.tbl = ctx->tbl->td;
     if (pipe && c >= ctx->nbuf) CU(cudaStreamWaitEvent(st_tr, EV(c - ctx->nbuf, 3), 0)); // LOS buffer free again
-    // Tracer beside the EGA kernel (JRB_OVERLAP_TRACER=1, off by default -- see profiles/README.md).  For a large batch handled
-    // by the free-running tiled kernel the rays are traced in sub-ranges on a second stream: the EGA kernel starts after the
-    // first sub-range and a warp waits at a watermark word (rays whose records are final) before it starts a ray.  The later
-    // sub-ranges need registers beside the persistent EGA CTAs.  Registers are per sub-partition (16384 each): a 24-warp CTA
-    // of 80 registers leaves 1024 in each, which no tracer warp (104 x 32) fits -- with that shape the tracer never runs and
-    // the kernel waits forever.  The EGA CTA therefore gets 23 warps in this mode: one sub-partition keeps 3584 registers free.
-    const long long sub_rays = 8192; // multiple of 32: a cache line of per-ray data belongs to one sub-range
     // segment-tiled form (jrb_ega_tiled.cuh): a warp handles one ray x 32 channels, shared (p,T) axes
     int use_tiled = 1;
     if (const char *s = getenv("JRB_EGA_TILED")) use_tiled = atoi(s) != 0;
     use_tiled = use_tiled && ctx->use_fast && ctx->cpw == 32 && th.all_shared &&
                 ega_tiled_fits(ctx->n_gas_blocks > 1 ? ctx->gases_per_block : ng, ctx->los.rec, (size_t)ctx->smem_optin);
-    bool overlap = use_tiled && ctx->n_gas_blocks == 1 && !pipe && !fov && (r1 - r0) >= 4 * sub_rays; // (only the tiled kernel waits at the watermark)
-    {
-      const char *s = getenv("JRB_OVERLAP_TRACER");
-      overlap = overlap && s && atoi(s) != 0;
-      int regs_sm = 0;
-      cudaDeviceGetAttribute(&regs_sm, cudaDevAttrMaxRegistersPerMultiprocessor, ctx->device);
-      if (regs_sm / 4 - 5 * 80 * 32 < 104 * 32) overlap = false; // a tracer warp must fit the sub-partition that holds 5 EGA warps
-    }
-    unsigned long long *watermark = (unsigned long long *)ctx->d_counter.p + 4 * c + 3;
     CU(cudaEventRecord(EV(c, 0), st_tr));
     int nl = 0;
-    if (!overlap) {
-      CU(launch_raytrace(t, st_tr, &nl));
-      launches += nl;
-      CU(cudaEventRecord(EV(c, 1), st_tr));
-    } else {
-      // sub-range 0 on the compute stream at full width; the rest on the tracer stream with small CTAs
-      TraceArgs ts = t;
-      ts.n_rays = sub_rays;
-      CU(launch_raytrace(ts, ctx->stream, &nl));
-      launches += nl;
-      CU(launch_set_word(watermark, (unsigned long long)sub_rays, ctx->stream));
-      CU(cudaEventRecord(EV(c, 1), ctx->stream));
-      CU(cudaStreamWaitEvent(ctx->s_trace, EV(c, 1), 0));
-      for (long long q0 = sub_rays; q0 < r1 - r0; q0 += sub_rays) {
-        const long long qn = std::min(sub_rays, (r1 - r0) - q0);
-        ts = t;
-        ts.n_rays = qn; ts.prepare_atm = 0; ts.small_blocks = 1;
-        ts.geo = t.geo + q0; ts.ray_pkg = t.ray_pkg + q0;
-        ts.los_data = t.los_data + (size_t)q0 * per_ray;
-        ts.ray_np = t.ray_np + q0; ts.ray_tsurf = t.ray_tsurf + q0; ts.ray_level0 = t.ray_level0 + q0;
-        ts.tp = t.tp + q0; ts.tp_host = t.tp_host + q0;
-        CU(launch_raytrace(ts, ctx->s_trace, &nl));
-        launches += nl;
-        CU(launch_set_word(watermark, (unsigned long long)(q0 + qn), ctx->s_trace));
-      }
-      CU(cudaEventRecord(ctx->ev_trace_done(), ctx->s_trace));
-    }
+    CU(launch_raytrace(t, st_tr, &nl));
+    launches += nl;
+    CU(cudaEventRecord(EV(c, 1), st_tr));
 
     EgaArgs e;
     e.n_rays = r1 - r0; e.ng = ng; e.nd = nd; e.nw = nw;
@@ -1000,10 +957,6 @@ static int run_locked(jrb_context *ctx) {
     if (pipe) CU(cudaStreamWaitEvent(st_e, EV(c, 1), 0));
     CU(cudaEventRecord(EV(c, 2), st_e));
     e.use_tiled = use_tiled;
-    e.rays_ready = overlap ? watermark : nullptr;
-    e.block_threads = overlap ? 736 : 0;
-    e.error_flag = ctx->err_flag;
-    if (overlap) e.phase_lock_mode = 0; // ray lengths are not known yet when the kernel starts: free-running CTAs
     e.n_gas_blocks = ctx->n_gas_blocks; e.gases_per_block = ctx->gases_per_block; e.blocks_per_group = ctx->blocks_per_group;
     e.partial = nullptr; e.partial_len = nullptr; e.seg_pre = nullptr;
     if (ctx->use_fast && ctx->n_gas_blocks > 1) { // split mode: gas-block passes, then the combine kernel
@@ -1021,7 +974,6 @@ static int run_locked(jrb_context *ctx) {
       else { CU(launch_ega_fast(e, st_e, &ngb)); ctx->stats.ega_tiled = 0; }
     } else CU(launch_ega_generic(e, st_e));
     launches += (ctx->use_fast && e.phase_lock_mode < 0 && e.n_rays > 0) ? 2 : 1; // + chunk_balance_kernel
-    if (overlap) { CU(cudaStreamWaitEvent(st_e, ctx->ev_trace_done(), 0)); n_overlapped++; }
     CU(cudaEventRecord(EV(c, 3), st_e));
   }
   if (pipe) {
@@ -1060,9 +1012,7 @@ static int run_locked(jrb_context *ctx) {
   CU(cudaEventRecord(ctx->events[1], ctx->stream));
   CU(cudaStreamSynchronize(ctx->stream));
   if (ctx->err_flag && *ctx->err_flag) {
-    const int flag = *ctx->err_flag;
     *ctx->err_flag = 0;
-    if (flag & 2) return ctx->fail(JRB_ERR_CUDA, "internal error: the EGA kernel waited in vain for the ray tracer (set JRB_OVERLAP_TRACER=0)");
     return ctx->fail(JRB_ERR_LIMIT, "Too many LOS points!"); // like the reference's CPU path (src/jr_common.h:693-695)
   }
   if (ctx->fov_applied) {
@@ -1097,7 +1047,7 @@ static int run_locked(jrb_context *ctx) {
   ctx->stats.n_kernel_launches = launches;
   ctx->stats.cum_runs++; ctx->stats.cum_launches += launches; ctx->stats.cum_ega_launches += nchunks;
   ctx->stats.cum_ms_ega += ms_ega; ctx->stats.cum_ms_raytrace += ms_rt; ctx->stats.cum_ms_device += ms_tot;
-  ctx->stats.n_chunks = (int)nchunks; ctx->stats.pipelined = pipe ? 1 : (n_overlapped ? 2 : 0);
+  ctx->stats.n_chunks = (int)nchunks; ctx->stats.pipelined = pipe ? 1 : 0;
   ctx->stats.ega_kernel_variant = ctx->use_fast; ctx->stats.ega_ngb = ctx->use_fast ? ngb : 0;
   ctx->stats.ega_ctm_mask = ctx->ctm_mask;
   ctx->stats.ega_gas_blocks = ctx->use_fast ? ctx->n_gas_blocks : 0;

@@ -11,7 +11,7 @@ if [ "${2:-}" != "skip-tests" ]; then
 fi
 python bench.py --steps 5 --warmup 3 > $out/bench_$tag.json 2> $out/bench_$tag.err; echo "bench rc=$?"
 tail -c 3000 $out/bench_$tag.json
-SHORT="python bench.py --steps 2 --warmup 1 --packages 16 --no-e2e --no-cpu-baseline"
+SHORT="python bench.py --steps 2 --warmup 1 --packages 16 --no-cpu-baseline --no-config-e"
 $SHORT > $out/plain_$tag.log 2>&1 &&
 ncu --metrics gpu__time_duration.sum --clock-control none -c 40 --csv --log-file $out/launches_$tag.csv $SHORT > $out/ncu_launches_$tag.log 2>&1
 echo "ncu launches rc=$?"
