@@ -89,7 +89,9 @@ __global__ void __launch_bounds__(kEgaBlock, JRB_EGA_MINBLOCKS) ega_tiled_kernel
       g1 = min(ng, g0 + a.gases_per_block);
     }
     const int grp = (int)(item / (unsigned long long)a.n_rays);
-    const long long ir = (long long)(item - (unsigned long long)grp * (unsigned long long)a.n_rays);
+    long long ir = (long long)(item - (unsigned long long)grp * (unsigned long long)a.n_rays);
+    if (!SPLIT && a.tail_n > 0 && item >= n_items - (unsigned long long)a.tail_n) // the last items: longest ray first
+      ir = a.n_rays - a.tail_n + a.tail_perm[item - (n_items - (unsigned long long)a.tail_n)];
     const int id_raw = grp * 32 + lane;
     const bool lane_on = id_raw < nd;
     const int id = lane_on ? id_raw : nd - 1;
@@ -245,6 +247,22 @@ __global__ void __launch_bounds__(kEgaBlock, JRB_EGA_MINBLOCKS) ega_tiled_kernel
   }
 }
 
+// counting sort of the last n rays of a launch by their number of segments, descending: perm[k] = index (within the tail)
+// of the k-th longest ray.  One CTA; n is a few thousand.
+static __global__ void __launch_bounds__(1024) tail_sort_kernel(const int *__restrict__ np_tail, const int n, int *__restrict__ perm) {
+  __shared__ int bins[kNLOS + 2];
+  for (int i = threadIdx.x; i < kNLOS + 2; i += blockDim.x) bins[i] = 0;
+  __syncthreads();
+  for (int i = threadIdx.x; i < n; i += blockDim.x) atomicAdd(&bins[min(max(np_tail[i], 0), kNLOS)], 1);
+  __syncthreads();
+  if (threadIdx.x == 0) { // start offsets, longest first
+    int acc = 0;
+    for (int b = kNLOS; b >= 0; b--) { const int c = bins[b]; bins[b] = acc; acc += c; }
+  }
+  __syncthreads();
+  for (int i = threadIdx.x; i < n; i += blockDim.x) perm[atomicAdd(&bins[min(max(np_tail[i], 0), kNLOS)], 1)] = i;
+}
+
 template <int MASK, bool ROBUST, bool SPLIT = false>
 cudaError_t launch_ega_tiled_tm(const EgaArgs &a, cudaStream_t stream, int sm_count) {
   const int ng_state = SPLIT ? a.gases_per_block : a.ng;
@@ -279,6 +297,15 @@ cudaError_t launch_ega_tiled_tm(const EgaArgs &a, cudaStream_t stream, int sm_co
   const long long need = (n_items + block / 32 - 1) / (block / 32);
   if (grid > need) grid = need;
   if (grid < 1) grid = 1;
+  // the last two rounds of rays longest first (only worth it when the launch has many rounds)
+  args.tail_n = 0;
+  if (!SPLIT && args.tail_perm && !getenv("JRB_NO_TAIL_SORT")) {
+    const long long tail = 2 * grid * (block / 32);
+    if (tail <= args.tail_cap && a.n_rays >= 4 * tail) {
+      args.tail_n = (int)tail;
+      tail_sort_kernel<<<1, 1024, 0, stream>>>(a.ray_np + (a.n_rays - tail), (int)tail, args.tail_perm);
+    }
+  }
   ega_tiled_kernel<MASK, ROBUST, SPLIT><<<(unsigned)grid, block, smem, stream>>>(args);
   return cudaGetLastError();
 }

@@ -60,6 +60,11 @@ struct EgaArgs {
   double *const *rad_host, *const *tau_host;
   unsigned long long *work_counter; // dynamic work distribution (zeroed before launch)
   int work_chunk;                   // consecutive items a CTA draws at a time (1..200); 0 = one per warp of the CTA
+  // Tail of the work list: the last tail_n items of a launch are handed out longest ray first (tail_perm, built on the device
+  // from ray_np by tail_sort_kernel), so that the kernel ends with its shortest rays -- what a warp still has to do after the
+  // list ran empty is at most one SHORT ray.  tail_cap = capacity of tail_perm; tail_n is set by the launcher (0 = off).
+  int *tail_perm;
+  int tail_cap, tail_n;
   unsigned long long *balance;      // [2] scratch (zeroed before launch): idle / total segment slots of lock-step execution
   int phase_lock_mode;              // -1 decide on the device from `balance`, 0 never, 1 always
   int cpw;                          // channels of a ray per warp: 32, or less (= several rays per warp, see jrb_ega_fast.cuh)

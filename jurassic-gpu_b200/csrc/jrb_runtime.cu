@@ -89,6 +89,7 @@ void *registered_dev_ptr(const void *p, size_t n) {
 
 std::string g_create_error;
 
+constexpr int kTailCap = 16384; // rays of a launch that may be handed out in sorted order (two rounds of warps)
 inline size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
 inline double now_ms() {
   return std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now().time_since_epoch()).count();
@@ -147,10 +148,12 @@ struct jrb_context {
   int use_fast = 0;
   int cpw = 32;
   int n_gas_blocks = 1, gases_per_block = 1, blocks_per_group = 1; // split mode (jrb_ega_split.cu) when n_gas_blocks > 1
+  bool scan_pending = false; // direct mode: the NaN-mask scan of the staged batch is still to be done (before the EGA kernel starts)
+  int npk_staging = 0;
   int *err_flag = nullptr;   // word in the pinned table buffer the tracer reports "too many LOS points" through
   int los_evict_first = 0;   // L2 policy (see apply_l2_policy)
   bool l2_window_set = false;
-  DevBuf d_partial;
+  DevBuf d_partial, d_tail;
   std::vector<cudaEvent_t> events;
   jrb_stats stats;
   bool np_fetched = false;
@@ -222,7 +225,7 @@ void jrb_destroy(jrb_context *ctx) {
   ctx->d_chan.release(); ctx->d_window.release(); ctx->tbl.reset();
   ctx->d_in.release(); ctx->d_tab.release(); ctx->d_out.release(); ctx->d_rayout.release(); ctx->d_los.release();
   ctx->d_np.release(); ctx->d_tsurf.release(); ctx->d_counter.release(); ctx->d_slope.release(); ctx->d_level0.release();
-  ctx->d_raypkg.release(); ctx->d_pkgnp.release(); ctx->d_partial.release();
+  ctx->d_raypkg.release(); ctx->d_pkgnp.release(); ctx->d_partial.release(); ctx->d_tail.release();
   ctx->h_in.release(); ctx->h_out.release(); ctx->h_tab.release();
   ctx->d_fov.release(); ctx->d_fov_out.release(); ctx->d_mask.release(); ctx->d_flag.release();
   cudaStreamDestroy(ctx->stream);
@@ -566,7 +569,21 @@ static void scan_package(const jrb_obs_view &o, long long r0, int nd, bool reset
   }
 }
 
-static int stage_locked(jrb_context *ctx, int npk, const jrb_atm_view *atm, const jrb_obs_view *obs) {
+// direct mode: NaN-mask scan and reset of the columns beyond nd over the staged obs views (touches only the caller's rad/tau
+// rows, which the device does not read and the EGA kernel has not started to write)
+static void scan_staged_obs(jrb_context *ctx) {
+  const int npk = ctx->npk_staging, nd = ctx->nd;
+  const double t0 = now_ms();
+  std::vector<std::vector<std::pair<long long, int>>> masks(npk);
+#pragma omp parallel for schedule(dynamic, 4) num_threads(host_threads())
+  for (int k = 0; k < npk; k++) scan_package(ctx->st_obs[k], ctx->pk_ray_off[k], nd, ctx->st_obs[k].nd_reset > nd, masks[k]);
+  ctx->nan_mask.clear();
+  for (int k = 0; k < npk; k++) ctx->nan_mask.insert(ctx->nan_mask.end(), masks[k].begin(), masks[k].end());
+  ctx->scan_pending = false;
+  ctx->stats.host_ms_pack = (float)(now_ms() - t0);
+}
+
+static int stage_locked(jrb_context *ctx, int npk, const jrb_atm_view *atm, const jrb_obs_view *obs, bool defer_scan = false) {
   ctx->invalidate(); // whatever was staged before is gone, whether or not this call succeeds
   if (!ctx->have_ctl || !ctx->have_tbl()) return ctx->fail(JRB_ERR_STATE, "control and tables must be set before staging");
   CU(cudaSetDevice(ctx->device));
@@ -751,18 +768,21 @@ static int stage_locked(jrb_context *ctx, int npk, const jrb_atm_view *atm, cons
     sa.out = (const OutTab *)(DT + off_out); sa.ray_out = ctx->ray_out;
     CU(launch_stage(sa, ctx->stream));
   }
+  ctx->st_obs.assign(obs, obs + npk);
+  ctx->npk_staging = npk;
+  ctx->scan_pending = false;
+  for (int k = 0; k < npk; k++) ctx->nan_mask.insert(ctx->nan_mask.end(), masks[k].begin(), masks[k].end());
   if (direct) {
-    // the staging kernel is pulling the inputs over PCIe meanwhile: NaN-mask scan and reset of the columns beyond nd
-    // (both touch only the caller's rad/tau rows, which the device does not read)
-#pragma omp parallel for schedule(dynamic, 4) num_threads(host_threads())
-    for (int k = 0; k < npk; k++) scan_package(obs[k], ctx->pk_ray_off[k], nd, obs[k].nd_reset > nd, masks[k]);
+    // the staging kernel is pulling the inputs over PCIe meanwhile.  The NaN-mask scan (and the reset of the columns beyond
+    // nd) only has to be done before the EGA kernel starts to store results: a complete call (jrb_formod_batch) does it
+    // while the ray tracer runs, the split API does it here
+    if (defer_scan) ctx->scan_pending = true;
+    else scan_staged_obs(ctx);
     t_pack1 = now_ms();
     long long in_b = 0;
     for (int k = 0; k < npk; k++) in_b += (long long)obs[k].nr * 8 * 7 + (long long)atm[k].np * 8 * n_af;
     h2d_bytes += (size_t)in_b; // read by the staging kernel from the caller's memory
   }
-  for (int k = 0; k < npk; k++) ctx->nan_mask.insert(ctx->nan_mask.end(), masks[k].begin(), masks[k].end());
-  ctx->st_obs.assign(obs, obs + npk);
 
   // ---- LOS buffer ----
   ctx->use_fast = use_fast;
@@ -814,12 +834,13 @@ static int stage_locked(jrb_context *ctx, int npk, const jrb_atm_view *atm, cons
   {
     const long long nch = R > 0 ? (R + chunk - 1) / chunk : 1;
     CU(ctx->d_counter.ensure((size_t)nch * 32 + 256)); // per LOS chunk: work counter, lock-step balance (idle, total), pad
+    CU(ctx->d_tail.ensure((size_t)nch * kTailCap * 4));  // per LOS chunk: order of the last rays of the launch (longest first)
   }
 
   CU(cudaStreamSynchronize(ctx->stream));
   ctx->npk = npk; ctx->n_rays = R; ctx->n_atm = A;
   ctx->direct = direct;
-  ctx->stats.host_ms_pack = (float)(t_pack1 - t_pack0);
+  if (!direct) ctx->stats.host_ms_pack = (float)(t_pack1 - t_pack0);
   ctx->stats.host_ms_h2d = (float)(now_ms() - t_pack1);
   ctx->stats.host_ms_stage = (float)(now_ms() - t_begin);
   ctx->stats.h2d_bytes = (long long)h2d_bytes;
@@ -929,6 +950,7 @@ static int run_locked(jrb_context *ctx) {
     CU(launch_raytrace(t, st_tr, &nl));
     launches += nl;
     CU(cudaEventRecord(EV(c, 1), st_tr));
+    if (ctx->scan_pending) scan_staged_obs(ctx); // on the host, while the device traces rays
 
     EgaArgs e;
     e.n_rays = r1 - r0; e.ng = ng; e.nd = nd; e.nw = nw;
@@ -957,6 +979,7 @@ static int run_locked(jrb_context *ctx) {
     if (pipe) CU(cudaStreamWaitEvent(st_e, EV(c, 1), 0));
     CU(cudaEventRecord(EV(c, 2), st_e));
     e.use_tiled = use_tiled;
+    e.tail_perm = (int *)ctx->d_tail.p + (size_t)c * kTailCap; e.tail_cap = kTailCap; e.tail_n = 0;
     e.n_gas_blocks = ctx->n_gas_blocks; e.gases_per_block = ctx->gases_per_block; e.blocks_per_group = ctx->blocks_per_group;
     e.partial = nullptr; e.partial_len = nullptr; e.seg_pre = nullptr;
     if (ctx->use_fast && ctx->n_gas_blocks > 1) { // split mode: gas-block passes, then the combine kernel
@@ -976,6 +999,7 @@ static int run_locked(jrb_context *ctx) {
     launches += (ctx->use_fast && e.phase_lock_mode < 0 && e.n_rays > 0) ? 2 : 1; // + chunk_balance_kernel
     CU(cudaEventRecord(EV(c, 3), st_e));
   }
+  if (ctx->scan_pending) scan_staged_obs(ctx); // (a batch without rays)
   if (pipe) {
     CU(cudaStreamWaitEvent(ctx->stream, EV(nchunks - 1, 3), 0));
     if (nchunks > 1) CU(cudaStreamWaitEvent(ctx->stream, EV(nchunks - 2, 3), 0));
@@ -1122,7 +1146,7 @@ int jrb_formod_batch(jrb_context *ctx, int npk, const jrb_atm_view *atm, const j
   if (!ctx || npk < 0 || (npk > 0 && (!atm || !obs))) return JRB_ERR_ARG;
   std::lock_guard<std::mutex> lk(ctx->mtx); // one batch at a time per context; concurrency = several contexts (lanes)
   const double t0 = now_ms();
-  int rc = stage_locked(ctx, npk, atm, obs);
+  int rc = stage_locked(ctx, npk, atm, obs, /*defer_scan=*/true);
   if (rc != JRB_OK) return rc;
   const double t1 = now_ms();
   rc = run_locked(ctx);
