@@ -436,7 +436,8 @@ def run_workload(args, jr, D, workload, steps, warmup, cpu_seconds, with_gather_
     if not st["ega_kernel_variant"]:
         kernel = "ega_generic_kernel"
     elif st["ega_tiled"]:
-        kernel = f"ega_tiled_kernel<mask={st['ega_ctm_mask']}> ({st['ega_ngb']} gases, 32 channels per warp, tiles of 8 segments, free-running CTAs)"
+        kernel = (f"ega_tiled_kernel<mask={st['ega_ctm_mask']}> ({st['ega_ngb']} gases, 32 channels per warp, tiles of 6 segments, "
+                  f"{'lock-step' if st['ega_phase_lock'] else 'free-running'} CTAs)")
     else:
         kernel = (f"ega_fast_kernel<mask={st['ega_ctm_mask']}> ({st['ega_ngb']} gases, {st['ega_channels_per_warp']} channels per warp, "
                   f"{'lock-step' if st['ega_phase_lock'] else 'free-running'} CTAs)")

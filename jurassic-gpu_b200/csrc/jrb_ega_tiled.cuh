@@ -22,7 +22,7 @@
 namespace jrb {
 
 #ifndef JRB_EGA_TILE
-#define JRB_EGA_TILE 8
+#define JRB_EGA_TILE 6
 #endif
 constexpr int kEgaTile = JRB_EGA_TILE;
 

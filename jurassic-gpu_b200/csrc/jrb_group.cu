@@ -583,9 +583,9 @@ int jrb_shared_alloc(const char *name, size_t bytes, int create, void **out) {
   if (create && ftruncate(fd, (off_t)bytes) != 0) { close(fd); shm_unlink(name); return JRB_ERR_ARG; }
   void *p = mmap(nullptr, bytes, PROT_READ | PROT_WRITE, MAP_SHARED, fd, 0);
   close(fd);
-  if (p == MAP_FAILED) return JRB_ERR_ARG;
+  if (p == MAP_FAILED) { if (create) shm_unlink(name); return JRB_ERR_ARG; }
   const int rc = jrb_host_register(p, bytes);
-  if (rc != JRB_OK) { munmap(p, bytes); return rc; }
+  if (rc != JRB_OK) { munmap(p, bytes); if (create) shm_unlink(name); return rc; }
   *out = p;
   return JRB_OK;
 }

@@ -539,13 +539,18 @@ static void hydrostatic_host(const jrb_atm_view &a, double hydz, int ig_h2o) {
 // (32 channels x ng gases) cannot stay in L2 -- then narrower channel groups with several rays per warp (channel-group-major
 // order keeps the hot set at cpw x ng pairs).  Hot bytes per (gas, channel) pair: ~30 % of its brackets (measured on the
 // synthetic sets: a package touches 357 KB of a 1.26 MB pair); budget 0.7 x L2, which reproduces the measured optima
-// (Config D, 57 MB at 32 channels: 32 = 16 > 8; Config E, 94 MB: 16 best, -4 %; 30 gases, 343 MB: 8 best, -14 %).
+// (segment-by-segment kernel -- Config D, 57 MB at 32 channels: 32 = 16 > 8; Config E, 94 MB: 16 best, -4 %; 30 gases, 343 MB: 8 best, -14 %).
 static int choose_cpw(const jrb_context *ctx, int gases_per_pass) {
   const int nd = ctx->nd, ng = ctx->ng;
   int cpw = nd <= 16 ? nd : 32;
   if (nd > 16 && ng > 0) {
     const double pair_hot = 0.3 * 16.0 * (double)ctx->tbl->th.n_entries / ((double)ng * nd);
-    while (cpw > 4 && pair_hot * cpw * gases_per_pass > 0.7 * (double)ctx->l2_bytes) cpw >>= 1;
+    // the segment-tiled kernel (32-channel groups only) re-reads a bracket half as often, so it tolerates a hot set of the
+    // size of the L2: Config E (94 MB at 32 channels) runs 7 % faster tiled at 32 than segment by segment at 16
+    const bool tiled_ok = ctx->tbl->th.all_shared && !(getenv("JRB_EGA_TILED") && atoi(getenv("JRB_EGA_TILED")) == 0) &&
+                          ega_tiled_fits(gases_per_pass, make_los_layout(ng, ctx->nw, 1, ctx->tbl->th.gas_axes_same).rec, (size_t)ctx->smem_optin);
+    if (!(tiled_ok && pair_hot * 32 * gases_per_pass <= 1.0 * (double)ctx->l2_bytes))
+      while (cpw > 4 && pair_hot * cpw * gases_per_pass > 0.7 * (double)ctx->l2_bytes) cpw >>= 1;
   }
   if (const char *s = getenv("JRB_EGA_CPW")) { const int v = atoi(s); if (v >= 1 && v <= 32 && (v == nd || (32 % v == 0 && v <= nd))) cpw = v; } // experiments
   return cpw;

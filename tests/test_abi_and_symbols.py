@@ -90,3 +90,26 @@ def test_no_gpu_means_loud_failure(jr):
         pytest.skip("a GPU is present")
     with pytest.raises(jr.JrbError, match="no usable CUDA device"):
         jr.Context(0)
+
+
+def test_new_entry_points_fail_loudly_without_a_gpu(jr):
+    """groups, page-locking and node-shared memory have no CPU fallback either"""
+    import numpy as np
+    lib = jr.load_core()
+    if lib.jrb_device_count() > 0:
+        pytest.skip("a GPU is present")
+    with pytest.raises(jr.JrbError):
+        jr.Group(ndev=1)
+    a = np.zeros(1024)
+    assert lib.jrb_host_register(a.ctypes.data_as(C.c_void_p), a.nbytes) != 0
+    assert lib.jrb_host_is_registered(a.ctypes.data_as(C.c_void_p), a.nbytes) == 0
+    p = C.c_void_p()
+    assert lib.jrb_shared_alloc(b"/jrb_test_no_gpu", 4096, 1, C.byref(p)) != 0 and not p.value
+
+
+def test_c_caller_builds_against_the_public_headers():
+    """tests/c/multi_gpu_formod.c compiles against include/*.h + the struct mirror and links the drop-in library"""
+    import subprocess
+    r = subprocess.run(["make", "-C", os.path.join(ROOT, "tests", "c")], capture_output=True, text=True)
+    assert r.returncode == 0, r.stdout + r.stderr
+    assert os.path.exists(os.path.join(ROOT, "tests", "c", "multi_gpu_formod"))
