@@ -545,11 +545,12 @@ static int choose_cpw(const jrb_context *ctx, int gases_per_pass) {
   int cpw = nd <= 16 ? nd : 32;
   if (nd > 16 && ng > 0) {
     const double pair_hot = 0.3 * 16.0 * (double)ctx->tbl->th.n_entries / ((double)ng * nd);
-    // the segment-tiled kernel (32-channel groups only) re-reads a bracket half as often, so it tolerates a hot set of the
-    // size of the L2: Config E (94 MB at 32 channels) runs 7 % faster tiled at 32 than segment by segment at 16
+    // the segment-tiled kernel (32-channel groups only) re-reads a bracket half as often, so it tolerates a larger hot set:
+    // Config E (94 MB at 32 channels) runs 7 % faster tiled at 32 than segment by segment at 16; at 121 MB (a 10-gas pass of
+    // the 30-gas refspec shape) the narrower groups win again (82.7 vs 98.7 ms)
     const bool tiled_ok = ctx->tbl->th.all_shared && !(getenv("JRB_EGA_TILED") && atoi(getenv("JRB_EGA_TILED")) == 0) &&
                           ega_tiled_fits(gases_per_pass, make_los_layout(ng, ctx->nw, 1, ctx->tbl->th.gas_axes_same).rec, (size_t)ctx->smem_optin);
-    if (!(tiled_ok && pair_hot * 32 * gases_per_pass <= 1.0 * (double)ctx->l2_bytes))
+    if (!(tiled_ok && pair_hot * 32 * gases_per_pass <= 0.8 * (double)ctx->l2_bytes)) // (E: 94 MB yes; 10 of 30 refspec gases: 121 MB no)
       while (cpw > 4 && pair_hot * cpw * gases_per_pass > 0.7 * (double)ctx->l2_bytes) cpw >>= 1;
   }
   if (const char *s = getenv("JRB_EGA_CPW")) { const int v = atoi(s); if (v >= 1 && v <= 32 && (v == nd || (32 % v == 0 && v <= nd))) cpw = v; } // experiments
