@@ -219,6 +219,37 @@ def test_binary_cache_round_trip_with_larger_extents(jr, tmp_path):
         jr.core.write_binary_tables(os.path.join(str(tmp_path), "x"), tbl, ctl, NG=1, ND=8)
 
 
+def test_binary_cache_header_is_untrusted_input(jr, tmp_path):
+    """advisor (round 1): header_size and the extents come from the file -- a header length other than the reference's
+    16384, or extents whose products would overflow, are rejected instead of being turned into array offsets"""
+    ctl = jr.Control(["CO2", "H2O"], [792.0, 832.0])
+    tbl = jr.synth.make_tables(ctl)
+    good = os.path.join(str(tmp_path), jr.core.binary_tables_filename(3, 8))
+    jr.core.write_binary_tables(good, tbl, ctl, NG=3, ND=8)
+    jr.core.read_binary_tables(ctl, good).close()
+    raw = open(good, "rb").read()
+    head, body = raw[:16384], raw[16384:]
+
+    def variant(name, old, new):
+        assert old in head
+        h = head.replace(old, new, 1)
+        h = h[:16384].ljust(16384, b"\0")
+        path = os.path.join(str(tmp_path), name)
+        with open(path, "wb") as f:
+            f.write(h + body)
+        return path
+
+    import re
+    m = re.search(rb"header_size\s+16384", head)
+    assert m
+    with pytest.raises(jr.JrbError, match="header_size"):
+        jr.core.read_binary_tables(ctl, variant("bad_header_size", m.group(0), m.group(0).replace(b"16384", b"16388")))
+    m = re.search(rb"TBLNU\s+304", head)
+    assert m
+    with pytest.raises(jr.JrbError, match="4096|table_size|extents"):
+        jr.core.read_binary_tables(ctl, variant("bad_extent", m.group(0), m.group(0).replace(b"304", b"99999999")))
+
+
 @pytest.mark.gpu
 def test_dropin_init_from_files_uses_and_writes_the_binary_cache(jr, oracle, tmp_path, monkeypatch):
     """jr_b200_init_from_files follows init_tbl's READ_BINARY / WRITE_BINARY protocol (src/jurassic.c:312-320, 669-671)"""
