@@ -9,7 +9,7 @@ echo "== D 32 default"; NPK=32 WITH_E=0 timeout 200 python tools/gpu_time.py
 echo "== D 32 tail not sorted"; JRB_NO_TAIL_SORT=1 NPK=32 WITH_E=0 timeout 200 python tools/gpu_time.py
 } > $out/variants_r2l.log 2>&1
 grep -E "^==|^\[|Error" $out/variants_r2l.log
-bash tools/gpu_r2k.sh
+bash tools/round2/gpu_r2k.sh
 timeout 1200 python -m pytest tests -m gpu -q > $out/pytest_gpu_r2l.log 2>&1; echo "pytest all rc=$?"; tail -4 $out/pytest_gpu_r2l.log
 timeout 900 python bench.py --steps 5 --warmup 3 --no-config-e > $out/bench_r2l.json 2> $out/bench_r2l.err; echo "bench rc=$?"
 tail -c 400 $out/bench_r2l.err; python - <<'PY'
