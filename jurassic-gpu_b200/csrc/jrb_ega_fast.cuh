@@ -667,6 +667,6 @@ cudaError_t launch_ega_split(const EgaArgs &a, cudaStream_t stream, int sm_count
 template <int MASK>
 cudaError_t launch_ega_fast_mask(const EgaArgs &a, cudaStream_t stream, int sm_count, int *ngb_out);
 template <int MASK>
-cudaError_t launch_ega_tiled_mask(const EgaArgs &a, cudaStream_t stream, int sm_count); // segment-tiled form (jrb_ega_tiled.cuh)
+cudaError_t launch_ega_tiled_mask(const EgaArgs &a, cudaStream_t stream, int sm_count, int *n_launched); // segment-tiled form (jrb_ega_tiled.cuh)
 
 } // namespace jrb

@@ -18,8 +18,8 @@ cudaError_t launch_ega_fast_mask<JRB_MASK>(const EgaArgs &a, cudaStream_t stream
 }
 
 template <>
-cudaError_t launch_ega_tiled_mask<JRB_MASK>(const EgaArgs &a, cudaStream_t stream, int sm_count) {
-  return a.unsorted_columns ? launch_ega_tiled_tm<JRB_MASK, true>(a, stream, sm_count) : launch_ega_tiled_tm<JRB_MASK, false>(a, stream, sm_count);
+cudaError_t launch_ega_tiled_mask<JRB_MASK>(const EgaArgs &a, cudaStream_t stream, int sm_count, int *n_launched) {
+  return a.unsorted_columns ? launch_ega_tiled_tm<JRB_MASK, true>(a, stream, sm_count, n_launched) : launch_ega_tiled_tm<JRB_MASK, false>(a, stream, sm_count, n_launched);
 }
 
 } // namespace jrb

@@ -264,7 +264,8 @@ static __global__ void __launch_bounds__(1024) tail_sort_kernel(const int *__res
 }
 
 template <int MASK, bool ROBUST, bool SPLIT = false>
-cudaError_t launch_ega_tiled_tm(const EgaArgs &a, cudaStream_t stream, int sm_count) {
+cudaError_t launch_ega_tiled_tm(const EgaArgs &a, cudaStream_t stream, int sm_count, int *n_launched = nullptr) {
+  int nl = 0;
   const int ng_state = SPLIT ? a.gases_per_block : a.ng;
   const long long n_items = a.n_rays * ((a.nd + 31) / 32) * (SPLIT ? a.n_gas_blocks : 1);
   int dev = 0, smem_max = 0;
@@ -292,6 +293,7 @@ cudaError_t launch_ega_tiled_tm(const EgaArgs &a, cudaStream_t stream, int sm_co
   if (args.phase_lock_mode < 0 && args.balance != nullptr && a.n_rays > 0) { // let the device decide: equal-length chunks -> lock step
     const long long n_chunks = (n_items + block / 32 - 1) / (block / 32);
     chunk_balance_kernel<<<(unsigned)((n_chunks + 127) / 128), 128, 0, stream>>>(a.ray_np, a.n_rays, 1, block / 32, args.balance);
+    nl++;
   }
   long long grid = (long long)sm_count * blocks_per_sm;
   const long long need = (n_items + block / 32 - 1) / (block / 32);
@@ -304,9 +306,11 @@ cudaError_t launch_ega_tiled_tm(const EgaArgs &a, cudaStream_t stream, int sm_co
     if (tail <= args.tail_cap && a.n_rays >= 4 * tail) {
       args.tail_n = (int)tail;
       tail_sort_kernel<<<1, 1024, 0, stream>>>(a.ray_np + (a.n_rays - tail), (int)tail, args.tail_perm);
+      nl++;
     }
   }
   ega_tiled_kernel<MASK, ROBUST, SPLIT><<<(unsigned)grid, block, smem, stream>>>(args);
+  if (n_launched) *n_launched = nl + 1;
   return cudaGetLastError();
 }
 

@@ -123,7 +123,7 @@ cudaError_t launch_ega_fast(const EgaArgs &a, cudaStream_t stream, int *ngb_out)
 cudaError_t launch_ega_split_passes(const EgaArgs &a, cudaStream_t stream);
 cudaError_t launch_ega_segments(const EgaArgs &a, cudaStream_t stream); // everything but the recurrence, per (segment, channel), fully parallel
 cudaError_t launch_ega_combine(const EgaArgs &a, cudaStream_t stream);
-cudaError_t launch_ega_tiled(const EgaArgs &a, cudaStream_t stream); // segment-tiled form (jrb_ega_tiled.cuh)
+cudaError_t launch_ega_tiled(const EgaArgs &a, cudaStream_t stream, int *n_launched); // segment-tiled form (jrb_ega_tiled.cuh); kernels it launched
 bool ega_tiled_fits(int ng, int los_rec, size_t smem_max);
 bool ega_fast_available(int ng, int ctm_mask);
 bool ega_fast_fits(int ng, int los_head, int cpw, size_t smem_max);

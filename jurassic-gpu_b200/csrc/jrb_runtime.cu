@@ -997,12 +997,11 @@ static int run_locked(jrb_context *ctx) {
       ctx->stats.ega_tiled = e.use_tiled;
       CU(launch_ega_segments(e, st_e));
       CU(launch_ega_combine(e, st_e));
-      launches += 2;
+      launches += 3 + ((e.phase_lock_mode < 0 && e.n_rays > 0) ? 1 : 0); // pass kernel (+ balance), segment kernel, combine kernel
     } else if (ctx->use_fast) {
-      if (e.use_tiled) { CU(launch_ega_tiled(e, st_e)); ctx->stats.ega_tiled = 1; }
-      else { CU(launch_ega_fast(e, st_e, &ngb)); ctx->stats.ega_tiled = 0; }
-    } else CU(launch_ega_generic(e, st_e));
-    launches += (ctx->use_fast && e.phase_lock_mode < 0 && e.n_rays > 0) ? 2 : 1; // + chunk_balance_kernel
+      if (e.use_tiled) { int nk = 1; CU(launch_ega_tiled(e, st_e, &nk)); ctx->stats.ega_tiled = 1; launches += nk; } // + balance, tail sort
+      else { CU(launch_ega_fast(e, st_e, &ngb)); ctx->stats.ega_tiled = 0; launches += (e.phase_lock_mode < 0 && e.n_rays > 0) ? 2 : 1; }
+    } else { CU(launch_ega_generic(e, st_e)); launches++; }
     CU(cudaEventRecord(EV(c, 3), st_e));
   }
   if (ctx->scan_pending) scan_staged_obs(ctx); // (a batch without rays)
