@@ -8,12 +8,15 @@ import sys
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 LIB = os.path.join(ROOT, "jurassic-gpu_b200", "lib", "libjurassic_b200.so")
-WANT = [("ega_fast_kernel<12,0,0,0,0>  (Config D: CO2+H2O continua, one ray per warp, fused)", "ega_fast_kernelILi12ELb0ELb0ELb0ELb0EE"),
+WANT = [("ega_tiled_kernel<12,0,0>  (Config D: CO2+H2O continua, segment-tiled, the default)", "ega_tiled_kernelILi12ELb0ELb0EE"),
+        ("ega_tiled_kernel<15,0,0>  (Config E: all continua, segment-tiled, 32-channel groups)", "ega_tiled_kernelILi15ELb0ELb0EE"),
+        ("ega_tiled_kernel<0,0,1>   (segment-tiled gas-block pass of the split mode)", "ega_tiled_kernelILi0ELb0ELb1EE"),
+        ("ega_fast_kernel<12,0,0,0,0>  (Config D, segment by segment: the round-1 form)", "ega_fast_kernelILi12ELb0ELb0ELb0ELb0EE"),
         ("ega_fast_kernel<15,1,0,0,0>  (Config E: all continua, 16 channels per warp, fused)", "ega_fast_kernelILi15ELb1ELb0ELb0ELb0EE"),
-        ("ega_fast_kernel<0,0,0,1,0>   (gas-block pass of the split mode)", "ega_fast_kernelILi0ELb0ELb0ELb1ELb0EE"),
+        ("ega_fast_kernel<0,1,0,1,0>   (gas-block pass, several rays per warp)", "ega_fast_kernelILi0ELb1ELb0ELb1ELb0EE"),
         ("ega_fast_kernel<12,0,1,0,1>  (channel-dependent axes)", "ega_fast_kernelILi12ELb0ELb1ELb0ELb1EE"),
         ("ega_combine_kernel", "ega_combine_kernel"), ("ega_segment_kernel", "ega_segment_kernel"),
-        ("ray_step_kernel", "ray_step_kernel"), ("los_finalize_kernel", "los_finalize_kernel"), ("stage_kernel", "stage_kernel")]
+        ("ray_step_kernel<1>  (thread per ray)", "ray_step_kernelILi1EE"), ("ray_step_kernel<8>  (8 lanes per ray)", "ray_step_kernelILi8EE"), ("los_finalize_kernel", "los_finalize_kernel"), ("stage_kernel", "stage_kernel")]
 KEYS = ["UBLKCP", "SYNCS", "LDG", "LDS", "STS", "STG", "DFMA", "DMUL", "DADD", "DSETP", "F2F", "MUFU", "FSETP", "IMAD", "SHFL", "BAR", "BRA", "ATOM"]
 
 out = subprocess.run(["cuobjdump", "-sass", LIB], capture_output=True, text=True).stdout
