@@ -81,17 +81,32 @@ __global__ void __launch_bounds__(kEgaBlock, JRB_EGA_MINBLOCKS) ega_tiled_kernel
       item = __shfl_sync(0xffffffffu, item, 0);
       if (item >= n_items) break;
     }
-    int g0 = 0, g1 = ng, gblk = 0; // gases of this item
+    int g0 = 0, g1 = ng, gblk = 0, grp; // gases and channel group of this item
+    long long ir;
+    if (SPLIT && a.tail_n > 0) {
+      // latency mode: ALL rays longest first (tail_perm covers the whole launch), the gas blocks and channel groups of a ray
+      // next to each other -- the items that start last are the shortest ones, which is what sets the duration of a launch
+      // that is only one to two rounds of warps long
+      const unsigned long long per_ray = (unsigned long long)a.n_gas_blocks * ngroups;
+      const unsigned long long rr = item / per_ray;
+      const unsigned rest = (unsigned)(item - rr * per_ray);
+      gblk = (int)(rest % (unsigned)a.n_gas_blocks);
+      grp = (int)(rest / (unsigned)a.n_gas_blocks);
+      ir = a.tail_perm[rr];
+    } else {
+      if (SPLIT) {
+        gblk = (int)(item / n_items_blk);
+        item -= (unsigned long long)gblk * n_items_blk;
+      }
+      grp = (int)(item / (unsigned long long)a.n_rays);
+      ir = (long long)(item - (unsigned long long)grp * (unsigned long long)a.n_rays);
+      if (!SPLIT && a.tail_n > 0 && item >= n_items - (unsigned long long)a.tail_n) // the last items: longest ray first
+        ir = a.n_rays - a.tail_n + a.tail_perm[item - (n_items - (unsigned long long)a.tail_n)];
+    }
     if (SPLIT) {
-      gblk = (int)(item / n_items_blk);
-      item -= (unsigned long long)gblk * n_items_blk;
       g0 = gblk * a.gases_per_block;
       g1 = min(ng, g0 + a.gases_per_block);
     }
-    const int grp = (int)(item / (unsigned long long)a.n_rays);
-    long long ir = (long long)(item - (unsigned long long)grp * (unsigned long long)a.n_rays);
-    if (!SPLIT && a.tail_n > 0 && item >= n_items - (unsigned long long)a.tail_n) // the last items: longest ray first
-      ir = a.n_rays - a.tail_n + a.tail_perm[item - (n_items - (unsigned long long)a.tail_n)];
     const int id_raw = grp * 32 + lane;
     const bool lane_on = id_raw < nd;
     const int id = lane_on ? id_raw : nd - 1;
@@ -301,6 +316,11 @@ cudaError_t launch_ega_tiled_tm(const EgaArgs &a, cudaStream_t stream, int sm_co
   if (grid < 1) grid = 1;
   // the last two rounds of rays longest first (only worth it when the launch has many rounds)
   args.tail_n = 0;
+  if (SPLIT && args.tail_perm && a.n_rays > 0 && a.n_rays <= args.tail_cap && !getenv("JRB_NO_TAIL_SORT")) {
+    args.tail_n = (int)a.n_rays; // latency mode: the whole (small) launch in order of decreasing ray length
+    tail_sort_kernel<<<1, 1024, 0, stream>>>(a.ray_np, (int)a.n_rays, args.tail_perm);
+    nl++;
+  }
   if (!SPLIT && args.tail_perm && !getenv("JRB_NO_TAIL_SORT")) {
     const long long tail = 2 * grid * (block / 32);
     if (tail <= args.tail_cap && a.n_rays >= 4 * tail) {
