@@ -17,26 +17,6 @@ namespace jrb {
 
 namespace {
 
-// Latency mode only: the gas-independent part of a segment -- exp(-beta_ds) of the continua / extinction and the band Planck
-// source -- needs nothing from the gas-block passes, so it runs on a second stream beside them (its blocks fill the SMs the
-// persistent pass CTAs vacate towards the end) and leaves {exp(-beta_ds), src} in a.seg_pre for ega_segment_kernel.
-__global__ void __launch_bounds__(256) ega_pre_kernel(const EgaArgs a) {
-  const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-  const int nd = a.nd;
-  const long long seg = idx / nd;
-  const int id = (int)(idx - seg * nd);
-  const long long ir = seg / kNLOS;
-  const int ip = (int)(seg - ir * kNLOS);
-  if (ir >= a.n_rays || ip >= a.ray_np[ir]) return;
-  const LosLayout L = a.los;
-  const double *__restrict__ rec = a.los_data + ((size_t)ir * kNLOS + ip) * L.rec;
-  const double p = rec[0], t = rec[1], ds = rec[2];
-  const double u_co2 = (a.ctm_mask & 8) ? rec[L.u0 + a.ig_co2] : 0.0;
-  const double u_h2o = (a.ctm_mask & 4) ? rec[L.u0 + a.ig_h2o] : 0.0;
-  const double beta_ds = continuum_beta_ds(a.ctm_mask, a.chan, nd, id, p, t, ds, a.nw > 0 ? rec[4 + a.window[id]] : 0.0, u_co2, u_h2o, rec[3]);
-  a.seg_pre[idx] = make_double2(exp(-beta_ds), planck_source(a.tbl.sr, nd, id, t));
-}
-
 // Everything of a segment except the along-ray recurrence, fully parallel: thread per (ray, segment, channel).
 //   tau_gas = product of the block products in the canonical order (groups in order, inside a group in gas order; a block
 //             whose gas went opaque at an earlier segment contributes 0)
@@ -63,11 +43,7 @@ __global__ void __launch_bounds__(256) ega_segment_kernel(const EgaArgs a) {
     tau_gas *= pg;
   }
   double2 out = make_double2(0.0, 1.0);
-  if (tau_gas > 1e-50 && a.pre_done) { // new_obs_core (src/jr_common.h:293-300) on the values ega_pre_kernel left
-    const double2 es = a.seg_pre[idx];
-    const double eps = 1. - tau_gas * es.x;
-    out = make_double2(es.y * eps, 1. - eps);
-  } else if (tau_gas > 1e-50) {
+  if (tau_gas > 1e-50) { // new_obs_core (src/jr_common.h:293-300)
     const LosLayout L = a.los;
     const double *__restrict__ rec = a.los_data + ((size_t)ir * kNLOS + ip) * L.rec;
     const double p = rec[0], t = rec[1], ds = rec[2];
@@ -140,14 +116,6 @@ cudaError_t launch_ega_segments(const EgaArgs &a, cudaStream_t stream) {
   if (n <= 0) return cudaSuccess;
   if (!a.seg_pre) return cudaErrorInvalidValue;
   ega_segment_kernel<<<(unsigned)((n + 255) / 256), 256, 0, stream>>>(a);
-  return cudaGetLastError();
-}
-
-cudaError_t launch_ega_pre(const EgaArgs &a, cudaStream_t stream) {
-  const long long n = a.n_rays * kNLOS * a.nd;
-  if (n <= 0) return cudaSuccess;
-  if (!a.seg_pre) return cudaErrorInvalidValue;
-  ega_pre_kernel<<<(unsigned)((n + 255) / 256), 256, 0, stream>>>(a);
   return cudaGetLastError();
 }
 

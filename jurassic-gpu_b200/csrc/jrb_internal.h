@@ -74,7 +74,6 @@ struct EgaArgs {
   double *partial;                  // [n_gas_blocks][n_rays][NLOS][nd] per-segment product of the block's gas factors
   int *partial_len;                 // [n_gas_blocks][n_rays][nd] segments that carry a product (a gas went opaque at len-1 if < np)
   double2 *seg_pre;                 // [n_rays][NLOS][nd] {src * eps, 1 - eps} per segment and channel (ega_segment_kernel)
-  int pre_done;                     // 1: ega_pre_kernel left {exp(-beta_ds), src} in seg_pre (latency mode)
 };
 
 struct FovArgs { // optional epilogue: field-of-view convolution (formod_fov, src/jurassic.c:214-258)
@@ -123,7 +122,6 @@ cudaError_t launch_ega_fast(const EgaArgs &a, cudaStream_t stream, int *ngb_out)
 // multiplies the block products per segment and does continuum, Planck source, accumulation and the epilogues
 cudaError_t launch_ega_split_passes(const EgaArgs &a, cudaStream_t stream);
 cudaError_t launch_ega_segments(const EgaArgs &a, cudaStream_t stream); // everything but the recurrence, per (segment, channel), fully parallel
-cudaError_t launch_ega_pre(const EgaArgs &a, cudaStream_t stream);      // latency mode: continuum / source part beside the passes
 cudaError_t launch_ega_combine(const EgaArgs &a, cudaStream_t stream);
 cudaError_t launch_ega_tiled(const EgaArgs &a, cudaStream_t stream, int *n_launched); // segment-tiled form (jrb_ega_tiled.cuh); kernels it launched
 bool ega_tiled_fits(int ng, int los_rec, size_t smem_max);

@@ -155,8 +155,6 @@ struct jrb_context {
   bool l2_window_set = false;
   DevBuf d_partial, d_tail;
   std::vector<cudaEvent_t> events;
-  cudaEvent_t ev_side_ = nullptr;
-  cudaEvent_t ev_side() { if (!ev_side_) cudaEventCreateWithFlags(&ev_side_, cudaEventDisableTiming); return ev_side_; }
   jrb_stats stats;
   bool np_fetched = false;
 
@@ -224,7 +222,6 @@ void jrb_destroy(jrb_context *ctx) {
   cudaSetDevice(ctx->device);
   cudaStreamSynchronize(ctx->stream);
   for (auto ev : ctx->events) cudaEventDestroy(ev);
-  if (ctx->ev_side_) cudaEventDestroy(ctx->ev_side_);
   ctx->d_chan.release(); ctx->d_window.release(); ctx->tbl.reset();
   ctx->d_in.release(); ctx->d_tab.release(); ctx->d_out.release(); ctx->d_rayout.release(); ctx->d_los.release();
   ctx->d_np.release(); ctx->d_tsurf.release(); ctx->d_counter.release(); ctx->d_slope.release(); ctx->d_level0.release();
@@ -990,25 +987,14 @@ static int run_locked(jrb_context *ctx) {
     e.use_tiled = use_tiled;
     e.tail_perm = (int *)ctx->d_tail.p + (size_t)c * kTailCap; e.tail_cap = kTailCap; e.tail_n = 0;
     e.n_gas_blocks = ctx->n_gas_blocks; e.gases_per_block = ctx->gases_per_block; e.blocks_per_group = ctx->blocks_per_group;
-    e.partial = nullptr; e.partial_len = nullptr; e.seg_pre = nullptr; e.pre_done = 0;
+    e.partial = nullptr; e.partial_len = nullptr; e.seg_pre = nullptr;
     if (ctx->use_fast && ctx->n_gas_blocks > 1) { // split mode: gas-block passes, then the combine kernel
       char *pb = (char *)ctx->d_partial.p;
       e.seg_pre = (double2 *)pb; pb += (size_t)e.n_rays * kNLOS * nd * 16;
       e.partial = (double *)pb; pb += (size_t)ctx->n_gas_blocks * (size_t)e.n_rays * kNLOS * nd * 8;
       e.partial_len = (int *)pb;
-      // latency mode (one gas per pass item): the continuum / source part of every segment runs on a second stream beside
-      // the passes (submitted after them: the pass CTAs take the SMs first, its blocks fill what they vacate)
-      const bool side = ctx->blocks_per_group > 1 && !pipe && !getenv("JRB_NO_SIDE_STREAM");
-      e.pre_done = side ? 1 : 0;
       CU(launch_ega_split_passes(e, st_e));
       ctx->stats.ega_tiled = e.use_tiled;
-      if (side) {
-        CU(cudaStreamWaitEvent(ctx->s_ega[0], EV(c, 1), 0)); // the records are final
-        CU(launch_ega_pre(e, ctx->s_ega[0]));
-        CU(cudaEventRecord(ctx->ev_side(), ctx->s_ega[0]));
-        CU(cudaStreamWaitEvent(st_e, ctx->ev_side(), 0));
-        launches++;
-      }
       CU(launch_ega_segments(e, st_e));
       CU(launch_ega_combine(e, st_e));
       launches += 3 + ((e.phase_lock_mode < 0 && e.n_rays > 0) ? 1 : 0); // pass kernel (+ balance), segment kernel, combine kernel
