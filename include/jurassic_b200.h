@@ -52,7 +52,8 @@ typedef struct {
   double hydz; /* < 0: no hydrostatic adjustment */
   int write_bbt;
   int formod; /* must be 2 (EGA) */
-  int ip;     /* must be 1 (1-D profile interpolation) */
+  int ip;     /* atmosphere interpolation (src/jurassic.c:685-691): 1 = 1-D profile, 2 = 2-D (profiles along a track), 3 = 3-D (weighted average) */
+  double cz, cx; /* ip == 3: vertical / horizontal influence radius [km] (ctl->cz, ctl->cx) */
 } jrb_ctl_view;
 
 typedef struct {

@@ -27,7 +27,9 @@ extern "C" {
 #endif
 
 /* Drop-in for the reference symbol.  Tables: if jr_b200_init() was not called, they are taken from the
- * reference's get_tbl(ctl) (src/jr_common.h:60-78) when that symbol is linked in, else the call is fatal. */
+ * reference's get_tbl(ctl) (src/jr_common.h:60-78) when that symbol is linked in, else the call is fatal.
+ * ctl->ip = 2, 3 (2-D / 3-D atmosphere, ctl->cz, ctl->cx) selects intpol_atm_2d / _3d (src/jurassic.c:685-804) inside the
+ * tracer, where the reference's own formod_GPU stops at an assert (src/jr_common.h:573,581). */
 void formod_GPU(ctl_t const *ctl, atm_t *atm, obs_t *obs);
 
 /* Explicit initialisation with a caller-owned table (kept only until this call returns).

@@ -59,7 +59,7 @@ class CtlView(C.Structure):
                 ("ctm_co2", C.c_int), ("ctm_h2o", C.c_int), ("ctm_n2", C.c_int), ("ctm_o2", C.c_int),
                 ("ig_co2", C.c_int), ("ig_h2o", C.c_int), ("refrac", C.c_int), ("rayds", C.c_double),
                 ("raydz", C.c_double), ("hydz", C.c_double), ("write_bbt", C.c_int), ("formod", C.c_int),
-                ("ip", C.c_int)]
+                ("ip", C.c_int), ("cz", C.c_double), ("cx", C.c_double)]
 
 
 class AtmView(C.Structure):

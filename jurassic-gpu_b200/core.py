@@ -277,6 +277,7 @@ class Control:
         self.ctm_co2, self.ctm_h2o, self.ctm_n2, self.ctm_o2 = ctm_co2, ctm_h2o, ctm_n2, ctm_o2
         self.refrac, self.rayds, self.raydz, self.hydz, self.write_bbt = refrac, rayds, raydz, hydz, write_bbt
         self.formod, self.ip = 2, 1
+        self.cz, self.cx = 0.0, 0.0  # influence radii of the 3-D interpolation (ip = 3), read_ctl defaults
         self.tblbase = tblbase
         self.auto_ctm()
 
@@ -304,6 +305,7 @@ class Control:
         v.ig_co2 = self.find_emitter("CO2") if self.ctm_co2 else -999
         v.refrac, v.rayds, v.raydz, v.hydz = self.refrac, self.rayds, self.raydz, self.hydz
         v.write_bbt, v.formod, v.ip = self.write_bbt, self.formod, self.ip
+        v.cz, v.cx = self.cz, self.cx
         return v
 
     @property

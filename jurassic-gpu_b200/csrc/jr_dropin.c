@@ -55,6 +55,7 @@ static void fill_ctl_view(ctl_t const *ctl, jrb_ctl_view *v) {
   v->ig_co2 = ctl->ctm_co2 ? emitter_index(ctl, "CO2") : -999;
   v->refrac = ctl->refrac; v->rayds = ctl->rayds; v->raydz = ctl->raydz; v->hydz = ctl->hydz;
   v->write_bbt = ctl->write_bbt; v->formod = ctl->formod; v->ip = ctl->ip;
+  v->cz = ctl->cz; v->cx = ctl->cx;
 }
 
 static void fill_tbl_view(tbl_t const *t, jrb_tbl_view *v) {

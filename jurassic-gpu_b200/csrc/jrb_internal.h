@@ -20,9 +20,14 @@ struct TraceArgs {
   long long n_atm;
   int prepare_atm;             // 1: (re)compute atm_lnp_slope before tracing
   int small_blocks;            // 1: 32/64-thread CTAs that fit beside the resident EGA CTAs (pipelined chunks)
+  // 2-D / 3-D atmospheres (ip != 1): geo2cart(0, lon, lat) of every point [3][atm_stride] and the end of its column [atm_stride]
+  double *atm_cart;
+  int *atm_next;
   // control
   int refrac, ig_h2o;
   double rayds, raydz;
+  int ip;                      // atmosphere interpolation (src/jurassic.c:685-691): 1 = 1-D, 2 = 2-D, 3 = 3-D
+  double cz, cx;               // influence radii of the 3-D form
   // outputs
   LosLayout los;
   double *los_data; // [n_rays][NLOS][rec]
@@ -33,7 +38,8 @@ struct TraceArgs {
   double *const *tp_host; // optional [3][geo_stride] per-ray addresses in host-mapped memory (the caller's obs_t or the
                           // pinned result buffer): the tangent point is also stored there -- no device-to-host copy phase
   TblDev tbl;       // used when los.fast
-  int *error_flag;  // host-mapped word: bit 0 = a ray needs NLOS or more points (fatal "Too many LOS points!" in the reference's CPU path)
+  int *error_flag;  // host-mapped words, each one a fatal condition of the reference: [0] a ray needs NLOS or more points ("Too many
+                    // LOS points!"), [1] / [2] profile list of the 2-D interpolation ("Cannot identify profiles", "Distance ... too large")
 };
 
 struct EgaArgs {

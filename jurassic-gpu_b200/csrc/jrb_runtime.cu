@@ -109,6 +109,8 @@ struct jrb_context {
   bool have_ctl = false;
   int ng = 0, nd = 0, nw = 0, ctm_mask = 0, ig_co2 = -1, ig_h2o = -1, refrac = 1, write_bbt = 0;
   double rayds = 10, raydz = 0.5, hydz = -999;
+  int ip = 1;            // atmosphere interpolation: 1-D profiles, 2-D track, 3-D weighted average (src/jurassic.c:685-691)
+  double cz = 0, cx = 0; // influence radii of the 3-D form
   std::vector<double> nu;
   std::vector<int> window;
   DevBuf d_chan, d_window;
@@ -243,7 +245,9 @@ int jrb_set_control(jrb_context *ctx, const jrb_ctl_view *c) {
   if (c->nd < 1) return ctx->fail(JRB_ERR_ARG, "nd must be >= 1");
   if (c->nw < 0 || c->nw > JRB_MAX_NW) return ctx->fail(JRB_ERR_LIMIT, "nw out of range (max 8)");
   if (c->formod != 2) return ctx->fail(JRB_ERR_ARG, "only FORMOD=2 (EGA) is supported (reference asserts the same, src/jr_common.h:707)");
-  if (c->ip != 1) return ctx->fail(JRB_ERR_ARG, "only IP=1 (1-D profiles) is supported (reference asserts the same, src/jr_common.h:573)");
+  // 1-D profiles are the reference's formod() path; 2 and 3 are the dispatch of src/jurassic.c:685-691 (see jrb_raytrace.cu)
+  if (c->ip < 1 || c->ip > 3) return ctx->fail(JRB_ERR_ARG, "Unknown interpolation method, check IP!"); // src/jurassic.c:690
+  if (c->ip == 3 && !(c->cz > 0 && c->cx > 0)) return ctx->fail(JRB_ERR_ARG, "IP=3 needs influence radii CZ > 0 and CX > 0");
   for (int id = 0; id < c->nd; id++)
     if (c->window[id] < 0 || c->window[id] >= (c->nw > 0 ? c->nw : 1)) return ctx->fail(JRB_ERR_ARG, "window index out of range");
   const int mask = ((1 == c->ctm_co2) && (c->ig_co2 >= 0)) * 8 + ((1 == c->ctm_h2o) && (c->ig_h2o >= 0)) * 4 +
@@ -251,7 +255,7 @@ int jrb_set_control(jrb_context *ctx, const jrb_ctl_view *c) {
   // unchanged control (the drop-in layer pushes it on every call, like the reference re-uploads ctl_t): nothing to do
   if (ctx->have_ctl && ctx->ng == c->ng && ctx->nd == c->nd && ctx->nw == c->nw && ctx->ig_co2 == c->ig_co2 && ctx->ig_h2o == c->ig_h2o &&
       ctx->ctm_mask == mask && ctx->refrac == c->refrac && ctx->rayds == c->rayds && ctx->raydz == c->raydz && ctx->hydz == c->hydz &&
-      ctx->write_bbt == c->write_bbt && std::equal(ctx->nu.begin(), ctx->nu.end(), c->nu) &&
+      ctx->write_bbt == c->write_bbt && ctx->ip == c->ip && ctx->cz == c->cz && ctx->cx == c->cx && std::equal(ctx->nu.begin(), ctx->nu.end(), c->nu) &&
       std::equal(ctx->window.begin(), ctx->window.end(), c->window))
     return JRB_OK;
   CU(cudaSetDevice(ctx->device));
@@ -260,6 +264,7 @@ int jrb_set_control(jrb_context *ctx, const jrb_ctl_view *c) {
   ctx->ng = c->ng; ctx->nd = c->nd; ctx->nw = c->nw;
   ctx->ig_co2 = c->ig_co2; ctx->ig_h2o = c->ig_h2o;
   ctx->ctm_mask = mask;
+  ctx->ip = c->ip; ctx->cz = c->cz; ctx->cx = c->cx;
   ctx->refrac = c->refrac; ctx->rayds = c->rayds; ctx->raydz = c->raydz; ctx->hydz = c->hydz;
   ctx->write_bbt = c->write_bbt;
   ctx->nu.assign(c->nu, c->nu + c->nd);
@@ -652,7 +657,7 @@ static int stage_locked(jrb_context *ctx, int npk, const jrb_atm_view *atm, cons
   const double **h_src = (const double **)(HT + off_src);
 
   ctx->err_flag = (int *)(HT + off_flag);
-  *ctx->err_flag = 0;
+  ctx->err_flag[0] = ctx->err_flag[1] = ctx->err_flag[2] = 0;
   ctx->pk_nr.resize(npk);
   ctx->pk_ray_off.resize(npk + 1);
   {
@@ -716,7 +721,8 @@ static int stage_locked(jrb_context *ctx, int npk, const jrb_atm_view *atm, cons
   ctx->ray_out = (double **)ctx->d_rayout.p;
   CU(ctx->d_np.ensure((size_t)(R ? R : 1) * 4));
   CU(ctx->d_tsurf.ensure((size_t)(R ? R : 1) * 8));
-  CU(ctx->d_slope.ensure((size_t)(A ? A : 1) * 16));
+  // level slopes [2][A]; 2-D / 3-D atmospheres: + Cartesian positions [3][A] and column ends [A]
+  CU(ctx->d_slope.ensure((size_t)(A ? A : 1) * (ctx->ip != 1 ? 48 : 16)));
   CU(ctx->d_level0.ensure((size_t)(R ? R : 1) * 4));
 
   double t_pack0 = now_ms(), t_pack1 = t_pack0;
@@ -936,6 +942,8 @@ static int run_locked(jrb_context *ctx) {
     t.atm_stride = A;
     t.atm_lnp_slope = (double *)ctx->d_slope.p; t.n_atm = A; t.prepare_atm = (c == 0);
     t.small_blocks = pipe && c > 0;
+    t.atm_cart = (double *)ctx->d_slope.p + 2 * A; t.atm_next = (int *)((double *)ctx->d_slope.p + 5 * A);
+    t.ip = ctx->ip; t.cz = ctx->cz; t.cx = ctx->cx;
     t.refrac = ctx->refrac; t.ig_h2o = (ctx->ctm_mask & 4) ? ctx->ig_h2o : -1;
     t.rayds = ctx->rayds; t.raydz = ctx->raydz;
     t.los = ctx->los; t.los_data = los_buf;
@@ -1040,8 +1048,11 @@ static int run_locked(jrb_context *ctx) {
   }
   CU(cudaEventRecord(ctx->events[1], ctx->stream));
   CU(cudaStreamSynchronize(ctx->stream));
-  if (ctx->err_flag && *ctx->err_flag) {
-    *ctx->err_flag = 0;
+  if (ctx->err_flag && (ctx->err_flag[0] | ctx->err_flag[1] | ctx->err_flag[2])) {
+    const int e0 = ctx->err_flag[0], e1 = ctx->err_flag[1];
+    ctx->err_flag[0] = ctx->err_flag[1] = ctx->err_flag[2] = 0;
+    if (e1) return ctx->fail(JRB_ERR_ARG, "Cannot identify profiles. Check ordering of data points!"); // src/jurassic.c:727
+    if (!e0) return ctx->fail(JRB_ERR_ARG, "Distance of profiles is too large!");                      // src/jurassic.c:728
     return ctx->fail(JRB_ERR_LIMIT, "Too many LOS points!"); // like the reference's CPU path (src/jr_common.h:693-695)
   }
   if (ctx->fov_applied) {

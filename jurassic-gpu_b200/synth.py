@@ -81,6 +81,41 @@ def limb_package(ctl, n_profiles=17, rays_per_profile=64, z0=3.0, dz=1.0, obsz=7
     return pkg
 
 
+def track_package(ctl, n_profiles=9, rays=24, lat0=-10.0, dlat=3.0, z0=6.0, dz=1.5, obsz=780.0, seed=20240519, obslat=-24.0):
+    """Atmosphere for the 2-D / 3-D interpolation (ctl.ip = 2, 3; src/jurassic.c:704-804): n_profiles columns of one time
+    stamp along a meridional track (latitude lat0 + j*dlat, longitude drifting a little), each with its own pressure and
+    temperature perturbation and vmr scaling, and limb rays whose paths cross several columns (the default track covers the
+    rays from where they enter the atmosphere, latitude -6, to where they leave it, latitude +13)."""
+    rng = np.random.default_rng(seed)
+    prof = base_profile()
+    nz = prof["z"].size
+    pkg = Package(ctl.ng, ctl.nw, ctl.nd, n_profiles * nz, rays)
+    for j in range(n_profiles):
+        s = slice(j * nz, (j + 1) * nz)
+        pkg.atm_time[s] = 0.0
+        pkg.z[s] = prof["z"]
+        pkg.lon[s] = 0.3 * j
+        pkg.lat[s] = lat0 + dlat * j
+        pkg.p[s] = prof["p"] * (1.0 + rng.uniform(-0.05, 0.05))
+        pkg.t[s] = prof["t"] + rng.uniform(-20.0, 20.0) + 3.0 * np.sin(prof["z"] / 7.0 + j)
+        scale = 1.0 + rng.uniform(-0.3, 0.3)
+        for ig, g in enumerate(ctl.emitters):
+            pkg.q[ig, s] = (prof[g] if g in prof else 1e-9) * scale
+        pkg.k[:, s] = 1e-4 * np.exp(-prof["z"] / 8.0) * (1.0 + 0.1 * j)
+    for r in range(rays):
+        vpz = z0 + dz * r
+        # observer south of the track looking north: tangent point near the middle of the track
+        a = np.arccos((RE + vpz) / (RE + obsz)) * 180.0 / np.pi
+        pkg.time[r] = 0.0
+        pkg.obsz[r] = obsz
+        pkg.obslat[r] = obslat
+        pkg.obslon[r] = 0.3 * (n_profiles - 1) / 2
+        pkg.vpz[r] = vpz
+        pkg.vplat[r] = obslat + a
+        pkg.vplon[r] = 0.3 * (n_profiles - 1) / 2 + 0.05 * r / max(rays - 1, 1)
+    return pkg
+
+
 def nadir_package(ctl, n_profiles=16, rays_per_profile=68, obsz=700.0, lat0=-6.03, dlat=0.18, seed=20240518,
                   perturb=True):
     """Config-E style package: nadir footprints looking at the ground (surface term active)."""

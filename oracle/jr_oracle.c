@@ -221,7 +221,115 @@ static void o_intpol_qk(const jrb_ctl_view *c, const jrb_atm_view *a, int idx0, 
   }
 }
 
-/* traceray (:585-711).  los[] must hold O_NLOS points whose q/k/u arrays are allocated.  Returns np. */
+/* ---- 2-D / 3-D atmosphere interpolation (src/jurassic.c:685-804) ---------------------------------------------------
+ * intpol_atm_geo dispatches on ctl->ip.  The reference's formod() path never gets there: its tracer calls
+ * intpol_atm_geo_pt/_qk, which assert ip == 1 (src/jr_common.h:569-583).  The restatement below is what the dispatch of
+ * src/jurassic.c:685-691 gives when it is applied to the atmosphere slice [idx0, idx0+n) that locate_atm selected for the
+ * ray -- i.e. the tracer of src/jr_common.h:585-711 with its two assert-guarded calls replaced by intpol_atm_geo.
+ * The interpolation itself is pinned bit for bit against the reference's intpol_atm_geo (tests/test_oracle_vs_reference.py);
+ * the composition with the tracer has no reference behaviour to compare with (the reference aborts).
+ * The reference keeps the profile list of the 2-D case in function statics guarded by atm->init; here it is rebuilt per
+ * call (same values).  Return: 0, or the reference's fatal conditions: -3 "Cannot identify profiles. Check ordering of
+ * data points!", -4 "Distance of profiles is too large!" (:727-728). */
+static void o_intpol_1d(const jrb_ctl_view *c, const jrb_atm_view *a, int idx0, int n, double z0, double *p, double *t, double *q, double *k) {
+  o_intpol_pt(a, idx0, n, z0, p, t);      /* intpol_atm_1d (:694-701): EXP / LIN macros = eip / lip */
+  o_intpol_qk(c, a, idx0, n, z0, q, k);
+}
+static double o_dist2(const double a[3], const double b[3]) { /* DIST2, src/jurassic.h:61 */
+  return (a[0] - b[0]) * (a[0] - b[0]) + (a[1] - b[1]) * (a[1] - b[1]) + (a[2] - b[2]) * (a[2] - b[2]);
+}
+static int o_intpol_2d(const jrb_ctl_view *c, const jrb_atm_view *a, int idx0, int n, double z0, double lon0, double lat0,
+                       double *p, double *t, double *q, double *k) { /* intpol_atm_2d (:704-760) */
+  const double dlat = 10;
+  double dhmin0 = 1e99, dhmin1 = 1e99, lat1 = -999, lon1 = -999, x0[3], x1a[3] = {0, 0, 0}, x1b[3] = {0, 0, 0};
+  int nx = 0, ix0 = 0, ix1 = 0;
+  int *idx = (int *)malloc(sizeof(int) * (size_t)(n > 0 ? n : 1) * 2), *nz = idx + (n > 0 ? n : 1);
+  for (int ip = idx0; ip < idx0 + n; ip++) { /* profile list (:713-725) */
+    if ((a->lon[ip] != lon1) || (a->lat[ip] != lat1)) {
+      ++nx; nz[nx - 1] = 0; lon1 = a->lon[ip]; lat1 = a->lat[ip]; idx[nx - 1] = ip;
+    }
+    ++nz[nx - 1];
+  }
+  for (int ix = 0; ix < nx; ix++) {
+    if (nz[ix] <= 1) { free(idx); return -3; }
+    if ((ix > 0) && (fabs(a->lat[idx[ix - 1]] - a->lat[idx[ix]]) > dlat)) { free(idx); return -4; }
+  }
+  o_geo2cart(0, lon0, lat0, x0);
+  for (int ix = 0; ix < nx; ix++) /* two nearest profiles (:732-745) */
+    if (fabs(lat0 - a->lat[idx[ix]]) <= dlat) {
+      double xp[3];
+      o_geo2cart(0, a->lon[idx[ix]], a->lat[idx[ix]], xp);
+      const double dh = o_dist2(x0, xp);
+      if (dh <= dhmin0) { dhmin1 = dhmin0; ix1 = ix0; dhmin0 = dh; ix0 = ix; }
+      else if (dh <= dhmin1) { dhmin1 = dh; ix1 = ix; }
+    }
+  double p0, p1, t0, t1, q0[JRB_MAX_NG], q1[JRB_MAX_NG], k0[JRB_MAX_NW], k1[JRB_MAX_NW], r;
+  o_intpol_1d(c, a, idx[ix0], nz[ix0], z0, &p0, &t0, q0, k0);
+  o_intpol_1d(c, a, idx[ix1], nz[ix1], z0, &p1, &t1, q1, k1);
+  o_geo2cart(0, a->lon[idx[ix0]], a->lat[idx[ix0]], x1a);
+  o_geo2cart(0, a->lon[idx[ix1]], a->lat[idx[ix1]], x1b);
+  const double x2 = o_dist2(x1a, x1b), x = sqrt(x2), r0 = (dhmin0 - dhmin1 + x2) / (2 * x), r1 = x - r0; /* :750-755 */
+  if (r0 <= 0) r = 0; else r = (r1 <= 0) ? 1 : r0 / (r0 + r1);
+  *p = (1 - r) * p0 + r * p1;
+  *t = (1 - r) * t0 + r * t1;
+  for (int ig = 0; ig < c->ng; ig++) q[ig] = (1 - r) * q0[ig] + r * q1[ig];
+  for (int iw = 0; iw < c->nw; iw++) k[iw] = (1 - r) * k0[iw] + r * k1[iw];
+  free(idx);
+  return 0;
+}
+static int o_intpol_3d(const jrb_ctl_view *c, const jrb_atm_view *a, int idx0, int n, double z0, double lon0, double lat0,
+                       double *p, double *t, double *q, double *k) { /* intpol_atm_3d (:763-804) */
+  const double rm2 = c->cx * c->cx;
+  double wsum = 0, x0[3];
+  *p = *t = 0.;
+  for (int ig = 0; ig < c->ng; ig++) q[ig] = 0;
+  for (int iw = 0; iw < c->nw; iw++) k[iw] = 0;
+  for (int ip = idx0; ip < idx0 + n; ip++) {
+    const double dz = fabs(a->z[ip] - z0);
+    if (dz >= c->cz) continue;
+    if (fabs(a->lat[ip] - lat0) * 111.13 >= c->cx) continue;
+    double xp[3];
+    o_geo2cart(0, lon0, lat0, x0);
+    o_geo2cart(0, a->lon[ip], a->lat[ip], xp);
+    const double dx2 = o_dist2(x0, xp);
+    if (dx2 >= rm2) continue;
+    const double w = (1 - dz / c->cz) * (rm2 - dx2) / (rm2 + dx2);
+    wsum += w;
+    *p += w * a->p[ip];
+    *t += w * a->t[ip];
+    for (int ig = 0; ig < c->ng; ig++) q[ig] += w * (a->q_rows ? a->q_rows[ig] : a->q + (size_t)ig * a->q_stride)[ip];
+    for (int iw = 0; iw < c->nw; iw++) k[iw] += w * (a->k_rows ? a->k_rows[iw] : a->k + (size_t)iw * a->k_stride)[ip];
+  }
+  if (wsum >= 1e-6) {
+    *p /= wsum; *t /= wsum;
+    for (int ig = 0; ig < c->ng; ig++) q[ig] /= wsum;
+    for (int iw = 0; iw < c->nw; iw++) k[iw] /= wsum;
+  } else {
+    *p = *t = NAN;
+    for (int ig = 0; ig < c->ng; ig++) q[ig] = NAN;
+    for (int iw = 0; iw < c->nw; iw++) k[iw] = NAN;
+  }
+  return 0;
+}
+/* intpol_atm_geo (:685-691) on a slice */
+static int o_intpol_geo(const jrb_ctl_view *c, const jrb_atm_view *a, int idx0, int n, double z0, double lon0, double lat0,
+                        double *p, double *t, double *q, double *k) {
+  if (c->ip == 1) { o_intpol_1d(c, a, idx0, n, z0, p, t, q, k); return 0; }
+  if (c->ip == 2) return o_intpol_2d(c, a, idx0, n, z0, lon0, lat0, p, t, q, k);
+  if (c->ip == 3) return o_intpol_3d(c, a, idx0, n, z0, lon0, lat0, p, t, q, k);
+  return -1; /* "Unknown interpolation method, check IP!" */
+}
+/* the dispatch applied to the whole atmosphere, as the reference's intpol_atm_geo does; out = {p, t, q[ng], k[nw]} */
+int jro_intpol_atm_geo(const jrb_ctl_view *c, const jrb_atm_view *a, double z0, double lon0, double lat0, double *out) {
+  double q[JRB_MAX_NG], k[JRB_MAX_NW];
+  const int rc = o_intpol_geo(c, a, 0, a->np, z0, lon0, lat0, &out[0], &out[1], q, k);
+  for (int ig = 0; ig < c->ng; ig++) out[2 + ig] = q[ig];
+  for (int iw = 0; iw < c->nw; iw++) out[2 + c->ng + iw] = k[iw];
+  return rc;
+}
+
+/* traceray (:585-711).  los[] must hold O_NLOS points whose q/k/u arrays are allocated.  Returns np (or < 0: the fatal
+ * conditions of the 2-D interpolation, see above). */
 static int o_traceray(const jrb_ctl_view *c, const jrb_atm_view *a, const jrb_obs_view *o, int ir, o_pos *los, double *tsurf) {
   double ex0[3], ex1[3], q[JRB_MAX_NG], k[JRB_MAX_NW], lat, lon, p, t, x[3], xobs[3], xvp[3], z = 1e99, z_low = z, zmax, zmin;
   const double zrefrac = 60;
@@ -260,6 +368,9 @@ static int o_traceray(const jrb_ctl_view *c, const jrb_atm_view *a, const jrb_ob
     }
   }
   int np = 0, z_low_idx = -1;
+  double qd[JRB_MAX_NG], kd[JRB_MAX_NW]; /* the probe points need p and T only */
+#define O_PROBE_PT() do { if (c->ip == 1) o_intpol_pt(a, idx0, n, z, &p, &t); \
+                          else { const int rc_ = o_intpol_geo(c, a, idx0, n, z, lon, lat, &p, &t, qd, kd); if (rc_) return rc_; } } while (0)
   for (int stop = 0; np < O_NLOS; ++np) {
     double ds = c->rayds, dz = c->raydz;
     if (dz > 0.) {
@@ -282,8 +393,8 @@ static int o_traceray(const jrb_ctl_view *c, const jrb_atm_view *a, const jrb_ob
       los[np - 1].ds = ds * frac;
       ds = 0.;
     }
-    o_intpol_pt(a, idx0, n, z, &p, &t);
-    o_intpol_qk(c, a, idx0, n, z, q, k);
+    if (c->ip == 1) { o_intpol_pt(a, idx0, n, z, &p, &t); o_intpol_qk(c, a, idx0, n, z, q, k); }
+    else { const int rc = o_intpol_geo(c, a, idx0, n, z, lon, lat, &p, &t, q, k); if (rc) return rc; }
     los[np].lon = lon; los[np].lat = lat; los[np].z = z; los[np].p = p; los[np].t = t; los[np].ds = ds; /* write_pos_point :422-434 */
     for (int ig = 0; ig < c->ng; ig++) los[np].q[ig] = q[ig];
     for (int iw = 0; iw < c->nw; iw++) los[np].k[iw] = k[iw];
@@ -295,13 +406,13 @@ static int o_traceray(const jrb_ctl_view *c, const jrb_atm_view *a, const jrb_ob
       double xh[3];
       for (i = 0; i < 3; i++) xh[i] = x[i] + 0.5 * ds * ex0[i];
       o_cart2geo(xh, &z, &lon, &lat);
-      o_intpol_pt(a, idx0, n, z, &p, &t);
+      O_PROBE_PT();
       const double n2 = 7.753e-05 * p / t;
       for (i = 0; i < 3; i++) {
         const double h = 0.02;
         xh[i] += h;
         o_cart2geo(xh, &z, &lon, &lat);
-        o_intpol_pt(a, idx0, n, z, &p, &t);
+        O_PROBE_PT();
         ng[i] = (7.753e-05 * p / t - n2) / h;
         xh[i] -= h;
       }
@@ -392,12 +503,13 @@ static int o_fourbit(const jrb_ctl_view *c) { /* CPUdrivers.c:130-134 */
 
 /* formod_CPU (CPUdrivers.c:108-151) for one package */
 int jro_formod(const jrb_ctl_view *c, const jrb_tbl_view *v, const jrb_atm_view *a, const jrb_obs_view *o) {
-  if (c->ng > JRB_MAX_NG || c->nw > JRB_MAX_NW || c->formod != 2 || c->ip != 1) return -1;
+  if (c->ng > JRB_MAX_NG || c->nw > JRB_MAX_NW || c->formod != 2 || c->ip < 1 || c->ip > 3) return -1;
   const int nr = o->nr, nd = c->nd, fourbit = o_fourbit(c);
   char *mask = (char *)malloc((size_t)nr * nd + 1);
   for (int ir = 0; ir < nr; ir++)
     for (int id = 0; id < nd; id++) mask[(size_t)ir * nd + id] = !isfinite(o->rad[(size_t)ir * o->row_stride + id]); /* save_mask :193-200 */
   if (c->hydz >= 0) o_hydrostatic(c, a, c->ig_h2o); /* hydrostatic1d_CPU :97-103 (idempotent, so once) */
+  int fatal = 0;
   int too_many = 0; /* the reference is fatal ("Too many LOS points!") when a ray needs NLOS points or more (:693-695) */
 #pragma omp parallel
   {
@@ -406,7 +518,12 @@ int jro_formod(const jrb_ctl_view *c, const jrb_tbl_view *v, const jrb_atm_view 
 #pragma omp for schedule(dynamic, 1)
     for (int ir = 0; ir < nr; ir++) {
       double tsurf;
-      const int np = o_traceray(c, a, o, ir, los, &tsurf);
+      int np = o_traceray(c, a, o, ir, los, &tsurf);
+      if (np < 0) { /* fatal in the reference (2-D profile list, src/jurassic.c:727-728) */
+#pragma omp atomic write
+        fatal = np;
+        np = 0;
+      }
       if (np >= O_NLOS) {
 #pragma omp atomic write
         too_many = 1;
@@ -440,7 +557,7 @@ int jro_formod(const jrb_ctl_view *c, const jrb_tbl_view *v, const jrb_atm_view 
     o_free_los(los);
   }
   free(mask);
-  return too_many ? -2 : 0;
+  return too_many ? -2 : fatal;
 }
 
 /* LOS of one ray flattened like oracle/ref_hooks.c:jrref_traceray:

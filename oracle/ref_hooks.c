@@ -82,6 +82,15 @@ int jrref_traceray(ctl_t const *ctl, atm_t const *atm, obs_t *obs, int ir, doubl
   return np;
 }
 
+/* the reference's atmosphere interpolation dispatch (src/jurassic.c:685-691; 1-D, 2-D, 3-D); out = {p, t, q[ng], k[nw]}.
+ * The 2-D / 3-D forms keep their geometry in function statics guarded by atm->init: pass a fresh atm (init == 0). */
+void jrref_intpol_atm_geo(ctl_t const *ctl, atm_t *atm, double z0, double lon0, double lat0, double *out) {
+  double q[NG], k[NW];
+  intpol_atm_geo(ctl, atm, z0, lon0, lat0, &out[0], &out[1], q, k);
+  for (int ig = 0; ig < ctl->ng; ig++) out[2 + ig] = q[ig];
+  for (int iw = 0; iw < ctl->nw; iw++) out[2 + ctl->ng + iw] = k[iw];
+}
+
 /* ---- forward model with a caller-supplied table ------------------------------------------------ */
 /* Same call sequence as formod_CPU (src/CPUdrivers.c:108-151), but with `tbl` given instead of get_tbl(),
  * and ig_co2/ig_h2o looked up on every call instead of cached in function statics (Appendix D #16). */

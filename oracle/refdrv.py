@@ -36,6 +36,9 @@ class Oracle:
         lib.jro_max_threads.restype = C.c_int
         lib.jro_formod_fov.argtypes = [C.POINTER(abi.ObsView), C.c_int, C.c_int, abi.c_double_p, abi.c_double_p]
         lib.jro_formod_fov.restype = C.c_int
+        lib.jro_intpol_atm_geo.argtypes = [C.POINTER(abi.CtlView), C.POINTER(abi.AtmView), C.c_double, C.c_double, C.c_double,
+                                           abi.c_double_p]
+        lib.jro_intpol_atm_geo.restype = C.c_int
         self.lib = lib
 
     def formod(self, ctl, tbl, pkg):
@@ -43,6 +46,10 @@ class Oracle:
         rc = self.lib.jro_formod(C.byref(cv), C.byref(tv), C.byref(av), C.byref(ov))
         if rc == -2:
             raise RuntimeError("Too many LOS points!")  # where the reference's CPU path exits (src/jr_common.h:693-695)
+        if rc == -3:
+            raise RuntimeError("Cannot identify profiles. Check ordering of data points!")  # src/jurassic.c:727
+        if rc == -4:
+            raise RuntimeError("Distance of profiles is too large!")  # src/jurassic.c:728
         if rc != 0:
             raise RuntimeError("jro_formod failed")
 
@@ -60,6 +67,13 @@ class Oracle:
         ts = C.c_double()
         n = self.lib.jro_traceray(C.byref(cv), C.byref(av), C.byref(ov), ir, _dp(buf), C.byref(ts))
         return buf[: n * stride].reshape(n, stride).copy(), ts.value
+
+    def intpol_atm_geo(self, ctl, pkg, z, lon, lat):
+        """intpol_atm_geo (ctl.ip = 1, 2, 3) over the whole atmosphere of pkg -> (rc, [p, t, q.., k..])"""
+        cv, av = ctl.view(), pkg.atm_view()
+        out = np.zeros(2 + ctl.ng + ctl.nw)
+        rc = self.lib.jro_intpol_atm_geo(C.byref(cv), C.byref(av), z, lon, lat, _dp(out))
+        return rc, out
 
     def threads(self):
         return self.lib.jro_max_threads()
@@ -104,6 +118,9 @@ class Reference:
         lib.jrref_kernel.argtypes = [vp, vp, vp, abi.c_double_p, C.c_size_t, C.c_size_t]
         lib.formod_fov.argtypes = [vp, vp]  # the reference's own public symbol (src/jurassic.c:214)
         lib.formod_fov.restype = None
+        if hasattr(lib, "jrref_intpol_atm_geo"):
+            lib.jrref_intpol_atm_geo.argtypes = [vp, vp, C.c_double, C.c_double, C.c_double, abi.c_double_p]
+            lib.jrref_intpol_atm_geo.restype = None
         self.lib = lib
 
     # ---- ABI facts ----
@@ -131,6 +148,7 @@ class Reference:
         c.hydz = ctl.hydz
         c.ctm_co2, c.ctm_h2o, c.ctm_n2, c.ctm_o2 = ctl.ctm_co2, ctl.ctm_h2o, ctl.ctm_n2, ctl.ctm_o2
         c.ip, c.refrac, c.rayds, c.raydz = ctl.ip, ctl.refrac, ctl.rayds, ctl.raydz
+        c.cz, c.cx = getattr(ctl, "cz", 0.0), getattr(ctl, "cx", 0.0)
         c.write_bbt, c.formod, c.useGPU = ctl.write_bbt, ctl.formod, useGPU
         c.read_binary, c.write_binary = 0, 0
         c.fov = b"-"
@@ -207,6 +225,12 @@ class Reference:
         ts = C.c_double()
         n = self.lib.jrref_traceray(C.addressof(c), C.addressof(a), C.addressof(o), ir, _dp(buf), C.byref(ts))
         return buf[: n * stride].reshape(n, stride).copy(), ts.value
+
+    def intpol_atm_geo(self, c, a, z, lon, lat, ng, nw):
+        """the reference's intpol_atm_geo (src/jurassic.c:685-691); a must be a fresh atm_t (init == 0) per atmosphere"""
+        out = np.zeros(2 + ng + nw)
+        self.lib.jrref_intpol_atm_geo(C.addressof(c), C.addressof(a), z, lon, lat, _dp(out))
+        return out
 
     def formod_fov(self, c, o):
         """the reference's FOV convolution; NOTE it caches the shape file of the first call for the life of the process"""

@@ -254,3 +254,92 @@ def test_too_many_los_points_is_fatal_in_the_reference_and_an_error_in_the_oracl
     root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
     r = subprocess.run([sys.executable, "-c", _TOO_LONG.format(root=root)], capture_output=True, text=True, timeout=300)
     assert r.returncode != 0 and "Too many LOS points!" in r.stdout and "SURVIVED" not in r.stdout
+
+
+# ---- 3. 2-D / 3-D atmosphere interpolation (ctl->ip = 2, 3; src/jurassic.c:685-804) ---------------------------------
+def _track_case(jr, ip):
+    synth = jr.synth
+    ctl = synth.control_limb_example()
+    ctl.ip = ip
+    ctl.cz, ctl.cx = 1.7, 420.0
+    pkg = synth.track_package(ctl)
+    return ctl, pkg
+
+
+@pytest.mark.parametrize("ip", [1, 2, 3])
+def test_intpol_atm_geo_restatement_equals_reference(jr, oracle, refdrv, ip):
+    """the restated intpol_atm_geo / _1d / _2d / _3d against the reference's own, bit for bit, at points on, between and
+    outside the columns (incl. a point whose influence sphere is empty -> NaN in the 3-D form)"""
+    _need(refdrv, 2, 5)
+    ctl, pkg = _track_case(jr, ip)
+    if ip == 1:  # the 1-D form takes the whole atmosphere as one profile: keep one column
+        nz = pkg.n_atm // 9
+        for name in ("atm_time", "z", "lon", "lat", "p", "t"):
+            setattr(pkg, name, getattr(pkg, name)[:nz].copy())
+        pkg.q, pkg.k = pkg.q[:, :nz].copy(), pkg.k[:, :nz].copy()
+    ref = refdrv.Reference(2, 5)
+    c, a = ref.make_ctl(ctl), ref.make_atm(pkg)
+    assert a.init == 0
+    rng = np.random.default_rng(7 + ip)
+    pts = [(rng.uniform(0.0, 90.0), rng.uniform(-1.0, 3.5), rng.uniform(-9.5, 9.5)) for _ in range(300)]
+    pts += [(10.0, 0.6, -4.0), (33.3, 1.2, 0.0), (0.0, 0.0, -8.0), (90.0, 2.4, 8.0), (45.5, 0.0, 30.0), (20.0, 40.0, 0.0)]
+    n_nan = 0
+    for z, lon, lat in pts:
+        want = ref.intpol_atm_geo(c, a, z, lon, lat, ctl.ng, ctl.nw)
+        rc, got = oracle.intpol_atm_geo(ctl, pkg, z, lon, lat)
+        assert rc == 0
+        _same(got, want, f"ip={ip} at z={z} lon={lon} lat={lat}")
+        n_nan += int(np.isnan(want[0]))
+    # 3-D: empty influence sphere -> NaN by construction (:799-803); 2-D: no column within 10 degrees of latitude ->
+    # both neighbours default to column 0 and the blend is 0/0 (the point at latitude 30)
+    assert n_nan >= 1 if ip == 3 else n_nan == (1 if ip == 2 else 0)
+
+
+def test_intpol_2d_fatal_conditions(jr, oracle):
+    """profile list checks of intpol_atm_2d (src/jurassic.c:727-728) -- the reference exits there"""
+    ctl, pkg = _track_case(jr, 2)
+    bad = copy.deepcopy(pkg)
+    bad.lat[5] += 0.01  # a level that belongs to no column: "Cannot identify profiles"
+    rc, _ = oracle.intpol_atm_geo(ctl, bad, 10.0, 0.0, 0.0)
+    assert rc == -3
+    bad = copy.deepcopy(pkg)
+    nz = pkg.n_atm // 9
+    bad.lat[4 * nz:] += 15.0  # a gap of more than 10 degrees between neighbouring columns
+    rc, _ = oracle.intpol_atm_geo(ctl, bad, 10.0, 0.0, 0.0)
+    assert rc == -4
+    tbl = jr.synth.make_tables(ctl)
+    with pytest.raises(RuntimeError, match="Distance of profiles is too large"):
+        oracle.formod(ctl, tbl, bad)
+
+
+@pytest.mark.parametrize("ip", [2, 3])
+def test_oracle_formod_2d_3d_properties(jr, oracle, ip):
+    """formod with ip = 2, 3 (tracer of src/jr_common.h:585-711 over intpol_atm_geo): no reference behaviour exists (the
+    reference asserts ip == 1), so the composition is checked by properties: identical columns reproduce the 1-D result
+    (2-D: bit for bit up to the blend's rounding; 3-D: cz below the level spacing picks single levels)"""
+    synth = jr.synth
+    ctl, pkg = _track_case(jr, ip)
+    tbl = synth.make_tables(ctl)
+    nz = pkg.n_atm // 9
+    same = copy.deepcopy(pkg)
+    for j in range(1, 9):  # all columns equal to column 0
+        for name in ("p", "t"):
+            getattr(same, name)[j * nz:(j + 1) * nz] = getattr(same, name)[:nz]
+        same.q[:, j * nz:(j + 1) * nz] = same.q[:, :nz]
+        same.k[:, j * nz:(j + 1) * nz] = same.k[:, :nz]
+    oracle.formod(ctl, tbl, same)
+    assert np.all(np.isfinite(same.rad)) and np.all(same.rad > 0) and np.all((same.tau >= 0) & (same.tau <= 1))
+    if ip == 2:
+        one = copy.deepcopy(same)
+        c1 = copy.deepcopy(ctl)
+        c1.ip = 1
+        for name in ("atm_time", "z", "lon", "lat", "p", "t"):
+            setattr(one, name, getattr(one, name)[:nz].copy())
+        one.q, one.k = one.q[:, :nz].copy(), one.k[:, :nz].copy()
+        oracle.formod(c1, tbl, one)
+        assert np.allclose(same.rad, one.rad, rtol=1e-9, atol=0) and np.allclose(same.tau, one.tau, rtol=1e-9, atol=1e-300)
+        assert np.allclose(same.tpz, one.tpz, rtol=0, atol=1e-9)
+    # and the real case differs from it (the columns matter)
+    oracle.formod(ctl, tbl, pkg)
+    assert np.all(np.isfinite(pkg.rad))
+    assert np.max(np.abs(pkg.rad - same.rad) / same.rad) > 1e-3
