@@ -125,6 +125,18 @@ __device__ __forceinline__ double fast_rcp(double x) {
   r = fma(r, e, r);
   return r;
 }
+// Fast reciprocal square root: MUFU.RSQ64H seed (~2^-20) + two Newton steps (relative error ~1e-16); same caveats as fast_rcp.
+// sqrt(x) = x * fast_rsqrt(x) and 1/sqrt(x) come out of ONE dependent chain instead of an IEEE sqrt followed by a reciprocal.
+__device__ __forceinline__ double fast_rsqrt(double x) {
+  double y;
+  asm("rsqrt.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(x));
+  const double h = 0.5 * x;
+  double e = fma(-h * y, y, 0.5);
+  y = fma(y, e, y);
+  e = fma(-h * y, y, 0.5);
+  y = fma(y, e, y);
+  return y;
+}
 __device__ __forceinline__ double lerp_fast(double x0, double y0, double x1, double y1, double x) {
   return fma((x - x0) * (y1 - y0), fast_rcp(x1 - x0), y0);
 }

@@ -82,6 +82,12 @@ struct Profile {
 };
 
 __device__ __forceinline__ double refractivity(double p, double t) { return 7.753e-05 * p / t; }
+// the stepping loop of ray_step_kernel is one long dependent FP64 chain per ray: divisions and square roots there use the
+// Newton forms of jrb_device.cuh (1e-16 relative, no special-case branches) -- about a third of the chain
+// (explicitly rounded products: the two forms of the kernel use these values in different expressions, and a product that the
+//  compiler contracts into a following add in one form only would break their bit-identity)
+__device__ __forceinline__ double refractivity_fast(double p, double t) { return __dmul_rn(7.753e-05 * p, fast_rcp(t)); }
+__device__ __forceinline__ double fast_sqrt(double x) { return __dmul_rn(x, fast_rsqrt(x)); }
 
 } // namespace
 
@@ -105,8 +111,8 @@ __global__ void atm_slopes_kernel(const double *__restrict__ z, const double *__
 // the group; the per-step instruction count drops ~3x and a batch has 8x more warps.  That is what a small batch needs
 // (a single 1088-ray package is 34 warps in the throughput form: one warp per scheduler on 9 SMs, every dependent FP64
 // instruction exposed).  Every evaluation uses the same expressions in both forms: bit-identical results.
-template <int LPR>
-__global__ void __launch_bounds__(128) ray_step_kernel(TraceArgs a) {
+template <int LPR, int MINB = 1>
+__global__ void __launch_bounds__(128, MINB) ray_step_kernel(TraceArgs a) {
   const long long gtid = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   const long long r = gtid / LPR;
   const int role = LPR > 1 ? (int)(threadIdx.x & (LPR - 1)) : 0;                                   // lane within the ray's group
@@ -183,14 +189,14 @@ __global__ void __launch_bounds__(128) ray_step_kernel(TraceArgs a) {
     double xprev[3] = {0, 0, 0}, zprev = 0; // previous LOS point
     int level = 0, stop = 0;
     for (; np < kNLOS; ++np) {
-      const double rn = norm3(x);
+      const double rr = x[0] * x[0] + x[1] * x[1] + x[2] * x[2];
+      const double inv = fast_rsqrt(rr), rn = __dmul_rn(rr, inv); // |x| and 1/|x| from one chain
       double ds = a.rayds;
       if (a.raydz > 0.0) { // step length from the angle to the local vertical (:625-635)
-        const double inv = fast_rcp(rn);
         double dot = 0.0;
         for (int i = 0; i < 3; i++) dot += ex0[i] * x[i] * inv;
         const double cosa = fabs(dot);
-        if (cosa != 0.0) ds = fmin(ds, a.raydz / cosa);
+        if (cosa != 0.0) ds = fmin(ds, a.raydz * fast_rcp(cosa));
       }
       z = rn - kRE;
       if ((z < zmin) || (z > zmax)) { // left the atmosphere: clip the last segment (:637-648)
@@ -217,18 +223,19 @@ __global__ void __launch_bounds__(128) ray_step_kernel(TraceArgs a) {
           for (int i = 0; i < 3; i++) xh[i] = x[i] + 0.5 * ds * ex0[i];
           const double r2 = xh[0] * xh[0] + xh[1] * xh[1] + xh[2] * xh[2];
           const double xi = role == 2 ? xh[0] : (role == 3 ? xh[1] : xh[2]);
-          zj = (role == 1 ? sqrt(r2) : sqrt(fma(h, fma(2.0, xi, h), r2))) - kRE;
+          const double s2 = role == 1 ? r2 : fma(h, fma(2.0, xi, h), r2);
+          zj = fast_sqrt(s2) - kRE;
         }
         const int lvj = P.locate(zj, level);
         double pj, tj;
         P.eval(zj, lvj, &pj, &tj);
-        const double nj = refractivity(pj, tj);
+        const double nj = refractivity_fast(pj, tj);
         p = __shfl_sync(gmask, pj, 0, LPR); t = __shfl_sync(gmask, tj, 0, LPR);
         level = __shfl_sync(gmask, lvj, 0, LPR);
         const double n2 = __shfl_sync(gmask, nj, 1, LPR);
         const double g0 = __shfl_sync(gmask, nj, 2, LPR), g1 = __shfl_sync(gmask, nj, 3, LPR), g2 = __shfl_sync(gmask, nj, 4, LPR);
         if (a.refrac && z <= 60.0) {
-          nref += refractivity(p, t);
+          nref += refractivity_fast(p, t);
           ngr[0] = (g0 - n2) * (1.0 / h); ngr[1] = (g1 - n2) * (1.0 / h); ngr[2] = (g2 - n2) * (1.0 / h);
         }
       }
@@ -246,27 +253,27 @@ __global__ void __launch_bounds__(128) ray_step_kernel(TraceArgs a) {
       if (stop) { tsurf = (stop == 2 ? t : -999.0); break; }
 
       if (LPR == 1 && a.refrac && z <= 60.0) { // refractivity gradient by finite differences at the half step (:664-681)
-        nref += refractivity(p, t);
+        nref += refractivity_fast(p, t);
         // the four probe points (half step, and half step + h along each axis) are independent: altitudes, level
         // searches and the exponentials are evaluated side by side
         double xh[3], zz[4], ph[4], th[4];
         int lv[4];
         for (int i = 0; i < 3; i++) xh[i] = x[i] + 0.5 * ds * ex0[i];
         const double r2 = xh[0] * xh[0] + xh[1] * xh[1] + xh[2] * xh[2];
-        zz[0] = sqrt(r2) - kRE;
+        zz[0] = fast_sqrt(r2) - kRE;
 #pragma unroll
-        for (int i = 0; i < 3; i++) zz[1 + i] = sqrt(fma(h, fma(2.0, xh[i], h), r2)) - kRE; // |xh + h e_i|
+        for (int i = 0; i < 3; i++) { const double s2 = fma(h, fma(2.0, xh[i], h), r2); zz[1 + i] = fast_sqrt(s2) - kRE; } // |xh + h e_i|
 #pragma unroll
         for (int j = 0; j < 4; j++) lv[j] = P.locate(zz[j], level);
 #pragma unroll
         for (int j = 0; j < 4; j++) P.eval(zz[j], lv[j], &ph[j], &th[j]);
-        const double n2 = refractivity(ph[0], th[0]);
+        const double n2 = refractivity_fast(ph[0], th[0]);
 #pragma unroll
-        for (int i = 0; i < 3; i++) ngr[i] = (refractivity(ph[1 + i], th[1 + i]) - n2) * (1.0 / h);
+        for (int i = 0; i < 3; i++) ngr[i] = (refractivity_fast(ph[1 + i], th[1 + i]) - n2) * (1.0 / h);
       }
       double ex1[3];
       for (int i = 0; i < 3; i++) ex1[i] = ex0[i] * nref + ds * ngr[i];
-      const double in1 = fast_rcp(norm3(ex1));
+      const double in1 = fast_rsqrt(ex1[0] * ex1[0] + ex1[1] * ex1[1] + ex1[2] * ex1[2]);
       for (int i = 0; i < 3; i++) {
         ex1[i] *= in1;
         x[i] += 0.5 * ds * (ex0[i] + ex1[i]);
@@ -687,6 +694,8 @@ cudaError_t launch_raytrace(const TraceArgs &a, cudaStream_t stream, int *launch
   const bool coop = !a.small_blocks && a.n_rays <= 16384 && !getenv("JRB_NO_COOP_TRACER");
   if (a.ip != 1) ray_geo_kernel<<<(unsigned)((a.n_rays + bs - 1) / bs), bs, 0, stream>>>(a);
   else if (coop) ray_step_kernel<8><<<(unsigned)((a.n_rays * 8 + 127) / 128), 128, 0, stream>>>(a);
+  else if (const char *o = getenv("JRB_TRACER_OCC"); o && atoi(o) == 6) ray_step_kernel<1, 6><<<(unsigned)((a.n_rays + bs - 1) / bs), bs, 0, stream>>>(a);
+  else if (o && atoi(o) == 5) ray_step_kernel<1, 5><<<(unsigned)((a.n_rays + bs - 1) / bs), bs, 0, stream>>>(a);
   else ray_step_kernel<1><<<(unsigned)((a.n_rays + bs - 1) / bs), bs, 0, stream>>>(a);
   const long long n = a.n_rays * kNLOS;
   los_finalize_kernel<<<(unsigned)((n + bf - 1) / bf), bf, 0, stream>>>(a);
