@@ -81,12 +81,15 @@ enum ChanField {
 
 // ---- LOS record ------------------------------------------------------------------------------------------------
 // doubles: [0]p [1]t [2]ds [3]q_h2o [4..4+nw)k  [U0..U0+ng)u  (fast: {wp,wt0,wt1,cell} once, or per gas if the gases'
-//          (p,T) grids differ)
-//          tail [Z0..Z0+6): altitude z, raw step length, atmosphere level index, Cartesian x,y,z of the point
-// The EGA kernels read only the first `head` doubles of a record (everything before the tail).
+//          (p,T) grids differ); `rec` = `head` doubles, a multiple of 16 bytes (records are moved by TMA bulk copies).
+// The stepping kernels do not write records: a thread that walks a ray would touch a few doubles of one 100-200 byte record
+// per step, 64 KB away from its neighbour's -- partial-sector writes scattered over DRAM pages.  They write one compact raw
+// point per step instead (kRaw doubles = 64 bytes = two full sectors, consecutive steps adjacent):
+//   raw: [0]p [1]t, then the tail [2] altitude z, [3] raw step length, [4] atmosphere level index, [5..8) Cartesian x,y,z
+// and los_finalize_kernel, fully parallel and coalesced, turns raw points into records.
 struct LosLayout {
   int nw, ng, fast;
-  int u0, c0, cstride, z0, head, rec; // offsets in doubles; cell block of gas ig at c0 + cstride*ig (cstride 0: shared)
+  int u0, c0, cstride, head, rec; // offsets in doubles; cell block of gas ig at c0 + cstride*ig (cstride 0: shared)
 };
 __host__ __device__ inline LosLayout make_los_layout(int ng, int nw, int fast, int shared_cell) {
   LosLayout L;
@@ -94,12 +97,12 @@ __host__ __device__ inline LosLayout make_los_layout(int ng, int nw, int fast, i
   L.u0 = 4 + nw;
   L.c0 = L.u0 + ng;
   L.cstride = (fast && !shared_cell) ? 4 : 0;
-  L.z0 = L.c0 + (fast ? (shared_cell ? 4 : 4 * ng) : 0);
-  L.z0 = (L.z0 + 1) & ~1;       // 16-byte multiples: the head of a record is moved by TMA bulk copies
-  L.head = L.z0;
-  L.rec = L.z0 + 6;
+  L.head = L.c0 + (fast ? (shared_cell ? 4 : 4 * ng) : 0);
+  L.head = (L.head + 1) & ~1;       // 16-byte multiples
+  L.rec = L.head;
   return L;
 }
+constexpr int kRaw = 8, kRawTail = 2; // doubles per raw point; offset of the tail in it
 enum LosTail { LT_Z = 0, LT_DSRAW = 1, LT_LEVEL = 2, LT_X = 3 };
 // column descriptor {first bracket, nu}: top bit of nu marks a column that is not monotone in u or eps; its lookups use the
 // reference's plain bisection over the whole column instead of the hinted search (whose equivalence needs sorted data)

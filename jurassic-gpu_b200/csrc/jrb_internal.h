@@ -30,7 +30,8 @@ struct TraceArgs {
   double cz, cx;               // influence radii of the 3-D form
   // outputs
   LosLayout los;
-  double *los_data; // [n_rays][NLOS][rec]
+  double *los_data; // [n_rays][NLOS][rec] records (written by los_finalize_kernel)
+  double *raw;      // [n_rays][NLOS][kRaw] raw points (written by the stepping kernels, see jrb_device.cuh)
   int *ray_np;      // [n_rays]
   int *ray_level0;  // [n_rays] first atmosphere level of the ray's profile (relative to its package)
   double *ray_tsurf;

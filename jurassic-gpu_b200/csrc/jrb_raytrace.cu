@@ -111,16 +111,15 @@ __global__ void atm_slopes_kernel(const double *__restrict__ z, const double *__
 // the group; the per-step instruction count drops ~3x and a batch has 8x more warps.  That is what a small batch needs
 // (a single 1088-ray package is 34 warps in the throughput form: one warp per scheduler on 9 SMs, every dependent FP64
 // instruction exposed).  Every evaluation uses the same expressions in both forms: bit-identical results.
-template <int LPR, int MINB = 1>
-__global__ void __launch_bounds__(128, MINB) ray_step_kernel(TraceArgs a) {
+template <int LPR>
+__global__ void __launch_bounds__(128) ray_step_kernel(TraceArgs a) {
   const long long gtid = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   const long long r = gtid / LPR;
   const int role = LPR > 1 ? (int)(threadIdx.x & (LPR - 1)) : 0;                                   // lane within the ray's group
   const unsigned gmask = LPR > 1 ? ((LPR >= 32 ? 0xffffffffu : ((1u << LPR) - 1u)) << ((threadIdx.x & 31) & ~(LPR - 1))) : 0u; // the group's lanes
   if (r >= a.n_rays) return;
 
-  const LosLayout L = a.los;
-  double *__restrict__ rec0 = a.los_data + (size_t)r * kNLOS * L.rec;
+  double *__restrict__ raw0 = a.raw + (size_t)r * kNLOS * kRaw; // this ray's raw points
 
   const int pk = a.ray_pkg[r];
   const long long abase = a.pkg_atm_off[pk];
@@ -206,7 +205,7 @@ __global__ void __launch_bounds__(128, MINB) ray_step_kernel(TraceArgs a) {
         const double frac = (zfrac - zprev) / (z - zprev);
         for (int i = 0; i < 3; i++) x[i] = xprev[i] + frac * (x[i] - xprev[i]);
         z = norm3(x) - kRE;
-        if (role == 0) rec0[(size_t)(np - 1) * L.rec + L.z0 + LT_DSRAW] = ds * frac;
+        if (role == 0) raw0[(size_t)(np - 1) * kRaw + kRawTail + LT_DSRAW] = ds * frac;
         ds = 0.0;
       }
       double nref = 1.0, ngr[3] = {0.0, 0.0, 0.0};
@@ -239,12 +238,10 @@ __global__ void __launch_bounds__(128, MINB) ray_step_kernel(TraceArgs a) {
           ngr[0] = (g0 - n2) * (1.0 / h); ngr[1] = (g1 - n2) * (1.0 / h); ngr[2] = (g2 - n2) * (1.0 / h);
         }
       }
-      if (role == 0) {
-        double *__restrict__ rec = rec0 + (size_t)np * L.rec;
-        rec[0] = p; rec[1] = t;
-        double *__restrict__ tail = rec + L.z0;
-        tail[LT_Z] = z; tail[LT_DSRAW] = ds; tail[LT_LEVEL] = (double)level;
-        tail[LT_X] = x[0]; tail[LT_X + 1] = x[1]; tail[LT_X + 2] = x[2];
+      if (role == 0) { // one 64-byte raw point: {p, t, z, ds} {level, x, y, z}
+        double4 *__restrict__ pt = reinterpret_cast<double4 *>(raw0 + (size_t)np * kRaw);
+        pt[0] = make_double4(p, t, z, ds);
+        pt[1] = make_double4((double)level, x[0], x[1], x[2]);
       }
       for (int i = 0; i < 3; i++) xprev[i] = x[i];
       zprev = z;
@@ -292,11 +289,11 @@ __global__ void __launch_bounds__(128, MINB) ray_step_kernel(TraceArgs a) {
   if (np > 0) {
     const int ip = z_low_idx;
     if (ip <= 0 || ip >= np - 1) { // nadir or zenith: last point
-      const double *tl = rec0 + (size_t)(np - 1) * L.rec + L.z0;
+      const double *tl = raw0 + (size_t)(np - 1) * kRaw + kRawTail;
       tpz = tl[LT_Z];
       cart_to_lonlat(tl + LT_X, &tplon, &tplat);
     } else {
-      const double *t0 = rec0 + (size_t)(ip - 1) * L.rec + L.z0, *t1 = t0 + L.rec, *t2 = t1 + L.rec;
+      const double *t0 = raw0 + (size_t)(ip - 1) * kRaw + kRawTail, *t1 = t0 + kRaw, *t2 = t1 + kRaw;
       const double yy0 = t0[LT_Z], yy1 = t1[LT_Z], yy2 = t2[LT_Z];
       const double ds0 = t1[LT_DSRAW], ds1 = t2[LT_DSRAW];
       const double dyy10 = yy1 - yy0, dyy21 = yy2 - yy1;
@@ -455,6 +452,7 @@ __global__ void __launch_bounds__(128) ray_geo_kernel(TraceArgs a) {
   if (r >= a.n_rays) return;
   const LosLayout L = a.los;
   double *__restrict__ rec0 = a.los_data + (size_t)r * kNLOS * L.rec;
+  double *__restrict__ raw0 = a.raw + (size_t)r * kNLOS * kRaw;
   const int pk = a.ray_pkg[r];
   const long long abase = a.pkg_atm_off[pk];
   const int anp = a.pkg_atm_np[pk];
@@ -529,18 +527,17 @@ __global__ void __launch_bounds__(128) ray_geo_kernel(TraceArgs a) {
         const double frac = (zfrac - zprev) / (z - zprev);
         for (int i = 0; i < 3; i++) x[i] = xprev[i] + frac * (x[i] - xprev[i]);
         cart_to_geo(x, &z, &lon, &lat);
-        rec0[(size_t)(np - 1) * L.rec + L.z0 + LT_DSRAW] = ds * frac;
+        raw0[(size_t)(np - 1) * kRaw + kRawTail + LT_DSRAW] = ds * frac;
         ds = 0.0;
       }
       G.eval(z, lon, lat, &p, &t, q, k, true);
       {
-        double *__restrict__ rec = rec0 + (size_t)np * L.rec;
-        rec[0] = p; rec[1] = t;
+        double *__restrict__ rec = rec0 + (size_t)np * L.rec; // extinction and vmr go straight into the record
         for (int iw = 0; iw < L.nw; iw++) rec[4 + iw] = k[iw];
         for (int ig = 0; ig < L.ng; ig++) rec[L.u0 + ig] = q[ig];
-        double *__restrict__ tail = rec + L.z0;
-        tail[LT_Z] = z; tail[LT_DSRAW] = ds; tail[LT_LEVEL] = 0.0;
-        tail[LT_X] = x[0]; tail[LT_X + 1] = x[1]; tail[LT_X + 2] = x[2];
+        double4 *__restrict__ pt = reinterpret_cast<double4 *>(raw0 + (size_t)np * kRaw);
+        pt[0] = make_double4(p, t, z, ds);
+        pt[1] = make_double4(0.0, x[0], x[1], x[2]);
       }
       for (int i = 0; i < 3; i++) xprev[i] = x[i];
       zprev = z;
@@ -578,11 +575,11 @@ __global__ void __launch_bounds__(128) ray_geo_kernel(TraceArgs a) {
   if (np > 0) { // tangent point (:502-539)
     const int ip = z_low_idx;
     if (ip <= 0 || ip >= np - 1) {
-      const double *tl = rec0 + (size_t)(np - 1) * L.rec + L.z0;
+      const double *tl = raw0 + (size_t)(np - 1) * kRaw + kRawTail;
       tpz = tl[LT_Z];
       cart_to_lonlat(tl + LT_X, &tplon, &tplat);
     } else {
-      const double *t0 = rec0 + (size_t)(ip - 1) * L.rec + L.z0, *t1 = t0 + L.rec, *t2 = t1 + L.rec;
+      const double *t0 = raw0 + (size_t)(ip - 1) * kRaw + kRawTail, *t1 = t0 + kRaw, *t2 = t1 + kRaw;
       const double yy0 = t0[LT_Z], yy1 = t1[LT_Z], yy2 = t2[LT_Z], ds0 = t1[LT_DSRAW], ds1 = t2[LT_DSRAW];
       const double dyy10 = yy1 - yy0, dyy21 = yy2 - yy1, x1 = sqrt(ds0 * ds0 - dyy10 * dyy10),
                    x2 = x1 + sqrt(ds1 * ds1 - dyy21 * dyy21), dx12 = x1 - x2,
@@ -612,12 +609,13 @@ __global__ void __launch_bounds__(256) los_finalize_kernel(TraceArgs a) {
   if (ip >= np) return;
   const LosLayout L = a.los;
   double *__restrict__ rec = a.los_data + ((size_t)r * kNLOS + ip) * L.rec;
-  const double *__restrict__ tail = rec + L.z0;
-  const double p = rec[0], t = rec[1], z = tail[LT_Z];
+  const double *__restrict__ pt = a.raw + ((size_t)r * kNLOS + ip) * kRaw;
+  const double *__restrict__ tail = pt + kRawTail;
+  const double p = pt[0], t = pt[1], z = tail[LT_Z];
   // trapezoid rule on the raw step lengths (:437-443)
   const double ds_raw = tail[LT_DSRAW];
-  const double ds = (ip == 0) ? 0.5 * ds_raw : 0.5 * (tail[LT_DSRAW - L.rec] + ds_raw);
-  rec[2] = ds;
+  const double ds = (ip == 0) ? 0.5 * ds_raw : 0.5 * (tail[LT_DSRAW - kRaw] + ds_raw);
+  rec[0] = p; rec[1] = t; rec[2] = ds;
   const double dens = 10. * p / (kBoltzmann * t) * ds; // column density per unit vmr (:446-453)
   double qh2o = 0.0;
   if (a.ip != 1) { // 2-D / 3-D atmosphere: ray_geo_kernel stored extinction and vmr of the point
@@ -694,8 +692,6 @@ cudaError_t launch_raytrace(const TraceArgs &a, cudaStream_t stream, int *launch
   const bool coop = !a.small_blocks && a.n_rays <= 16384 && !getenv("JRB_NO_COOP_TRACER");
   if (a.ip != 1) ray_geo_kernel<<<(unsigned)((a.n_rays + bs - 1) / bs), bs, 0, stream>>>(a);
   else if (coop) ray_step_kernel<8><<<(unsigned)((a.n_rays * 8 + 127) / 128), 128, 0, stream>>>(a);
-  else if (const char *o = getenv("JRB_TRACER_OCC"); o && atoi(o) == 6) ray_step_kernel<1, 6><<<(unsigned)((a.n_rays + bs - 1) / bs), bs, 0, stream>>>(a);
-  else if (o && atoi(o) == 5) ray_step_kernel<1, 5><<<(unsigned)((a.n_rays + bs - 1) / bs), bs, 0, stream>>>(a);
   else ray_step_kernel<1><<<(unsigned)((a.n_rays + bs - 1) / bs), bs, 0, stream>>>(a);
   const long long n = a.n_rays * kNLOS;
   los_finalize_kernel<<<(unsigned)((n + bf - 1) / bf), bf, 0, stream>>>(a);

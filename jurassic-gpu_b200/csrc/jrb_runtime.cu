@@ -805,7 +805,8 @@ static int stage_locked(jrb_context *ctx, int npk, const jrb_atm_view *atm, cons
   ctx->blocks_per_group = bpg;
   // scratch per ray: the line-of-sight records, plus the per-segment block products in split mode
   const size_t part_per_ray = ctx->n_gas_blocks > 1 ? (size_t)ctx->n_gas_blocks * ((size_t)kNLOS * nd * 8 + (size_t)nd * 4) + (size_t)kNLOS * nd * 16 : 0;
-  const size_t per_ray = (size_t)kNLOS * ctx->los.rec * 8 + part_per_ray;
+  // (records + the raw points the stepping kernels write, jrb_device.cuh)
+  const size_t per_ray = (size_t)kNLOS * (ctx->los.rec + kRaw) * 8 + part_per_ray;
   // LOS scratch: JRB_LOS_GB / jrb_set_los_limit_gb (default 72 GB: the 1 000 960 rays of BASELINE's config D need 64 GB),
   // but never more than half of what is free on the device.  The driver is only asked (cudaMemGetInfo takes a
   // device-wide lock and was seen to stall for tens of ms) when the buffer has to grow.
@@ -921,7 +922,7 @@ static int run_locked(jrb_context *ctx) {
   const size_t need_ev = 2 + 4 * (size_t)nchunks;
   while (ctx->events.size() < need_ev) { cudaEvent_t ev; CU(cudaEventCreate(&ev)); ctx->events.push_back(ev); }
   auto EV = [&](long long c, int k) { return ctx->events[2 + 4 * (size_t)c + k]; };
-  const size_t per_ray = (size_t)kNLOS * ctx->los.rec;
+  const size_t per_ray = (size_t)kNLOS * ctx->los.rec, per_ray_raw = (size_t)kNLOS * kRaw;
   long long launches = 0;
   int ngb = ng;
   cudaStream_t st_tr = pipe ? ctx->s_trace : ctx->stream;
@@ -930,7 +931,9 @@ static int run_locked(jrb_context *ctx) {
   if (ctx->use_fast && nchunks > 0) CU(cudaMemsetAsync(ctx->d_counter.p, 0, (size_t)nchunks * 32, st_tr));
   for (long long c = 0; c < nchunks; c++) {
     const long long r0 = c * ctx->chunk_rays, r1 = std::min(R, r0 + ctx->chunk_rays);
-    double *los_buf = (double *)ctx->d_los.p + (size_t)(c % ctx->nbuf) * (size_t)ctx->chunk_rays * per_ray;
+    // buffer of the chunk: [chunk_rays] records, then [chunk_rays] raw points
+    double *los_buf = (double *)ctx->d_los.p + (size_t)(c % ctx->nbuf) * (size_t)ctx->chunk_rays * (per_ray + per_ray_raw);
+    double *raw_buf = los_buf + (size_t)ctx->chunk_rays * per_ray;
     cudaStream_t st_e = pipe ? ctx->s_ega[c & 1] : ctx->stream;
     TraceArgs t;
     t.n_rays = r1 - r0;
@@ -946,7 +949,7 @@ static int run_locked(jrb_context *ctx) {
     t.ip = ctx->ip; t.cz = ctx->cz; t.cx = ctx->cx;
     t.refrac = ctx->refrac; t.ig_h2o = (ctx->ctm_mask & 4) ? ctx->ig_h2o : -1;
     t.rayds = ctx->rayds; t.raydz = ctx->raydz;
-    t.los = ctx->los; t.los_data = los_buf;
+    t.los = ctx->los; t.los_data = los_buf; t.raw = raw_buf;
     t.ray_np = (int *)ctx->d_np.p + r0; t.ray_tsurf = (double *)ctx->d_tsurf.p + r0;
     t.ray_level0 = (int *)ctx->d_level0.p + r0;
     t.tp = ctx->o_tp + r0;
@@ -1208,19 +1211,30 @@ int jrb_debug_los(jrb_context *ctx, long long ray, double *out, int max_doubles,
   const long long nchunks = (ctx->n_rays + ctx->chunk_rays - 1) / ctx->chunk_rays;
   const long long c = ray / ctx->chunk_rays;
   if (c < nchunks - ctx->nbuf) return ctx->fail(JRB_ERR_STATE, "LOS of this ray was overwritten by a later chunk");
-  const size_t per_ray = (size_t)kNLOS * ctx->los.rec;
-  const double *src = (const double *)ctx->d_los.p + (size_t)(c % ctx->nbuf) * (size_t)ctx->chunk_rays * per_ray +
-                      (size_t)(ray - c * ctx->chunk_rays) * per_ray;
+  const size_t per_ray = (size_t)kNLOS * ctx->los.rec, per_ray_raw = (size_t)kNLOS * kRaw;
+  const double *buf = (const double *)ctx->d_los.p + (size_t)(c % ctx->nbuf) * (size_t)ctx->chunk_rays * (per_ray + per_ray_raw);
+  const double *src = buf + (size_t)(ray - c * ctx->chunk_rays) * per_ray;
+  const double *src_raw = buf + (size_t)ctx->chunk_rays * per_ray + (size_t)(ray - c * ctx->chunk_rays) * per_ray_raw;
   CU(cudaSetDevice(ctx->device));
   int np = 0;
   CU(cudaMemcpy(&np, (int *)ctx->d_np.p + ray, 4, cudaMemcpyDeviceToHost));
   if (tsurf_out) CU(cudaMemcpy(tsurf_out, (double *)ctx->d_tsurf.p + ray, 8, cudaMemcpyDeviceToHost));
   if (np_out) *np_out = np;
-  if (rec_doubles) *rec_doubles = ctx->los.rec;
-  const size_t n = (size_t)np * ctx->los.rec;
+  // a point as reported: the record, then the tail of its raw point (altitude, raw step length, level, Cartesian position)
+  const int rec = ctx->los.rec, out_rec = rec + (kRaw - kRawTail);
+  if (rec_doubles) *rec_doubles = out_rec;
+  const size_t n = (size_t)np * out_rec;
   if (out) {
     if ((size_t)max_doubles < n) return ctx->fail(JRB_ERR_ARG, "output buffer too small");
-    CU(cudaMemcpy(out, src, n * 8, cudaMemcpyDeviceToHost));
+    std::vector<double> hr((size_t)np * rec), hw((size_t)np * kRaw);
+    if (np > 0) {
+      CU(cudaMemcpy(hr.data(), src, hr.size() * 8, cudaMemcpyDeviceToHost));
+      CU(cudaMemcpy(hw.data(), src_raw, hw.size() * 8, cudaMemcpyDeviceToHost));
+    }
+    for (int i = 0; i < np; i++) {
+      std::copy(hr.begin() + (size_t)i * rec, hr.begin() + (size_t)(i + 1) * rec, out + (size_t)i * out_rec);
+      std::copy(hw.begin() + (size_t)i * kRaw + kRawTail, hw.begin() + (size_t)(i + 1) * kRaw, out + (size_t)i * out_rec + rec);
+    }
   }
   return JRB_OK;
 }
