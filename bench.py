@@ -69,7 +69,7 @@ def config_dict(args, workload, world):
     total = args.packages if (workload == args.config and args.packages > 0) else W["packages"]
     return {"workload": W["name"] if total == W["packages"] else W["name"] + f" -- REDUCED to {total} packages",
             "packages_total": total, "rays_total": total * 1088, "channels": W["dims"][0], "gases": W["dims"][1],
-            "l2_policy": "inputs larger than L2 (line-of-sight records rewritten every step, 64 KB per ray; tables 0.2-1.3 GB)",
+            "l2_policy": "inputs larger than L2 (line-of-sight scratch rewritten every step, 70 KB per ray; tables 0.2-1.3 GB)",
             "parallelism": f"contiguous package slices over {world} GPU(s), one process per GPU, tables broadcast once by NCCL inside the library"}
 
 
