@@ -295,6 +295,25 @@ def test_intpol_atm_geo_restatement_equals_reference(jr, oracle, refdrv, ip):
     assert n_nan >= 1 if ip == 3 else n_nan == (1 if ip == 2 else 0)
 
 
+@pytest.mark.parametrize("ip", [1, 2, 3])
+def test_intpol_atm_geo_golden(jr, oracle, ip):
+    """the same against committed known answers of the reference (tests/golden/intpol_geo.json, generated from oracle/_ref by
+    tests/golden/make_golden_intpol.py) -- runs where the reference build is absent"""
+    import json
+    import sys
+    sys.path.insert(0, os.path.join(ROOT, "tests", "golden"))
+    import make_golden_intpol as g
+    gold = json.load(open(os.path.join(ROOT, "tests", "golden", "intpol_geo.json")))["cases"][str(ip)]
+    ctl, pkg = g.case(jr, ip)
+    assert len(gold) == 66
+    for row in gold:
+        z, lon, lat = (float.fromhex(row[k]) for k in ("z", "lon", "lat"))
+        want = np.array([float.fromhex(x) for x in row["out"]])
+        rc, got = oracle.intpol_atm_geo(ctl, pkg, z, lon, lat)
+        assert rc == 0
+        _same(got, want, f"golden ip={ip} at z={z} lon={lon} lat={lat}")
+
+
 def test_intpol_2d_fatal_conditions(jr, oracle):
     """profile list checks of intpol_atm_2d (src/jurassic.c:727-728) -- the reference exits there"""
     ctl, pkg = _track_case(jr, 2)
