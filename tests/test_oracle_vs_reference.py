@@ -33,6 +33,23 @@ def test_oracle_tangent_points_match_golden_rad_org(jr, oracle, case):
     assert np.all(np.abs(gold[:, 8] - pkg.tplon) < 2e-6), "tangent longitude (round-off level values)"
 
 
+@pytest.mark.parametrize("case", ["limb", "nadir"])
+def test_oracle_against_golden_reference_outputs(jr, oracle, case):
+    """rad / tau / tangent point of the reference's two examples as the reference itself computed them with the synthetic
+    tables (tests/golden/formod_examples.json, generated from oracle/_ref by tests/golden/make_golden_formod.py)"""
+    import json
+    import sys
+    sys.path.insert(0, os.path.join(ROOT, "tests", "golden"))
+    import make_golden_formod as g
+    gold = json.load(open(os.path.join(ROOT, "tests", "golden", "formod_examples.json")))["cases"][case]
+    ctl, tbl, pkg = g.setup(jr, case)
+    oracle.formod(ctl, tbl, pkg)
+    for name in ("rad", "tau", "tpz", "tplon", "tplat"):
+        want = np.array([float.fromhex(x) for x in gold[name]]).reshape(getattr(pkg, name).shape)
+        got = getattr(pkg, name)
+        assert np.allclose(got, want, rtol=1e-12, atol=1e-300 if name in ("rad", "tau") else 1e-12), name
+
+
 # ---- 2. the reference itself ---------------------------------------------------------------------------------------
 def _ref_run(refdrv, ND, NG, ctl, tbl, pkg):
     ref = refdrv.Reference(ND, NG)
