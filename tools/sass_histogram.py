@@ -16,7 +16,7 @@ WANT = [("ega_tiled_kernel<12,0,0>  (Config D: CO2+H2O continua, segment-tiled, 
         ("ega_fast_kernel<0,1,0,1,0>   (gas-block pass, several rays per warp)", "ega_fast_kernelILi0ELb1ELb0ELb1ELb0EE"),
         ("ega_fast_kernel<12,0,1,0,1>  (channel-dependent axes)", "ega_fast_kernelILi12ELb0ELb1ELb0ELb1EE"),
         ("ega_combine_kernel", "ega_combine_kernel"), ("ega_segment_kernel", "ega_segment_kernel"),
-        ("ray_step_kernel<1>  (thread per ray)", "ray_step_kernelILi1EE"), ("ray_step_kernel<8>  (8 lanes per ray)", "ray_step_kernelILi8EE"), ("los_finalize_kernel", "los_finalize_kernel"), ("stage_kernel", "stage_kernel")]
+        ("ray_step_kernel<1>  (thread per ray)", "ray_step_kernelILi1EE"), ("ray_step_kernel<8>  (8 lanes per ray)", "ray_step_kernelILi8EE"), ("ray_geo_kernel  (2-D / 3-D atmospheres)", "ray_geo_kernel"), ("los_finalize_kernel", "los_finalize_kernel"), ("stage_kernel", "stage_kernel")]
 KEYS = ["UBLKCP", "SYNCS", "LDG", "LDS", "STS", "STG", "DFMA", "DMUL", "DADD", "DSETP", "F2F", "MUFU", "FSETP", "IMAD", "SHFL", "BAR", "BRA", "ATOM"]
 
 out = subprocess.run(["cuobjdump", "-sass", LIB], capture_output=True, text=True).stdout
